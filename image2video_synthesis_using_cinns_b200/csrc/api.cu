@@ -1,0 +1,604 @@
+// C-ABI (include/i2v_b200.h) + host-side orchestration of the four networks of the sampling path.
+// The host code only sequences kernel launches on the caller's stream inside the caller's workspace;
+// it never allocates device memory and never synchronises.
+#include <algorithm>
+#include <cstdarg>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/i2v_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace i2v {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+namespace {
+
+struct TensorTable {
+    std::unordered_map<std::string, std::pair<const void*, size_t>> t;
+    int set(const char* name, const void* p, size_t nbytes) {
+        I2V_REQUIRE(name != nullptr && p != nullptr, "set_tensor: null name or pointer");
+        I2V_REQUIRE((reinterpret_cast<uintptr_t>(p) & 15) == 0, "set_tensor(%s): pointer not 16-byte aligned", name);
+        t[name] = {p, nbytes};
+        return 0;
+    }
+    bool has(const std::string& name) const { return t.count(name) != 0; }
+    // returns nullptr (and sets the error) when missing or of the wrong size
+    template <class T = float>
+    const T* get(const std::string& name, size_t elems) const {
+        auto it = t.find(name);
+        if (it == t.end()) { set_error("tensor '%s' was not registered", name.c_str()); return nullptr; }
+        if (it->second.second != elems * sizeof(T)) {
+            set_error("tensor '%s': %zu bytes registered, %zu expected", name.c_str(), it->second.second, elems * sizeof(T));
+            return nullptr;
+        }
+        return static_cast<const T*>(it->second.first);
+    }
+};
+
+// Bump allocator over the caller's workspace; in dry mode it only measures.
+struct Arena {
+    char* base; size_t cap; size_t off = 0; size_t peak = 0; bool dry;
+    Arena(void* b, size_t c, bool d) : base(static_cast<char*>(b)), cap(c), dry(d) {}
+    template <class T> T* take(size_t n) {
+        off = (off + 255) & ~(size_t)255;
+        T* p = dry ? reinterpret_cast<T*>(static_cast<uintptr_t>(256)) : reinterpret_cast<T*>(base + off);
+        off += n * sizeof(T);
+        if (off > peak) peak = off;
+        return p;
+    }
+    bool ok() const { return dry || off <= cap; }
+};
+
+#define I2V_TRY(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
+#define I2V_PTR(var, expr) auto var = (expr); if (!dry && var == nullptr) return -3
+
+// conv helper (stride-1 'same' or general), channels-last
+int conv(int engine, const float* x, const float* w, const float* bias, const float* res, float* y, int B, int Ti, int Hi,
+         int Wi, int Cin, int Cout, int kt, int kh, int kw, int st, int sh, int sw, int pt, int ph, int pw, int rut, int ruh,
+         int ruw, int act, int out_mode, cudaStream_t s) {
+    ConvArgs a;
+    a.x = x; a.w = w; a.bias = bias; a.res = res; a.y = y;
+    a.B = B; a.Ti = Ti; a.Hi = Hi; a.Wi = Wi; a.Cin = Cin;
+    a.To = (Ti + 2 * pt - kt) / st + 1; a.Ho = (Hi + 2 * ph - kh) / sh + 1; a.Wo = (Wi + 2 * pw - kw) / sw + 1;
+    a.Cout = Cout; a.kt = kt; a.kh = kh; a.kw = kw; a.st = st; a.sh = sh; a.sw = sw; a.pt = pt; a.ph = ph; a.pw = pw;
+    a.res_ut = rut; a.res_uh = ruh; a.res_uw = ruw; a.act = act; a.out_mode = out_mode;
+    (void)engine;
+    return launch_conv_simt(a, s);
+}
+
+int modulate(const float* x, const float* coef, const float* gb, const float* r, const float* coef2, float* out, int B,
+             int T, int H, int W, int C, int ut, int uh, int uw, int act, cudaStream_t s) {
+    ModArgs m;
+    m.x = x; m.coef = coef; m.gb = gb; m.r = r; m.coef2 = coef2; m.out = out;
+    m.B = B; m.T = T; m.H = H; m.W = W; m.C = C; m.ut = ut; m.uh = uh; m.uw = uw; m.act = act;
+    return launch_modulate(m, s);
+}
+
+}  // namespace
+}  // namespace i2v
+
+using namespace i2v;
+
+// =============================================================================== flow
+struct i2v_flow {
+    int n_flows, d, zc, hidden, depth;
+    std::vector<unsigned char> cond_mode;
+    TensorTable tt;
+};
+
+static int flow_weights(const i2v_flow* h, FlowWeights& fw) {
+    const size_t nf = h->n_flows, H = h->hidden, half = h->d / 2;
+    fw.n_flows = h->n_flows; fw.d = h->d; fw.half = h->d / 2; fw.zc = h->zc; fw.hidden = h->hidden; fw.depth = h->depth;
+    fw.cond_mode = h->cond_mode.data();
+    const bool dry = false;
+    I2V_PTR(w1x, h->tt.get("w1x", nf * 2 * 2 * H * half)); fw.w1x = w1x;
+    I2V_PTR(w1c, h->tt.get("w1c", nf * 2 * 2 * H * h->zc)); fw.w1c = w1c;
+    I2V_PTR(b1, h->tt.get("b1", nf * 2 * 2 * H)); fw.b1 = b1;
+    I2V_PTR(wh, h->tt.get("wh", nf * 2 * h->depth * 2 * H * H)); fw.wh = wh;
+    I2V_PTR(bh, h->tt.get("bh", nf * 2 * h->depth * 2 * H)); fw.bh = bh;
+    I2V_PTR(wo, h->tt.get("wo", nf * 2 * 2 * half * H)); fw.wo = wo;
+    I2V_PTR(bo, h->tt.get("bo", nf * 2 * 2 * half)); fw.bo = bo;
+    I2V_PTR(loc, h->tt.get("loc", nf * h->d)); fw.loc = loc;
+    I2V_PTR(scale, h->tt.get("scale", nf * h->d)); fw.scale = scale;
+    I2V_PTR(pf, h->tt.get<int>("perm_fwd", nf * h->d)); fw.perm_fwd = pf;
+    I2V_PTR(pb, h->tt.get<int>("perm_bwd", nf * h->d)); fw.perm_bwd = pb;
+    return 0;
+}
+
+extern "C" {
+
+int i2v_abi_version(void) { return I2V_ABI_VERSION; }
+const char* i2v_last_error(void) { return i2v::g_err; }
+
+i2v_flow* i2v_flow_create(int n_flows, int d, int zc, int hidden, int depth, const unsigned char* cond_mode) {
+    if (n_flows <= 0 || n_flows > 64 || d <= 0 || d % 2 || zc <= 0 || zc % 4 || hidden <= 0 || hidden % 4 || hidden > 512 ||
+        depth < 0) {
+        set_error("flow_create: unsupported geometry n_flows=%d d=%d zc=%d hidden=%d depth=%d", n_flows, d, zc, hidden, depth);
+        return nullptr;
+    }
+    auto* h = new i2v_flow();
+    h->n_flows = n_flows; h->d = d; h->zc = zc; h->hidden = hidden; h->depth = depth;
+    h->cond_mode.assign(n_flows, 0);
+    if (cond_mode) h->cond_mode.assign(cond_mode, cond_mode + n_flows);
+    return h;
+}
+int i2v_flow_set_tensor(i2v_flow* h, const char* name, const void* p, size_t n) { return h ? h->tt.set(name, p, n) : -1; }
+size_t i2v_flow_workspace_bytes(const i2v_flow* h, int batch) {
+    FlowWeights fw{};
+    fw.n_flows = h->n_flows; fw.d = h->d; fw.half = h->d / 2; fw.zc = h->zc; fw.hidden = h->hidden; fw.depth = h->depth;
+    return flow_workspace_bytes(fw, batch);
+}
+int i2v_flow_reverse(i2v_flow* h, const float* residual, const float* cond, float* z, int batch, void* ws, size_t wsb,
+                     void* stream) {
+    FlowWeights fw{};
+    I2V_TRY(flow_weights(h, fw));
+    return launch_flow(fw, residual, cond, z, nullptr, batch, true, ws, wsb, static_cast<cudaStream_t>(stream));
+}
+int i2v_flow_forward(i2v_flow* h, const float* z, const float* cond, float* out, float* logdet, int batch, void* ws,
+                     size_t wsb, void* stream) {
+    FlowWeights fw{};
+    I2V_TRY(flow_weights(h, fw));
+    return launch_flow(fw, z, cond, out, logdet, batch, false, ws, wsb, static_cast<cudaStream_t>(stream));
+}
+void i2v_flow_destroy(i2v_flow* h) { delete h; }
+
+}  // extern "C"
+
+// =============================================================================== embedder
+struct i2v_embedder {
+    int zc, norm_mode;
+    TensorTable tt;
+};
+
+// ResNet-50 v1.5 trunk on channels-last tensors (AE.py:131-141).  norm_mode 0: every conv is followed
+// by InstanceNorm2d(affine=False) -> statistics pass + fused normalise/ReLU(/residual) pass;
+// norm_mode 1: BatchNorm (eval) was folded into conv weight+bias at load, ReLU/residual ride in the
+// conv epilogue.
+static int embedder_run(const i2v_embedder* m, const float* x0, float* embed, int B, int H, int W, Arena& ar,
+                        cudaStream_t s, bool dry) {
+    const bool inorm = m->norm_mode == 0;
+    const int H1 = (H + 6 - 7) / 2 + 1, W1 = (W + 6 - 7) / 2 + 1;          // conv1 7x7 s2 p3
+    const int H2 = (H1 + 2 - 3) / 2 + 1, W2 = (W1 + 2 - 3) / 2 + 1;        // maxpool 3x3 s2 p1
+    const size_t act_max = (size_t)B * H1 * W1 * 64;                       // == B*H2*W2*256, the largest activation
+    float* xin = ar.take<float>((size_t)B * H * W * 3);
+    float* buf[5];
+    for (auto& b : buf) b = ar.take<float>(act_max);
+    double* sums = ar.take<double>((size_t)B * 2048 * 2);
+    double* sums2 = ar.take<double>((size_t)B * 2048 * 2);
+    float* coef = ar.take<float>((size_t)B * 2048 * 2);
+    float* coef2 = ar.take<float>((size_t)B * 2048 * 2);
+    float* pooled = ar.take<float>((size_t)B * 2048);
+    if (!ar.ok()) { set_error("embedder: workspace too small (%zu needed, %zu given)", ar.peak, ar.cap); return -4; }
+    if (dry) return 0;
+
+    auto W_ = [&](const std::string& n, size_t e) { return m->tt.get(n, e); };
+    auto Bv = [&](const std::string& n, size_t e) -> const float* { return inorm ? nullptr : m->tt.get(n, e); };
+    // conv (+ IN + ReLU) : in -> out ; raw conv output goes through `tmp` when instance-normalised
+    auto conv_norm_relu = [&](const std::string& name, const float* in, float* tmp, float* out, int Hi, int Wi, int Cin,
+                              int Cout, int k, int stride, int pad, int relu) -> int {
+        const float* w = W_(name + ".w", (size_t)k * k * Cout * Cin);
+        if (!w) return -3;
+        const int Ho = (Hi + 2 * pad - k) / stride + 1, Wo = (Wi + 2 * pad - k) / stride + 1;
+        if (inorm) {
+            I2V_TRY(conv(0, in, w, nullptr, nullptr, tmp, B, 1, Hi, Wi, Cin, Cout, 1, k, k, 1, stride, stride, 0, pad, pad, 1, 1,
+                         1, ACT_NONE, 0, s));
+            I2V_TRY(launch_channel_stats(tmp, sums, B, (long long)Ho * Wo, Cout, s));
+            I2V_TRY(launch_norm_coeffs(sums, coef, B, Cout, (long long)Ho * Wo, 0, 1e-5f, nullptr, nullptr, nullptr, s));
+            I2V_TRY(modulate(tmp, coef, nullptr, nullptr, nullptr, out, B, 1, Ho, Wo, Cout, 1, 1, 1, relu ? ACT_RELU : ACT_NONE, s));
+        } else {
+            const float* b = Bv(name + ".b", Cout);
+            if (!b) return -3;
+            I2V_TRY(conv(0, in, w, b, nullptr, out, B, 1, Hi, Wi, Cin, Cout, 1, k, k, 1, stride, stride, 0, pad, pad, 1, 1, 1,
+                         relu ? ACT_RELU : ACT_NONE, 0, s));
+        }
+        return 0;
+    };
+
+    I2V_TRY(launch_resize_bilinear_nchw_to_nhwc(x0, xin, B, 3, H, W, H, W, s));
+    I2V_TRY(conv_norm_relu("conv1", xin, buf[1], buf[0], H, W, 3, 64, 7, 2, 3, 1));
+    I2V_TRY(launch_maxpool3x3s2(buf[0], buf[1], B, H1, W1, 64, s));
+    float* cur = buf[1];
+    float* t1 = buf[0]; float* t2 = buf[2]; float* t3 = buf[3]; float* t4 = buf[4];
+    int Hc = H2, Wc = W2, Cc = 64;
+    const int nblocks[4] = {3, 4, 6, 3}, planes[4] = {64, 128, 256, 512};
+    for (int li = 0; li < 4; ++li) {
+        for (int bi = 0; bi < nblocks[li]; ++bi) {
+            const std::string p = "layer" + std::to_string(li + 1) + "." + std::to_string(bi) + ".";
+            const int pl = planes[li], stride = (li > 0 && bi == 0) ? 2 : 1;
+            const int Ho = (Hc + 2 - 3) / stride + 1, Wo = (Wc + 2 - 3) / stride + 1;
+            // conv1 1x1 -> t1 ; conv2 3x3 (stride) -> t2
+            I2V_TRY(conv_norm_relu(p + "conv1", cur, t3, t1, Hc, Wc, Cc, pl, 1, 1, 0, 1));
+            I2V_TRY(conv_norm_relu(p + "conv2", t1, t3, t2, Hc, Wc, pl, pl, 3, stride, 1, 1));
+            const float* w3 = W_(p + "conv3.w", (size_t)4 * pl * pl);
+            if (!w3) return -3;
+            if (inorm) {
+                // o3 raw -> t1 ; identity branch raw (downsample conv) -> t3 ; out = relu(IN(o3) + IN(ds) | h) -> t4
+                I2V_TRY(conv(0, t2, w3, nullptr, nullptr, t1, B, 1, Ho, Wo, pl, 4 * pl, 1, 1, 1, 1, 1, 1, 0, 0, 0, 1, 1, 1, ACT_NONE, 0, s));
+                I2V_TRY(launch_channel_stats(t1, sums, B, (long long)Ho * Wo, 4 * pl, s));
+                I2V_TRY(launch_norm_coeffs(sums, coef, B, 4 * pl, (long long)Ho * Wo, 0, 1e-5f, nullptr, nullptr, nullptr, s));
+                const float* idt = cur; const float* c2 = nullptr;
+                if (bi == 0) {
+                    const float* wd = W_(p + "ds.w", (size_t)4 * pl * Cc);
+                    if (!wd) return -3;
+                    I2V_TRY(conv(0, cur, wd, nullptr, nullptr, t3, B, 1, Hc, Wc, Cc, 4 * pl, 1, 1, 1, 1, stride, stride, 0, 0, 0, 1, 1, 1,
+                                 ACT_NONE, 0, s));
+                    I2V_TRY(launch_channel_stats(t3, sums2, B, (long long)Ho * Wo, 4 * pl, s));
+                    I2V_TRY(launch_norm_coeffs(sums2, coef2, B, 4 * pl, (long long)Ho * Wo, 0, 1e-5f, nullptr, nullptr, nullptr, s));
+                    idt = t3; c2 = coef2;
+                }
+                I2V_TRY(modulate(t1, coef, nullptr, idt, c2, t4, B, 1, Ho, Wo, 4 * pl, 1, 1, 1, ACT_RELU, s));
+            } else {
+                const float* b3 = m->tt.get(p + "conv3.b", (size_t)4 * pl);
+                if (!b3) return -3;
+                const float* idt = cur;
+                if (bi == 0) {
+                    const float* wd = W_(p + "ds.w", (size_t)4 * pl * Cc);
+                    const float* bd = m->tt.get(p + "ds.b", (size_t)4 * pl);
+                    if (!wd || !bd) return -3;
+                    I2V_TRY(conv(0, cur, wd, bd, nullptr, t3, B, 1, Hc, Wc, Cc, 4 * pl, 1, 1, 1, 1, stride, stride, 0, 0, 0, 1, 1, 1,
+                                 ACT_NONE, 0, s));
+                    idt = t3;
+                }
+                I2V_TRY(conv(0, t2, w3, b3, idt, t4, B, 1, Ho, Wo, pl, 4 * pl, 1, 1, 1, 1, 1, 1, 0, 0, 0, 1, 1, 1, ACT_RELU, 0, s));
+            }
+            float* old = cur; cur = t4; t4 = old;   // rotate: previous input buffer becomes scratch
+            Hc = Ho; Wc = Wo; Cc = 4 * pl;
+        }
+    }
+    // adaptive average pool -> fc (1x1 conv): only the first zc outputs (the mean) are consumed
+    I2V_TRY(launch_channel_stats(cur, sums, B, (long long)Hc * Wc, Cc, s));
+    I2V_TRY(launch_mean_from_sums(sums, pooled, B, Cc, (long long)Hc * Wc, s));
+    const float* fw = m->tt.get("fc.w", (size_t)m->zc * 2048);
+    const float* fb = m->tt.get("fc.b", (size_t)m->zc);
+    if (!fw || !fb) return -3;
+    I2V_TRY(launch_linear(pooled, fw, fb, embed, B, 2048, m->zc, ACT_NONE, s));
+    return 0;
+}
+
+extern "C" {
+i2v_embedder* i2v_embedder_create(int zc, int norm_mode) {
+    if (zc <= 0 || (norm_mode != 0 && norm_mode != 1)) { set_error("embedder_create: bad arguments"); return nullptr; }
+    auto* h = new i2v_embedder();
+    h->zc = zc; h->norm_mode = norm_mode;
+    return h;
+}
+int i2v_embedder_set_tensor(i2v_embedder* h, const char* n, const void* p, size_t b) { return h ? h->tt.set(n, p, b) : -1; }
+size_t i2v_embedder_workspace_bytes(const i2v_embedder* h, int batch, int height, int width) {
+    Arena ar(nullptr, 0, true);
+    embedder_run(h, nullptr, nullptr, batch, height, width, ar, nullptr, true);
+    return ar.peak + 256;
+}
+int i2v_embedder_forward(i2v_embedder* h, const float* x0, float* embed, int batch, int height, int width, void* ws,
+                         size_t wsb, void* stream) {
+    I2V_REQUIRE(h && x0 && embed && ws, "embedder_forward: null argument");
+    I2V_REQUIRE(batch > 0 && height >= 32 && width >= 32, "embedder_forward: bad shape B=%d H=%d W=%d", batch, height, width);
+    Arena ar(ws, wsb, false);
+    return embedder_run(h, x0, embed, batch, height, width, ar, static_cast<cudaStream_t>(stream), false);
+}
+void i2v_embedder_destroy(i2v_embedder* h) { delete h; }
+}  // extern "C"
+
+// =============================================================================== decoder
+struct i2v_decoder {
+    int nf, z_dim, us[2], ut[2], engine;
+    TensorTable tt;
+};
+
+struct DecBlock { const char* name; int cin, cout, ut, uh, uw; };
+
+static void decoder_blocks(const i2v_decoder* m, DecBlock out[6]) {
+    const int nf = m->nf;
+    const DecBlock b[6] = {{"head_0", 16 * nf, 16 * nf, 1, 1, 1},
+                           {"g_0", 16 * nf, 16 * nf, 2, 2, 2},
+                           {"g_1", 16 * nf, 8 * nf, 2, 2, 2},
+                           {"g_2", 8 * nf, 4 * nf, 2, 2, 2},
+                           {"g_3", 4 * nf, 2 * nf, m->ut[0], m->us[0], m->us[0]},
+                           {"g_4", 2 * nf, 1 * nf, m->ut[1], m->us[1], m->us[1]}};
+    for (int i = 0; i < 6; ++i) out[i] = b[i];
+}
+
+// Generator.forward (decoder.py:97-120) on channels-last tensors.  Per GeneratorBlock (decoder.py:33-49):
+//   stats(x)                       one pass over the PRE-upsample tensor (GroupNorm statistics are
+//                                  invariant under nearest upsampling)
+//   gb   = SPADE maps              bilinear(img) -> conv3x3+lrelu -> conv3x3 to (gamma|beta), 2-D only
+//   a0   = lrelu(GN(x)*(1+g)+b)    fused modulate pass, reads x through the upsample index map
+//   dx   = conv_0(a0)+bias
+//   a1   = lrelu(AdaIN(dx, z))     stats(dx) + Linear(z) + fused modulate pass
+//   xs   = conv_s(GN_affine(x))    at the PRE-upsample resolution (1x1x1 conv commutes with nearest
+//                                  upsampling) or x itself
+//   out  = conv_1(a1)+bias+up(xs)  residual read through the upsample map in the conv epilogue
+static int decoder_run(const i2v_decoder* m, const float* img, const float* z, float* frames, int B, int H, int W,
+                       Arena& ar, cudaStream_t s, bool dry) {
+    DecBlock blk[6];
+    decoder_blocks(m, blk);
+    const int zd = m->z_dim;
+    // geometry walk
+    int T = 1, Hc = 4, Wc = 4;
+    size_t max_out = (size_t)B * 16 * blk[0].cin, max_p = 0, max_d = 0, max_gb = 0, max_sh = 0, max_low_in = 0, max_low_out = 0;
+    int cmax = 0;
+    for (int i = 0; i < 6; ++i) {
+        const size_t low = (size_t)B * T * Hc * Wc;
+        T *= blk[i].ut; Hc *= blk[i].uh; Wc *= blk[i].uw;
+        const size_t vox = (size_t)B * T * Hc * Wc;
+        const int cmid = blk[i].cin < blk[i].cout ? blk[i].cin : blk[i].cout;
+        max_out = std::max(max_out, vox * blk[i].cout);
+        max_p = std::max(max_p, vox * blk[i].cin);
+        max_d = std::max(max_d, vox * cmid);
+        max_gb = std::max(max_gb, (size_t)B * Hc * Wc * 2 * blk[i].cin);
+        max_sh = std::max(max_sh, (size_t)B * Hc * Wc * 128);
+        if (blk[i].cin != blk[i].cout) {
+            max_low_in = std::max(max_low_in, low * blk[i].cin);
+            max_low_out = std::max(max_low_out, low * blk[i].cout);
+        }
+        cmax = std::max(cmax, blk[i].cin);
+    }
+    I2V_REQUIRE(Hc == H && Wc == W, "decoder: geometry yields %dx%d frames, caller asked for %dx%d", Hc, Wc, H, W);
+    const int Tout = T;
+
+    float* xa = ar.take<float>(max_out);
+    float* xb = ar.take<float>(max_out);
+    float* bufp = ar.take<float>(std::max(max_p, (size_t)B * Tout * H * W * m->nf));
+    float* bufd = ar.take<float>(max_d);
+    float* gb = ar.take<float>(max_gb);
+    float* sh = ar.take<float>(max_sh);
+    float* imgr = ar.take<float>((size_t)B * H * W * 3);
+    float* lowin = ar.take<float>(max_low_in);
+    float* lowout = ar.take<float>(max_low_out);
+    double* sums = ar.take<double>((size_t)B * cmax * 2);
+    float* coef = ar.take<float>((size_t)B * cmax * 2);
+    float* coefs = ar.take<float>((size_t)B * cmax * 2);
+    float* mod = ar.take<float>((size_t)B * 2 * cmax);
+    if (!ar.ok()) { set_error("decoder: workspace too small (%zu needed, %zu given)", ar.peak, ar.cap); return -4; }
+    if (dry) return 0;
+
+    const int eng = m->engine;
+    auto G = [&](const std::string& n, size_t e) { return m->tt.get(n, e); };
+
+    // fc: rows pre-permuted at load so the output is already [B,1,4,4,C] channels-last
+    const int C0 = blk[0].cin;
+    I2V_PTR(fcw, G("fc.w", (size_t)16 * C0 * zd));
+    I2V_PTR(fcb, G("fc.b", (size_t)16 * C0));
+    I2V_TRY(launch_linear(z, fcw, fcb, xa, B, zd, 16 * C0, ACT_NONE, s));
+
+    float* x = xa; float* xn = xb;
+    T = 1; Hc = 4; Wc = 4;
+    for (int i = 0; i < 6; ++i) {
+        const DecBlock& k = blk[i];
+        const std::string nm = k.name;
+        const int cin = k.cin, cout = k.cout, cmid = cin < cout ? cin : cout;
+        const int Tl = T, Hl = Hc, Wl = Wc;
+        T *= k.ut; Hc *= k.uh; Wc *= k.uw;
+        const long long vlow = (long long)Tl * Hl * Wl, vhi = (long long)T * Hc * Wc;
+
+        // statistics of the block input (pre-upsample)
+        I2V_TRY(launch_channel_stats(x, sums, B, vlow, cin, s));
+        // SPADE maps (normalization_layer.py:20-23)
+        I2V_PTR(scw, G(nm + ".spade.conv.w", (size_t)9 * 128 * 3));
+        I2V_PTR(scb, G(nm + ".spade.conv.b", 128));
+        I2V_PTR(sgw, G(nm + ".spade.gb.w", (size_t)9 * 2 * cin * 128));
+        I2V_PTR(sgb, G(nm + ".spade.gb.b", (size_t)2 * cin));
+        I2V_TRY(launch_resize_bilinear_nchw_to_nhwc(img, imgr, B, 3, H, W, Hc, Wc, s));
+        I2V_TRY(conv(0, imgr, scw, scb, nullptr, sh, B, 1, Hc, Wc, 3, 128, 1, 3, 3, 1, 1, 1, 0, 1, 1, 1, 1, 1, ACT_LRELU02, 0, s));
+        I2V_TRY(conv(eng, sh, sgw, sgb, nullptr, gb, B, 1, Hc, Wc, 128, 2 * cin, 1, 3, 3, 1, 1, 1, 0, 1, 1, 1, 1, 1, ACT_NONE, 0, s));
+        // a0 = lrelu(GN16(x) * (1+gamma) + beta), upsampled on the fly
+        int groups = 16;
+        while (cin % groups) --groups;
+        I2V_TRY(launch_norm_coeffs(sums, coef, B, cin, vlow, groups, 1e-5f, nullptr, nullptr, nullptr, s));
+        I2V_TRY(modulate(x, coef, gb, nullptr, nullptr, bufp, B, T, Hc, Wc, cin, k.ut, k.uh, k.uw, ACT_LRELU02, s));
+        // shortcut at low resolution
+        const float* xs = x;
+        if (cin != cout) {
+            I2V_PTR(nsw, G(nm + ".norm_s.w", cin));
+            I2V_PTR(nsb, G(nm + ".norm_s.b", cin));
+            I2V_PTR(csw, G(nm + ".conv_s.w", (size_t)cout * cin));
+            I2V_TRY(launch_norm_coeffs(sums, coefs, B, cin, vlow, 16, 1e-5f, nsw, nsb, nullptr, s));
+            I2V_TRY(modulate(x, coefs, nullptr, nullptr, nullptr, lowin, B, Tl, Hl, Wl, cin, 1, 1, 1, ACT_NONE, s));
+            I2V_TRY(conv(eng, lowin, csw, nullptr, nullptr, lowout, B, Tl, Hl, Wl, cin, cout, 1, 1, 1, 1, 1, 1, 0, 0, 0, 1, 1, 1,
+                         ACT_NONE, 0, s));
+            xs = lowout;
+        }
+        // dx = conv_0(a0)
+        I2V_PTR(w0, G(nm + ".conv_0.w", (size_t)27 * cmid * cin));
+        I2V_PTR(b0, G(nm + ".conv_0.b", cmid));
+        I2V_TRY(conv(eng, bufp, w0, b0, nullptr, bufd, B, T, Hc, Wc, cin, cmid, 3, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, ACT_NONE, 0, s));
+        // a1 = lrelu(AdaIN(dx, z))
+        I2V_PTR(aw, G(nm + ".adain.w", (size_t)2 * cmid * zd));
+        I2V_PTR(ab, G(nm + ".adain.b", (size_t)2 * cmid));
+        I2V_TRY(launch_linear(z, aw, ab, mod, B, zd, 2 * cmid, ACT_NONE, s));
+        I2V_TRY(launch_channel_stats(bufd, sums, B, vhi, cmid, s));
+        I2V_TRY(launch_norm_coeffs(sums, coef, B, cmid, vhi, 0, 1e-5f, nullptr, nullptr, mod, s));
+        I2V_TRY(modulate(bufd, coef, nullptr, nullptr, nullptr, bufp, B, T, Hc, Wc, cmid, 1, 1, 1, ACT_LRELU02, s));
+        // out = conv_1(a1) + up(xs)
+        I2V_PTR(w1, G(nm + ".conv_1.w", (size_t)27 * cout * cmid));
+        I2V_PTR(b1, G(nm + ".conv_1.b", cout));
+        I2V_TRY(conv(eng, bufp, w1, b1, xs, xn, B, T, Hc, Wc, cmid, cout, 3, 3, 3, 1, 1, 1, 1, 1, 1, k.ut, k.uh, k.uw, ACT_NONE, 0, s));
+        float* t = x; x = xn; xn = t;
+    }
+    // frames = tanh(conv_img(lrelu(x)))  written as [B,T,3,H,W]
+    I2V_PTR(wi, G("conv_img.w", (size_t)27 * 3 * m->nf));
+    I2V_PTR(bi, G("conv_img.b", 3));
+    I2V_TRY(modulate(x, nullptr, nullptr, nullptr, nullptr, bufp, B, T, Hc, Wc, m->nf, 1, 1, 1, ACT_LRELU02, s));
+    I2V_TRY(conv(eng, bufp, wi, bi, nullptr, frames, B, T, Hc, Wc, m->nf, 3, 3, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, ACT_TANH, 1, s));
+    return 0;
+}
+
+extern "C" {
+i2v_decoder* i2v_decoder_create(int nf, int z_dim, const int us[2], const int ut[2], int engine) {
+    if (nf <= 0 || nf % 4 || z_dim <= 0 || z_dim % 4 || !us || !ut) { set_error("decoder_create: bad arguments"); return nullptr; }
+    auto* h = new i2v_decoder();
+    h->nf = nf; h->z_dim = z_dim; h->us[0] = us[0]; h->us[1] = us[1]; h->ut[0] = ut[0]; h->ut[1] = ut[1]; h->engine = engine;
+    return h;
+}
+int i2v_decoder_set_tensor(i2v_decoder* h, const char* n, const void* p, size_t b) { return h ? h->tt.set(n, p, b) : -1; }
+size_t i2v_decoder_workspace_bytes(const i2v_decoder* h, int batch, int height, int width) {
+    Arena ar(nullptr, 0, true);
+    if (decoder_run(h, nullptr, nullptr, nullptr, batch, height, width, ar, nullptr, true)) return 0;
+    return ar.peak + 256;
+}
+int i2v_decoder_forward(i2v_decoder* h, const float* img, const float* z, float* frames, int batch, int height, int width,
+                        void* ws, size_t wsb, void* stream) {
+    I2V_REQUIRE(h && img && z && frames && ws, "decoder_forward: null argument");
+    I2V_REQUIRE(batch > 0, "decoder_forward: empty batch");
+    Arena ar(ws, wsb, false);
+    return decoder_run(h, img, z, frames, batch, height, width, ar, static_cast<cudaStream_t>(stream), false);
+}
+void i2v_decoder_destroy(i2v_decoder* h) { delete h; }
+}  // extern "C"
+
+// =============================================================================== 3-D encoder
+struct i2v_encoder3d {
+    int ch[5], ss[4], st[4], z_dim;
+    TensorTable tt;
+};
+
+// Encoder.forward (resnet3D.py:208-219): conv1 (3,7,7)/2 -> GN16 -> ReLU -> 4 stages x 2 BasicBlocks
+// (resnet3D.py:101-135; the downsample branch is a 3x3x3 conv + GN, :185-193) -> conv_mu on the
+// 4x4 map, emitted as (mu | logvar) [B, 2*z_dim]; the reparameterised sample (resnet3D.py:202-206)
+// is formed by the caller from CPU noise like the reference does.
+static int encoder3d_run(const i2v_encoder3d* m, const float* seq, float* mu, int B, int T, int H, int W, Arena& ar,
+                         cudaStream_t s, bool dry) {
+    auto od = [](int n, int k, int st, int p) { return (n + 2 * p - k) / st + 1; };
+    int T1 = od(T, 3, 2, 1), H1 = od(H, 7, 2, 3), W1 = od(W, 7, 2, 3);
+    size_t amax = (size_t)B * T1 * H1 * W1 * m->ch[0];
+    int cmax = m->ch[0];
+    {
+        int t = T1, h = H1, w = W1;
+        for (int l = 0; l < 4; ++l) {
+            t = od(t, 3, m->st[l], 1); h = od(h, 3, m->ss[l], 1); w = od(w, 3, m->ss[l], 1);
+            amax = std::max(amax, (size_t)B * t * h * w * m->ch[l + 1]);
+            cmax = std::max(cmax, m->ch[l + 1]);
+        }
+        I2V_REQUIRE(t == 1 && h == 4 && w == 4,
+                    "encoder3d: clip %dx%dx%d collapses to %dx%dx%d, the reference needs 1x4x4 (resnet3D.py:179,219)", T, H, W, t, h, w);
+    }
+    float* xin = ar.take<float>((size_t)B * T * H * W * 3);
+    float* buf[4];
+    for (auto& b : buf) b = ar.take<float>(amax);
+    double* sums = ar.take<double>((size_t)B * cmax * 2);
+    double* sums2 = ar.take<double>((size_t)B * cmax * 2);
+    float* coef = ar.take<float>((size_t)B * cmax * 2);
+    float* coef2 = ar.take<float>((size_t)B * cmax * 2);
+    if (!ar.ok()) { set_error("encoder3d: workspace too small (%zu needed, %zu given)", ar.peak, ar.cap); return -4; }
+    if (dry) return 0;
+    auto G = [&](const std::string& n, size_t e) { return m->tt.get(n, e); };
+
+    // [B,T,3,H,W] -> [B,T,H,W,3]
+    I2V_TRY(launch_resize_bilinear_nchw_to_nhwc(seq, xin, B * T, 3, H, W, H, W, s));
+    I2V_PTR(w1, G("conv1.w", (size_t)147 * m->ch[0] * 3));
+    I2V_PTR(n1w, G("norm1.w", m->ch[0]));
+    I2V_PTR(n1b, G("norm1.b", m->ch[0]));
+    I2V_TRY(conv(0, xin, w1, nullptr, nullptr, buf[1], B, T, H, W, 3, m->ch[0], 3, 7, 7, 2, 2, 2, 1, 3, 3, 1, 1, 1, ACT_NONE, 0, s));
+    long long V = (long long)T1 * H1 * W1;
+    I2V_TRY(launch_channel_stats(buf[1], sums, B, V, m->ch[0], s));
+    I2V_TRY(launch_norm_coeffs(sums, coef, B, m->ch[0], V, 16, 1e-5f, n1w, n1b, nullptr, s));
+    I2V_TRY(modulate(buf[1], coef, nullptr, nullptr, nullptr, buf[0], B, T1, H1, W1, m->ch[0], 1, 1, 1, ACT_RELU, s));
+    float* cur = buf[0]; float* ta = buf[1]; float* tb = buf[2]; float* tc = buf[3];
+    int Tc = T1, Hc = H1, Wc = W1, Cc = 64;   // resnet3D.py:140 hard-codes inplanes = 64
+    I2V_REQUIRE(m->ch[0] == 64, "encoder3d: channels[0] must be 64 (resnet3D.py:140)");
+    for (int l = 0; l < 4; ++l) {
+        const int pl = m->ch[l + 1];
+        for (int bi = 0; bi < 2; ++bi) {
+            const std::string p = "layer." + std::to_string(l) + "." + std::to_string(bi) + ".";
+            const int st = bi == 0 ? m->st[l] : 1, ss = bi == 0 ? m->ss[l] : 1;
+            const int To = od(Tc, 3, st, 1), Ho = od(Hc, 3, ss, 1), Wo = od(Wc, 3, ss, 1);
+            const long long Vo = (long long)To * Ho * Wo;
+            I2V_PTR(wc1, G(p + "conv1.w", (size_t)27 * pl * Cc));
+            I2V_PTR(g1w, G(p + "bn1.w", pl)); I2V_PTR(g1b, G(p + "bn1.b", pl));
+            I2V_PTR(wc2, G(p + "conv2.w", (size_t)27 * pl * pl));
+            I2V_PTR(g2w, G(p + "bn2.w", pl)); I2V_PTR(g2b, G(p + "bn2.b", pl));
+            // o = relu(GN(conv1(h)))
+            I2V_TRY(conv(0, cur, wc1, nullptr, nullptr, ta, B, Tc, Hc, Wc, Cc, pl, 3, 3, 3, st, ss, ss, 1, 1, 1, 1, 1, 1, ACT_NONE, 0, s));
+            I2V_TRY(launch_channel_stats(ta, sums, B, Vo, pl, s));
+            I2V_TRY(launch_norm_coeffs(sums, coef, B, pl, Vo, 16, 1e-5f, g1w, g1b, nullptr, s));
+            I2V_TRY(modulate(ta, coef, nullptr, nullptr, nullptr, tb, B, To, Ho, Wo, pl, 1, 1, 1, ACT_RELU, s));
+            // o = GN(conv2(o))
+            I2V_TRY(conv(0, tb, wc2, nullptr, nullptr, ta, B, To, Ho, Wo, pl, pl, 3, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, ACT_NONE, 0, s));
+            I2V_TRY(launch_channel_stats(ta, sums, B, Vo, pl, s));
+            I2V_TRY(launch_norm_coeffs(sums, coef, B, pl, Vo, 16, 1e-5f, g2w, g2b, nullptr, s));
+            const float* res = cur; const float* c2 = nullptr;
+            if (m->tt.has(p + "ds.w")) {
+                I2V_PTR(wd, G(p + "ds.w", (size_t)27 * pl * Cc));
+                I2V_PTR(gdw, G(p + "ds.gn.w", pl)); I2V_PTR(gdb, G(p + "ds.gn.b", pl));
+                I2V_TRY(conv(0, cur, wd, nullptr, nullptr, tb, B, Tc, Hc, Wc, Cc, pl, 3, 3, 3, st, ss, ss, 1, 1, 1, 1, 1, 1, ACT_NONE, 0, s));
+                I2V_TRY(launch_channel_stats(tb, sums2, B, Vo, pl, s));
+                I2V_TRY(launch_norm_coeffs(sums2, coef2, B, pl, Vo, 16, 1e-5f, gdw, gdb, nullptr, s));
+                res = tb; c2 = coef2;
+            } else {
+                I2V_REQUIRE(st == 1 && ss == 1 && Cc == pl, "encoder3d: block %s needs a downsample branch but none was registered", p.c_str());
+            }
+            I2V_TRY(modulate(ta, coef, nullptr, res, c2, tc, B, To, Ho, Wo, pl, 1, 1, 1, ACT_RELU, s));
+            float* old = cur; cur = tc; tc = old;
+            Tc = To; Hc = Ho; Wc = Wo; Cc = pl;
+        }
+    }
+    // conv_mu | conv_var (4x4 valid convs on the 4x4 map = one Linear over the flattened (h,w,c) map)
+    I2V_PTR(mw, G("muvar.w", (size_t)2 * m->z_dim * 16 * Cc));
+    I2V_PTR(mb, G("muvar.b", (size_t)2 * m->z_dim));
+    I2V_TRY(launch_linear(cur, mw, mb, mu, B, 16 * Cc, 2 * m->z_dim, ACT_NONE, s));
+    return 0;
+}
+
+extern "C" {
+i2v_encoder3d* i2v_encoder3d_create(const int channels[5], const int stride_s[4], const int stride_t[4], int z_dim) {
+    if (!channels || !stride_s || !stride_t || z_dim <= 0) { set_error("encoder3d_create: bad arguments"); return nullptr; }
+    auto* h = new i2v_encoder3d();
+    for (int i = 0; i < 5; ++i) h->ch[i] = channels[i];
+    for (int i = 0; i < 4; ++i) { h->ss[i] = stride_s[i]; h->st[i] = stride_t[i]; }
+    h->z_dim = z_dim;
+    return h;
+}
+int i2v_encoder3d_set_tensor(i2v_encoder3d* h, const char* n, const void* p, size_t b) { return h ? h->tt.set(n, p, b) : -1; }
+size_t i2v_encoder3d_workspace_bytes(const i2v_encoder3d* h, int batch, int frames, int height, int width) {
+    Arena ar(nullptr, 0, true);
+    if (encoder3d_run(h, nullptr, nullptr, batch, frames, height, width, ar, nullptr, true)) return 0;
+    return ar.peak + 256;
+}
+int i2v_encoder3d_forward(i2v_encoder3d* h, const float* seq, float* mu, int batch, int frames, int height, int width,
+                          void* ws, size_t wsb, void* stream) {
+    I2V_REQUIRE(h && seq && mu && ws, "encoder3d_forward: null argument");
+    Arena ar(ws, wsb, false);
+    return encoder3d_run(h, seq, mu, batch, frames, height, width, ar, static_cast<cudaStream_t>(stream), false);
+}
+void i2v_encoder3d_destroy(i2v_encoder3d* h) { delete h; }
+
+// =============================================================================== single ops
+int i2v_op_conv(const float* x, const float* w, const float* bias, const float* res, float* y, int B, int Ti, int Hi, int Wi,
+                int Cin, int Cout, int kt, int kh, int kw, int st, int sh, int sw, int pt, int ph, int pw, int rut, int ruh,
+                int ruw, int act, int out_mode, int engine, void* stream) {
+    I2V_REQUIRE(x && w && y, "op_conv: null argument");
+    return conv(engine, x, w, bias, res, y, B, Ti, Hi, Wi, Cin, Cout, kt, kh, kw, st, sh, sw, pt, ph, pw, rut, ruh, ruw, act, out_mode,
+                static_cast<cudaStream_t>(stream));
+}
+int i2v_op_channel_stats(const float* x, double* sums, int B, int64_t V, int C, void* stream) {
+    return launch_channel_stats(x, sums, B, V, C, static_cast<cudaStream_t>(stream));
+}
+int i2v_op_norm_coeffs(const double* sums, float* coef, int B, int C, int64_t V, int groups, float eps, const float* gamma,
+                       const float* beta, const float* mod, void* stream) {
+    return launch_norm_coeffs(sums, coef, B, C, V, groups, eps, gamma, beta, mod, static_cast<cudaStream_t>(stream));
+}
+int i2v_op_modulate(const float* x, const float* coef, const float* gb, const float* r, const float* coef2, float* out, int B,
+                    int T, int H, int W, int C, int ut, int uh, int uw, int act, void* stream) {
+    return modulate(x, coef, gb, r, coef2, out, B, T, H, W, C, ut, uh, uw, act, static_cast<cudaStream_t>(stream));
+}
+int i2v_op_linear(const float* x, const float* w, const float* bias, float* y, int B, int K, int N, int act, void* stream) {
+    return launch_linear(x, w, bias, y, B, K, N, act, static_cast<cudaStream_t>(stream));
+}
+int i2v_op_resize_bilinear(const float* img, float* out, int B, int C, int H0, int W0, int H, int W, void* stream) {
+    return launch_resize_bilinear_nchw_to_nhwc(img, out, B, C, H0, W0, H, W, static_cast<cudaStream_t>(stream));
+}
+int i2v_op_maxpool3x3s2(const float* x, float* y, int B, int H, int W, int C, void* stream) {
+    return launch_maxpool3x3s2(x, y, B, H, W, C, static_cast<cudaStream_t>(stream));
+}
+}  // extern "C"

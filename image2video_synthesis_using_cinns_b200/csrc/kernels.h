@@ -1,0 +1,88 @@
+// Internal kernel launchers (C++); the public C-ABI lives in include/i2v_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+
+namespace i2v {
+
+// ----------------------------------------------------------------------------- convolution
+struct ConvArgs {
+    const float* x;      // [B, Ti, Hi, Wi, Cin]
+    const float* w;      // [taps, Cout, Cin]
+    const float* bias;   // [Cout] or nullptr
+    const float* res;    // residual [B, To/res_ut, Ho/res_uh, Wo/res_uw, Cout] or nullptr
+    float* y;
+    int B, Ti, Hi, Wi, Cin;
+    int To, Ho, Wo, Cout;
+    int kt, kh, kw, st, sh, sw, pt, ph, pw;
+    int res_ut, res_uh, res_uw;
+    int act;        // i2v::Act
+    int out_mode;   // 0: [B,To,Ho,Wo,Cout]   1: [B,To,Cout,Ho,Wo] (video frames)
+};
+int launch_conv_simt(const ConvArgs& a, cudaStream_t stream);
+
+// ----------------------------------------------------------------------------- normalisation
+// Per-(sample, channel) sums of a channels-last tensor x[B, V, C] -> sums[B, C, 2] (double):
+// the single statistics pass feeding InstanceNorm (per channel), GroupNorm (per 16-group) and the
+// global average pool.
+int launch_channel_stats(const float* x, double* sums, int B, long long V, int C, cudaStream_t stream);
+
+// Turn sums into per-(b, c) affine coefficients  y = A*x + Bc  of the normalisation layer:
+//   groups == 0 : instance norm (one group per channel);  groups > 0 : GroupNorm(groups)
+//   gamma/beta  : optional per-channel affine [C] (GroupNorm affine=True)
+//   mod         : optional per-sample modulation [B, 2C] = (gamma | beta) (AdaIN, gamma*x_hat+beta)
+int launch_norm_coeffs(const double* sums, float* coef /*[B,C,2]*/, int B, int C, long long V, int groups,
+                       float eps, const float* gamma, const float* beta, const float* mod, cudaStream_t stream);
+
+// Fused element-wise pass producing a conv-ready tensor (channels-last):
+//   v   = A[b,c] * x[b, t/ut, h/uh, w/uw, c] + Bc[b,c]              (coef may be null: v = x)
+//   v   = v * (1 + g[b,h,w,c]) + bt[b,h,w,c]                         (SPADE maps gb[B,H,W,2C], optional)
+//   v  += A2[b,c] * r[b,t,h,w,c] + B2[b,c]                           (second normalised branch, optional)
+//   out = act(v)
+struct ModArgs {
+    const float* x; const float* coef;        // coef [B,C,2] or nullptr
+    const float* gb;                          // [B,H,W,2C] or nullptr
+    const float* r; const float* coef2;       // residual branch (same shape as out) + its coef or nullptr
+    float* out;
+    int B, T, H, W, C;                        // OUTPUT dims
+    int ut, uh, uw;                           // nearest-upsample factors from x to out
+    int act;
+};
+int launch_modulate(const ModArgs& a, cudaStream_t stream);
+
+// ----------------------------------------------------------------------------- small ops
+// y[b, n] = act(sum_k W[n, k] x[b, k] + bias[n])      (nn.Linear layout)
+int launch_linear(const float* x, const float* w, const float* bias, float* y, int B, int K, int N, int act,
+                  cudaStream_t stream);
+// img [B,3,H0,W0] (NCHW) -> out [B,H,W,3] bilinear, align_corners=True (normalization_layer.py:20);
+// H==H0 && W==W0 degenerates to an exact NCHW->NHWC repack.
+int launch_resize_bilinear_nchw_to_nhwc(const float* img, float* out, int B, int C, int H0, int W0, int H, int W,
+                                        cudaStream_t stream);
+// 3x3 stride-2 pad-1 max pool, channels-last [B,H,W,C] -> [B,Ho,Wo,C]
+int launch_maxpool3x3s2(const float* x, float* y, int B, int H, int W, int C, cudaStream_t stream);
+// mean over V from channel sums: y[b,c] = sums[b,c,0] / V
+int launch_mean_from_sums(const double* sums, float* y, int B, int C, long long V, cudaStream_t stream);
+
+// ----------------------------------------------------------------------------- flow
+struct FlowWeights {
+    int n_flows, d, half, zc, hidden, depth;  // depth == 2 hidden->hidden layers
+    const unsigned char* cond_mode;           // host array [n_flows]: 1 = 'cond' block (no x input)
+    // packed device tensors (see loader.py::pack_flow)
+    const float* w1x;    // [n_flows, 2, 2*hidden, half]   x-part of the first Linear (s rows, then t rows)
+    const float* w1c;    // [n_flows*2*2*hidden, zc]       cond-part of the first Linear
+    const float* b1;     // [n_flows*2*2*hidden]
+    const float* wh;     // [n_flows, 2, depth, 2, hidden, hidden]   hidden Linears (s then t)
+    const float* bh;     // [n_flows, 2, depth, 2*hidden]
+    const float* wo;     // [n_flows, 2, 2*half, hidden]   last Linear (s rows then t rows)
+    const float* bo;     // [n_flows, 2, 2*half]
+    const float* loc;    // [n_flows, d]
+    const float* scale;  // [n_flows, d]
+    const int* perm_fwd; // [n_flows, d]
+    const int* perm_bwd; // [n_flows, d]
+};
+size_t flow_workspace_bytes(const FlowWeights& fw, int B);
+// reverse: z = flow^-1(residual | cond);  forward: (out, logdet) = flow(z | cond)
+int launch_flow(const FlowWeights& fw, const float* in, const float* cond, float* out, float* logdet, int B,
+                bool reverse, void* ws, size_t ws_bytes, cudaStream_t stream);
+
+}  // namespace i2v

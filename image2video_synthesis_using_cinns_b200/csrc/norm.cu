@@ -1,0 +1,186 @@
+// Statistics + fused modulation passes of the decoder / encoders (HBM-bound, channels-last fp32).
+//
+//   channel_stats : one read of x -> per-(sample, channel) sum and sum of squares (double)
+//   norm_coeffs   : sums -> per-(sample, channel) affine (A, Bc) of GroupNorm(16) / InstanceNorm /
+//                   AdaIN / GroupNorm-affine  (normalization_layer.py:11,31,42 ; eps 1e-5, biased var)
+//   modulate      : y = act( (A x + Bc) * (1 + gamma) + beta  [+ A2 r + B2] ), reading x through a
+//                   nearest-upsample index map so the upsampled tensor of decoder.py:102-114 is never
+//                   materialised, SPADE's gamma/beta maps are read as 2-D maps (not repeated over T as
+//                   normalization_layer.py:22-23 does).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace i2v {
+
+namespace {
+
+constexpr int STATS_THREADS = 256;
+constexpr int STATS_ELEMS_PER_THREAD = 256;   // voxels summed by one thread per channel group
+
+__global__ void __launch_bounds__(STATS_THREADS) channel_stats_kernel(const float* __restrict__ x,
+                                                                      double* __restrict__ sums, long long V,
+                                                                      int C, int lanes_c, int rows) {
+    extern __shared__ double sh[];   // [C][2]
+    const int b = blockIdx.y;
+    const int C4 = C >> 2;
+    for (int i = threadIdx.x; i < 2 * C; i += STATS_THREADS) sh[i] = 0.0;
+    __syncthreads();
+    const int cl = threadIdx.x % lanes_c, rl = threadIdx.x / lanes_c;
+    const long long chunk = (long long)rows * STATS_ELEMS_PER_THREAD;
+    const long long v0 = (long long)blockIdx.x * chunk;
+    const long long v1 = min(V, v0 + chunk);
+    const float4* xb = reinterpret_cast<const float4*>(x + (long long)b * V * C);
+    if (rl < rows) {
+        for (int cg = cl; cg < C4; cg += lanes_c) {
+            double s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+            long long v = v0 + rl;
+            while (v < v1) {
+                float fs[4] = {0, 0, 0, 0}, fq[4] = {0, 0, 0, 0};
+#pragma unroll 4
+                for (int it = 0; it < 16 && v < v1; ++it, v += rows) {
+                    const float4 t = __ldg(xb + v * C4 + cg);
+                    fs[0] += t.x; fs[1] += t.y; fs[2] += t.z; fs[3] += t.w;
+                    fq[0] = fmaf(t.x, t.x, fq[0]); fq[1] = fmaf(t.y, t.y, fq[1]);
+                    fq[2] = fmaf(t.z, t.z, fq[2]); fq[3] = fmaf(t.w, t.w, fq[3]);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { s[j] += fs[j]; q[j] += fq[j]; }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                atomicAdd(&sh[2 * (cg * 4 + j)], s[j]);
+                atomicAdd(&sh[2 * (cg * 4 + j) + 1], q[j]);
+            }
+        }
+    }
+    __syncthreads();
+    double* out = sums + (long long)b * C * 2;
+    for (int i = threadIdx.x; i < 2 * C; i += STATS_THREADS) atomicAdd(out + i, sh[i]);
+}
+
+__global__ void norm_coeffs_kernel(const double* __restrict__ sums, float* __restrict__ coef, int B, int C,
+                                   double count_per_channel, int groups, float eps,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   const float* __restrict__ mod) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * C) return;
+    const int b = idx / C, c = idx - b * C;
+    double s = 0, q = 0, n;
+    if (groups > 0) {
+        const int cpg = C / groups, g = c / cpg;
+        const double* p = sums + ((long long)b * C + g * cpg) * 2;
+        for (int i = 0; i < cpg; ++i) { s += p[2 * i]; q += p[2 * i + 1]; }
+        n = count_per_channel * cpg;
+    } else {
+        s = sums[(long long)idx * 2]; q = sums[(long long)idx * 2 + 1];
+        n = count_per_channel;
+    }
+    const double mean = s / n;
+    double var = q / n - mean * mean;
+    if (var < 0) var = 0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    float A = rstd, Bc = (float)(-mean) * rstd;
+    if (gamma != nullptr) { A *= gamma[c]; Bc = Bc * gamma[c] + beta[c]; }
+    if (mod != nullptr) {
+        const float g = mod[(long long)b * 2 * C + c], bt = mod[(long long)b * 2 * C + C + c];
+        A *= g; Bc = Bc * g + bt;
+    }
+    coef[(long long)idx * 2] = A;
+    coef[(long long)idx * 2 + 1] = Bc;
+}
+
+__global__ void __launch_bounds__(256) modulate_kernel(const ModArgs a, long long total4) {
+    const int C4 = a.C >> 2;
+    const int Ts = a.T / a.ut, Hs = a.H / a.uh, Ws = a.W / a.uw;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % C4);
+        long long vox = i / C4;
+        const int w = (int)(vox % a.W); vox /= a.W;
+        const int h = (int)(vox % a.H); vox /= a.H;
+        const int t = (int)(vox % a.T);
+        const int b = (int)(vox / a.T);
+        const long long src = ((((long long)b * Ts + t / a.ut) * Hs + h / a.uh) * Ws + w / a.uw) * C4 + c4;
+        float4 xv = __ldg(reinterpret_cast<const float4*>(a.x) + src);
+        float v[4] = {xv.x, xv.y, xv.z, xv.w};
+        if (a.coef != nullptr) {
+            const float4* cf = reinterpret_cast<const float4*>(a.coef + ((long long)b * a.C + c4 * 4) * 2);
+            const float4 c0 = __ldg(cf), c1 = __ldg(cf + 1);
+            v[0] = fmaf(c0.x, v[0], c0.y); v[1] = fmaf(c0.z, v[1], c0.w);
+            v[2] = fmaf(c1.x, v[2], c1.y); v[3] = fmaf(c1.z, v[3], c1.w);
+        }
+        if (a.gb != nullptr) {
+            const float4* gp = reinterpret_cast<const float4*>(a.gb + (((long long)b * a.H + h) * a.W + w) * 2 * a.C);
+            const float4 g = __ldg(gp + c4), bt = __ldg(gp + C4 + c4);
+            v[0] = fmaf(v[0], 1.f + g.x, bt.x); v[1] = fmaf(v[1], 1.f + g.y, bt.y);
+            v[2] = fmaf(v[2], 1.f + g.z, bt.z); v[3] = fmaf(v[3], 1.f + g.w, bt.w);
+        }
+        if (a.r != nullptr) {
+            const float4 rv = __ldg(reinterpret_cast<const float4*>(a.r) + i);
+            float r[4] = {rv.x, rv.y, rv.z, rv.w};
+            if (a.coef2 != nullptr) {
+                const float4* cf = reinterpret_cast<const float4*>(a.coef2 + ((long long)b * a.C + c4 * 4) * 2);
+                const float4 c0 = __ldg(cf), c1 = __ldg(cf + 1);
+                r[0] = fmaf(c0.x, r[0], c0.y); r[1] = fmaf(c0.z, r[1], c0.w);
+                r[2] = fmaf(c1.x, r[2], c1.y); r[3] = fmaf(c1.z, r[3], c1.w);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] += r[j];
+        }
+        float4 o;
+        o.x = apply_act(v[0], a.act); o.y = apply_act(v[1], a.act);
+        o.z = apply_act(v[2], a.act); o.w = apply_act(v[3], a.act);
+        reinterpret_cast<float4*>(a.out)[i] = o;
+    }
+}
+
+__global__ void mean_from_sums_kernel(const double* __restrict__ sums, float* __restrict__ y, int n, double inv) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = (float)(sums[2 * (long long)i] * inv);
+}
+
+}  // namespace
+
+int launch_channel_stats(const float* x, double* sums, int B, long long V, int C, cudaStream_t stream) {
+    I2V_REQUIRE(C % 4 == 0 && C <= 2048, "channel_stats: C=%d must be a multiple of 4 and <= 2048", C);
+    I2V_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)B * C, stream));
+    const int C4 = C / 4;
+    const int lanes_c = C4 < STATS_THREADS ? C4 : STATS_THREADS;
+    const int rows = STATS_THREADS / lanes_c;
+    const long long chunk = (long long)rows * STATS_ELEMS_PER_THREAD;
+    dim3 grid(ceil_div(V, chunk), B);
+    channel_stats_kernel<<<grid, STATS_THREADS, sizeof(double) * 2 * C, stream>>>(x, sums, V, C, lanes_c, rows);
+    I2V_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_norm_coeffs(const double* sums, float* coef, int B, int C, long long V, int groups, float eps,
+                       const float* gamma, const float* beta, const float* mod, cudaStream_t stream) {
+    I2V_REQUIRE(groups == 0 || C % groups == 0, "norm_coeffs: C=%d not divisible by groups=%d", C, groups);
+    I2V_REQUIRE((gamma == nullptr) == (beta == nullptr), "norm_coeffs: gamma and beta go together");
+    const int n = B * C;
+    norm_coeffs_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(sums, coef, B, C, (double)V, groups, eps, gamma, beta, mod);
+    I2V_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_modulate(const ModArgs& a, cudaStream_t stream) {
+    I2V_REQUIRE(a.C % 4 == 0, "modulate: C=%d must be a multiple of 4", a.C);
+    I2V_REQUIRE(a.T % a.ut == 0 && a.H % a.uh == 0 && a.W % a.uw == 0, "modulate: upsample factors must divide dims");
+    const long long total4 = (long long)a.B * a.T * a.H * a.W * (a.C / 4);
+    long long blocks = (total4 + 255) / 256;
+    const long long cap = (long long)kNumSMs * 32;
+    if (blocks > cap) blocks = cap;
+    modulate_kernel<<<(int)blocks, 256, 0, stream>>>(a, total4);
+    I2V_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_mean_from_sums(const double* sums, float* y, int B, int C, long long V, cudaStream_t stream) {
+    const int n = B * C;
+    mean_from_sums_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(sums, y, n, 1.0 / (double)V);
+    I2V_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace i2v

@@ -1,0 +1,110 @@
+"""Drop-in for the reference's inference facade ``get_model.Model`` (get_model.py:10-103).
+
+Same constructor, attributes and methods; the same three YAML files and four ``torch.save``
+checkpoints load unchanged.  Differences are confined to *where* the
+arithmetic runs (libi2v_b200.so, sm_100a) and are listed in DESIGN.md.  Reference quirks that define
+"identical output" are reproduced and flagged:
+
+Q1  ``forward`` returns ``seq[:vid_length]`` -- a slice of the BATCH dimension (get_model.py:75);
+    T is never trimmed (seq_length 24 -> 32 frames).  Reproduced; ``sample()`` returns the unsliced
+    tensor for callers that want every video.
+Q4  ``transfer`` is only coherent for one query clip per call (get_model.py:93).
+Q5  the residual is drawn on the CPU generator and then moved to the device (get_model.py:59), so
+    ``torch.manual_seed(s)`` reproduces the reference's sample exactly.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import modules
+from .config import load_yaml
+
+
+def _load_state(path):
+    obj = torch.load(path, map_location="cpu")
+    if not isinstance(obj, dict) or "state_dict" not in obj:
+        raise ValueError(f"{path}: expected a torch.save'd dict with a 'state_dict' entry "
+                         "(utils/auxiliaries.py:8-12 format)")
+    return obj["state_dict"]
+
+
+class Model:
+    """``Model(model_path, vid_length, transfer=False)`` as in the reference; extra keyword-only knobs
+    select the device, the decoder micro-batch and the conv engine."""
+
+    def __init__(self, model_path, vid_length, transfer=False, *, device="cuda", micro_batch=16, conv_engine=0):
+        opt = load_yaml(model_path + "config_stage2.yaml")                                   # get_model.py:15
+        fs = opt.First_stage_model
+        path_stage1 = fs["model_path"] + fs["model_name"] + "/"                              # get_model.py:16
+        config = load_yaml(path_stage1 + "config_stage1.yaml")                               # get_model.py:19
+        self.device = torch.device(device)
+
+        self.decoder = modules.Generator(_load_state(path_stage1 + fs["checkpoint_decoder"] + ".pth"),
+                                         config.Decoder, device=device, conv_engine=conv_engine,
+                                         micro_batch=micro_batch)                             # get_model.py:22-24
+        if transfer:
+            self.encoder = modules.Encoder(_load_state(path_stage1 + fs["checkpoint_encoder"] + ".pth.tar"),
+                                           config.Encoder, device=device)                     # get_model.py:27-31
+
+        cm = opt.Conditioning_Model
+        control = bool(opt.Training["control"]) if opt.Training is not None else False        # get_model.py:42
+        z_dim = config.Decoder["z_dim"]
+        hidden = z_dim * opt.Flow["flow_mid_channels_factor"]                                 # get_model.py:34
+        ae_path = cm["model_path"] + cm["model_name"] + "/"                                   # INN.py:37
+        ae_cfg = load_yaml(ae_path + "config_stage2_AE.yaml")
+        embedder = modules.ResnetEncoder(_load_state(ae_path + cm["checkpoint_name"] + ".pth"), ae_cfg.AE,
+                                         device=device)                                       # INN.py:39-41
+        flow = modules.ConditionalFlow(_load_state(model_path + "cINN.pth"), in_channels=z_dim,
+                                       embedding_dim=cm["z_dim"] + (30 if control else 0), hidden_dim=hidden,
+                                       hidden_depth=opt.Flow["flow_hidden_depth"], n_flows=opt.Flow["n_flows"],
+                                       control=control, device=device)                        # get_model.py:43
+        self.flow = modules.SupervisedTransformer(flow, embedder, control)
+        self.z_dim = z_dim
+        self.vid_length = vid_length
+        self.config = opt
+
+    # nn.Module-isms the reference's callers use
+    def eval(self):
+        return self
+
+    def cuda(self, *a, **k):
+        return self
+
+    def parameters(self):
+        return iter(())
+
+    def _render(self, x_0, z):
+        seq = self.decoder(x_0, z)                                                            # get_model.py:68
+        while seq.shape[1] < self.vid_length:                                                 # get_model.py:71-73
+            seq = torch.cat((seq, self.decoder(seq[:, -1], z)), dim=1)
+        return seq
+
+    @torch.no_grad()
+    def sample(self, x_0, cond=None, residual=None, return_latent=False):
+        """All generated videos (B, T', 3, H, W); ``residual`` overrides the CPU-RNG draw."""
+        x_0 = x_0.to(self.device, torch.float32)
+        if residual is None:
+            residual = torch.randn(x_0.size(0), self.z_dim)                                   # CPU RNG (Q5)
+        z = self.flow(residual.to(self.device), [x_0, cond], reverse=True).view(x_0.size(0), -1)
+        seq = self._render(x_0, z)
+        return (seq, z) if return_latent else seq
+
+    def forward(self, x_0, cond=None):
+        """(BS, C, H, W) start frames -> (BS, T, C, H, W); see Q1 for the batch slice."""
+        return self.sample(x_0, cond)[: self.vid_length]                                      # get_model.py:75
+
+    __call__ = forward
+
+    @torch.no_grad()
+    def transfer(self, seq_query, x_0, return_latent=False):
+        """Motion transfer (get_model.py:77-103)."""
+        if not hasattr(self, "encoder"):
+            raise RuntimeError("Model was built with transfer=False: the 3-D encoder is not loaded")
+        seq_query = seq_query.to(self.device, torch.float32)
+        x_0 = x_0.to(self.device, torch.float32)
+        _, z, _ = self.encoder(seq_query[:, 1:].transpose(1, 2))                              # get_model.py:87
+        res, logdet = self.flow(z, [seq_query[:, 0]])                                         # get_model.py:90
+        res = res.view(z.size(0), -1).repeat(x_0.size(0), 1)
+        z_ref = self.flow(res, [x_0], reverse=True).view(x_0.size(0), -1)                     # get_model.py:93
+        seq = self._render(x_0, z_ref)
+        return (seq, z_ref, z, res, logdet) if return_latent else seq

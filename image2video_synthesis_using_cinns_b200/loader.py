@@ -1,0 +1,180 @@
+"""Load-time weight preprocessing: reference state-dicts -> kernel layouts.
+
+Everything here runs once per checkpoint on the host in fp32 (float64 where a reduction is folded)
+and is pure data movement / constant folding of things the reference recomputes on every forward:
+
+* spectral norm: eval-mode ``W = W_orig / (u . W_mat v)`` (decoder.py:20-25; the reference re-divides
+  all 150 M decoder weights per call -- 20 % of its CPU time) is folded once;
+* BatchNorm (eval) of the 'bn' embedder variants is folded into the preceding conv;
+* conv weights go to ``[taps, Cout, Cin]`` (channels-last implicit GEMM), SPADE's gamma/beta convs are
+  concatenated into one conv, the decoder's ``fc`` rows are permuted so its output is already the
+  channels-last [B,1,4,4,C] tensor ``decoder.py:99`` reshapes to;
+* flow MLPs: the first Linear of every subnet is split into its state part and its conditioning
+  part (the latter is hoisted out of the sequential chain), scale/translation nets are stacked.
+"""
+from __future__ import annotations
+
+import torch
+
+
+def _taps3(w):
+    """(Cout, Cin, kt, kh, kw) -> [kt*kh*kw, Cout, Cin]"""
+    co, ci = w.shape[:2]
+    return w.permute(2, 3, 4, 0, 1).reshape(-1, co, ci).contiguous()
+
+
+def _taps2(w):
+    """(Cout, Cin, kh, kw) -> [kh*kw, Cout, Cin]"""
+    co, ci = w.shape[:2]
+    return w.permute(2, 3, 0, 1).reshape(-1, co, ci).contiguous()
+
+
+def fold_spectral(sd, prefix):
+    if prefix + ".weight_orig" in sd:
+        w = sd[prefix + ".weight_orig"].double()
+        sigma = torch.dot(sd[prefix + ".weight_u"].double(), w.reshape(w.shape[0], -1) @ sd[prefix + ".weight_v"].double())
+        return (w / sigma).float()
+    return sd[prefix + ".weight"].float()
+
+
+# ------------------------------------------------------------------------------------------ flow
+def pack_flow(sd, n_flows, d, cond_channels, hidden, depth, control):
+    """ConditionalFlow state-dict (flow_blocks.py / modules.py key layout) -> packed tensors.
+
+    Returns (tensors, cond_mode list, zc_pad).  The conditioning width is zero-padded to a multiple of
+    4 (control=True makes it zc+30 = 94/158)."""
+    half = d // 2
+    zc_pad = (cond_channels + 3) // 4 * 4
+    H = hidden
+    w1x = torch.zeros(n_flows, 2, 2 * H, half)
+    w1c = torch.zeros(n_flows, 2, 2 * H, zc_pad)
+    b1 = torch.zeros(n_flows, 2, 2 * H)
+    wh = torch.zeros(n_flows, 2, max(depth, 1), 2, H, H)
+    bh = torch.zeros(n_flows, 2, max(depth, 1), 2 * H)
+    wo = torch.zeros(n_flows, 2, 2 * half, H)
+    bo = torch.zeros(n_flows, 2, 2 * half)
+    loc = torch.zeros(n_flows, d)
+    scale = torch.zeros(n_flows, d)
+    pf = torch.zeros(n_flows, d, dtype=torch.int32)
+    pb = torch.zeros(n_flows, d, dtype=torch.int32)
+    cond_mode = []
+    for fl in range(n_flows):
+        p = f"sub_layers.{fl}."
+        cm = bool(control) and fl % 4 != 0          # flow_blocks.py:24
+        cond_mode.append(1 if cm else 0)
+        if int(sd[p + "norm_layer.initialized"]) == 0:
+            raise ValueError(
+                f"{p}norm_layer.initialized == 0: the reference would data-initialise ActNorm on the first "
+                "forward even in eval (modules.py:76-78, quirk Q2); refusing to load an untrained flow")
+        loc[fl] = sd[p + "norm_layer.loc"].reshape(-1)
+        scale[fl] = sd[p + "norm_layer.scale"].reshape(-1)
+        pf[fl] = sd[p + "shuffle.forward_shuffle_idx"].to(torch.int32)
+        pb[fl] = sd[p + "shuffle.backward_shuffle_idx"].to(torch.int32)
+        for i in range(2):
+            for ni, net in enumerate(("s", "t")):
+                q = f"{p}coupling.{net}.{i}.main."
+                w0 = sd[q + "0.weight"].float()
+                rows = slice(ni * H, (ni + 1) * H)
+                if cm:
+                    assert w0.shape == (H, cond_channels), (w0.shape, cond_channels)
+                    w1c[fl, i, rows, :cond_channels] = w0
+                else:
+                    assert w0.shape == (H, half + cond_channels), (w0.shape, half, cond_channels)
+                    w1x[fl, i, rows] = w0[:, :half]
+                    w1c[fl, i, rows, :cond_channels] = w0[:, half:]
+                b1[fl, i, rows] = sd[q + "0.bias"]
+                for l in range(depth):
+                    wh[fl, i, l, ni] = sd[f"{q}{2 * (l + 1)}.weight"]
+                    bh[fl, i, l, rows] = sd[f"{q}{2 * (l + 1)}.bias"]
+                orow = slice(ni * half, (ni + 1) * half)
+                wo[fl, i, orow] = sd[f"{q}{2 * (depth + 1)}.weight"]
+                bo[fl, i, orow] = sd[f"{q}{2 * (depth + 1)}.bias"]
+    t = dict(w1x=w1x, w1c=w1c.reshape(-1, zc_pad), b1=b1.reshape(-1), wh=wh, bh=bh, wo=wo, bo=bo, loc=loc,
+             scale=scale, perm_fwd=pf, perm_bwd=pb)
+    return {k: v.contiguous() for k, v in t.items()}, cond_mode, zc_pad
+
+
+# --------------------------------------------------------------------------------------- decoder
+DEC_BLOCKS = ("head_0", "g_0", "g_1", "g_2", "g_3", "g_4")
+
+
+def pack_decoder(sd, nf):
+    t = {}
+    c0 = 16 * nf
+    # fc output index n = c*16 + (h*4+w)  ->  channels-last index (h*4+w)*C + c
+    fw = sd["fc.weight"].float().reshape(c0, 16, -1).permute(1, 0, 2).reshape(16 * c0, -1)
+    fb = sd["fc.bias"].float().reshape(c0, 16).t().reshape(-1)
+    t["fc.w"], t["fc.b"] = fw, fb
+    for name in DEC_BLOCKS:
+        t[f"{name}.conv_0.w"] = _taps3(fold_spectral(sd, f"{name}.conv_0"))
+        t[f"{name}.conv_0.b"] = sd[f"{name}.conv_0.bias"].float()
+        t[f"{name}.conv_1.w"] = _taps3(fold_spectral(sd, f"{name}.conv_1"))
+        t[f"{name}.conv_1.b"] = sd[f"{name}.conv_1.bias"].float()
+        if f"{name}.conv_s.weight_orig" in sd or f"{name}.conv_s.weight" in sd:
+            t[f"{name}.conv_s.w"] = _taps3(fold_spectral(sd, f"{name}.conv_s"))
+            t[f"{name}.norm_s.w"] = sd[f"{name}.norm_s.bn.weight"].float()
+            t[f"{name}.norm_s.b"] = sd[f"{name}.norm_s.bn.bias"].float()
+        t[f"{name}.spade.conv.w"] = _taps2(sd[f"{name}.norm_0.conv.weight"].float())
+        t[f"{name}.spade.conv.b"] = sd[f"{name}.norm_0.conv.bias"].float()
+        t[f"{name}.spade.gb.w"] = _taps2(torch.cat((sd[f"{name}.norm_0.conv_gamma.weight"],
+                                                    sd[f"{name}.norm_0.conv_beta.weight"]), 0).float())
+        t[f"{name}.spade.gb.b"] = torch.cat((sd[f"{name}.norm_0.conv_gamma.bias"],
+                                             sd[f"{name}.norm_0.conv_beta.bias"]), 0).float()
+        t[f"{name}.adain.w"] = sd[f"{name}.norm_1.linear.weight"].float()
+        t[f"{name}.adain.b"] = sd[f"{name}.norm_1.linear.bias"].float()
+    t["conv_img.w"] = _taps3(sd["conv_img.weight"].float())
+    t["conv_img.b"] = sd["conv_img.bias"].float()
+    return {k: v.contiguous() for k, v in t.items()}
+
+
+# -------------------------------------------------------------------------------------- embedder
+def pack_embedder(sd, zc, norm):
+    """torchvision-resnet50 keys under ``model.`` (AE.py:109) -> channels-last conv stacks."""
+    t = {}
+
+    def put(dst, conv_key, bn_key):
+        w = sd[conv_key].double()
+        if norm == "bn":
+            g, b = sd[bn_key + ".weight"].double(), sd[bn_key + ".bias"].double()
+            mean, var = sd[bn_key + ".running_mean"].double(), sd[bn_key + ".running_var"].double()
+            sc = g / torch.sqrt(var + 1e-5)
+            w = w * sc.reshape(-1, 1, 1, 1)
+            t[dst + ".b"] = (b - mean * sc).float()
+        t[dst + ".w"] = _taps2(w.float())
+
+    put("conv1", "model.conv1.weight", "model.bn1")
+    for li, nb in enumerate((3, 4, 6, 3)):
+        for bi in range(nb):
+            p, q = f"model.layer{li + 1}.{bi}.", f"layer{li + 1}.{bi}."
+            for j in (1, 2, 3):
+                put(f"{q}conv{j}", f"{p}conv{j}.weight", f"{p}bn{j}")
+            if bi == 0:
+                put(f"{q}ds", f"{p}downsample.0.weight", f"{p}downsample.1")
+    fcw = sd["model.fc.sub_layers.0.weight"].float()
+    if fcw.shape[2] != 1 or fcw.shape[3] != 1:
+        raise ValueError("embedder fc kernel is not 1x1: input size does not reduce to 1x1 before the fc")
+    t["fc.w"] = fcw.reshape(fcw.shape[0], -1)[:zc]      # mode() keeps the first zc channels
+    t["fc.b"] = sd["model.fc.sub_layers.0.bias"].float()[:zc]
+    return {k: v.contiguous() for k, v in t.items()}
+
+
+# ------------------------------------------------------------------------------------ 3-D encoder
+def pack_encoder3d(sd, n_stages=4, blocks=2):
+    t = {"conv1.w": _taps3(sd["conv1.weight"].float()), "norm1.w": sd["norm1.weight"].float(),
+         "norm1.b": sd["norm1.bias"].float()}
+    for l in range(n_stages):
+        for b in range(blocks):
+            p = f"layer.{l}.{b}."
+            t[p + "conv1.w"] = _taps3(sd[p + "conv1.weight"].float())
+            t[p + "conv2.w"] = _taps3(sd[p + "conv2.weight"].float())
+            for nm in ("bn1", "bn2"):
+                t[p + nm + ".w"], t[p + nm + ".b"] = sd[p + nm + ".weight"].float(), sd[p + nm + ".bias"].float()
+            if p + "downsample.0.weight" in sd:
+                t[p + "ds.w"] = _taps3(sd[p + "downsample.0.weight"].float())
+                t[p + "ds.gn.w"] = sd[p + "downsample.1.weight"].float()
+                t[p + "ds.gn.b"] = sd[p + "downsample.1.bias"].float()
+    # conv_mu / conv_var: (z, C, 4, 4) valid conv on the 4x4 map -> Linear over the (h, w, c) flattening
+    mv = torch.cat((sd["conv_mu.weight"], sd["conv_var.weight"]), 0).float()
+    t["muvar.w"] = mv.permute(0, 2, 3, 1).reshape(mv.shape[0], -1)
+    t["muvar.b"] = torch.cat((sd["conv_mu.bias"], sd["conv_var.bias"]), 0).float()
+    return {k: v.contiguous() for k, v in t.items()}

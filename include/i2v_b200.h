@@ -1,0 +1,118 @@
+/* i2v_b200.h -- C-ABI of the B200-native image->video sampling path.
+ *
+ * The reference (CompVis/image2video-synthesis-using-cINNs) is pure Python/PyTorch and has no
+ * FFI; the boundary it offers is the Python class get_model.Model (get_model.py:10-103) and the
+ * nn.Module seams below it.  Each entry point here replaces the arithmetic of one of those seams
+ * and is what a reference-side binding (ctypes) would call:
+ *
+ *   i2v_flow_reverse / i2v_flow_forward   <- ConditionalFlow.forward(x, embedding, reverse)
+ *                                            stage2_cINN/modules/flow_blocks.py:31-57
+ *                                            (called from SupervisedTransformer.forward, INN.py:59-73)
+ *   i2v_embedder_forward                  <- ResnetEncoder.encode(x).mode()
+ *                                            stage2_cINN/AE/modules/AE.py:126-166, distributions.py:41
+ *   i2v_decoder_forward                   <- Generator.forward(img, motion)
+ *                                            stage1_VAE/modules/decoder.py:97-120
+ *   i2v_encoder3d_forward                 <- Encoder.forward(x) -> (mu | logvar); get_model.py:87 consumes
+ *                                            mu only.  stage1_VAE/modules/resnet3D.py:202-219
+ *   i2v_op_*                              <- the individual kernels, exported for parity tests
+ *
+ * Conventions: plain pointers and sizes only (no torch types); every pointer named dev_* is a CUDA
+ * device pointer on the current device; `stream` is a cudaStream_t passed as void*; no entry point
+ * allocates device memory or synchronises -- the caller provides a workspace of at least
+ * i2v_*_workspace_bytes() bytes (256-byte aligned) that must stay alive until the stream has
+ * drained.  Weights are registered by name with i2v_*_set_tensor (layouts in DESIGN.md section 3;
+ * packed from the reference's state-dicts by loader.py) and are NOT copied: the caller keeps them
+ * alive for the life of the handle.  All functions returning int return 0 on success and a negative
+ * code on failure, with a message available from i2v_last_error() (thread-local).  Nothing throws
+ * across the ABI.  Handles are not thread-safe; use one per host thread / stream.
+ */
+#ifndef I2V_B200_H_
+#define I2V_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define I2V_ABI_VERSION 1
+
+int i2v_abi_version(void);
+const char* i2v_last_error(void);
+
+/* ---------------------------------------------------------------- conditional INN (stage 2) */
+typedef struct i2v_flow i2v_flow;
+/* d: latent width (64); zc: conditioning width padded to a multiple of 4; hidden: MLP width (<=512);
+ * depth: hidden->hidden layers per MLP (2); cond_mode[n_flows]: 1 where the block's subnets see only
+ * the conditioning (flow_blocks.py:24, control=True and fl % 4 != 0), may be NULL (= all 0). */
+i2v_flow* i2v_flow_create(int n_flows, int d, int zc, int hidden, int depth, const unsigned char* cond_mode);
+int i2v_flow_set_tensor(i2v_flow* h, const char* name, const void* dev_ptr, size_t nbytes);
+size_t i2v_flow_workspace_bytes(const i2v_flow* h, int batch);
+/* z[B,d] = flow^-1(residual[B,d] | cond[B,zc])            (Model.forward, get_model.py:65) */
+int i2v_flow_reverse(i2v_flow* h, const float* dev_residual, const float* dev_cond, float* dev_z, int batch,
+                     void* dev_ws, size_t ws_bytes, void* stream);
+/* out[B,d], logdet[B] = flow(z[B,d] | cond[B,zc])         (Model.transfer, get_model.py:90) */
+int i2v_flow_forward(i2v_flow* h, const float* dev_z, const float* dev_cond, float* dev_out, float* dev_logdet,
+                     int batch, void* dev_ws, size_t ws_bytes, void* stream);
+void i2v_flow_destroy(i2v_flow* h);
+
+/* ---------------------------------------------------------------- start-frame embedder */
+typedef struct i2v_embedder i2v_embedder;
+/* norm_mode: 0 = InstanceNorm2d (norm "in"), 1 = BatchNorm folded into conv weights+bias at load */
+i2v_embedder* i2v_embedder_create(int zc, int norm_mode);
+int i2v_embedder_set_tensor(i2v_embedder* h, const char* name, const void* dev_ptr, size_t nbytes);
+size_t i2v_embedder_workspace_bytes(const i2v_embedder* h, int batch, int height, int width);
+/* x0: [B,3,H,W] fp32 NCHW in [-1,1]  ->  embed: [B, zc] (the posterior mean) */
+int i2v_embedder_forward(i2v_embedder* h, const float* dev_x0, float* dev_embed, int batch, int height, int width,
+                         void* dev_ws, size_t ws_bytes, void* stream);
+void i2v_embedder_destroy(i2v_embedder* h);
+
+/* ---------------------------------------------------------------- 3-D conv decoder (stage 1) */
+typedef struct i2v_decoder i2v_decoder;
+/* nf: Decoder.channel_factor; upsample_s/t: the two config lists (decoder.py:65-66).
+ * conv_engine: 0 = fp32 SIMT implicit GEMM everywhere (exact-arithmetic engine). */
+i2v_decoder* i2v_decoder_create(int nf, int z_dim, const int upsample_s[2], const int upsample_t[2], int conv_engine);
+int i2v_decoder_set_tensor(i2v_decoder* h, const char* name, const void* dev_ptr, size_t nbytes);
+size_t i2v_decoder_workspace_bytes(const i2v_decoder* h, int batch, int height, int width);
+/* img: [B,3,H,W] NCHW; z: [B,z_dim]; frames: [B,16,3,H,W] (contiguous; the reference returns the
+ * same values as a transposed view, decoder.py:120) */
+int i2v_decoder_forward(i2v_decoder* h, const float* dev_img, const float* dev_z, float* dev_frames, int batch,
+                        int height, int width, void* dev_ws, size_t ws_bytes, void* stream);
+void i2v_decoder_destroy(i2v_decoder* h);
+
+/* ---------------------------------------------------------------- 3-D video encoder (transfer) */
+typedef struct i2v_encoder3d i2v_encoder3d;
+i2v_encoder3d* i2v_encoder3d_create(const int channels[5], const int stride_s[4], const int stride_t[4], int z_dim);
+int i2v_encoder3d_set_tensor(i2v_encoder3d* h, const char* name, const void* dev_ptr, size_t nbytes);
+size_t i2v_encoder3d_workspace_bytes(const i2v_encoder3d* h, int batch, int frames, int height, int width);
+/* seq: [B,T,3,H,W] fp32 (the query clip without its first frame, get_model.py:87)
+ * -> mu_logvar [B, 2*z_dim] = (conv_mu | conv_var) outputs, resnet3D.py:202-203 */
+int i2v_encoder3d_forward(i2v_encoder3d* h, const float* dev_seq, float* dev_mu_logvar, int batch, int frames, int height,
+                          int width, void* dev_ws, size_t ws_bytes, void* stream);
+void i2v_encoder3d_destroy(i2v_encoder3d* h);
+
+/* ---------------------------------------------------------------- single kernels (parity tests) */
+/* channels-last convolution, weights [taps,Cout,Cin]; res may be NULL; act: 0 none 1 relu 2 lrelu(0.2)
+ * 3 tanh; out_mode 0: [B,To,Ho,Wo,Cout], 1: [B,To,Cout,Ho,Wo]; engine 0 = fp32 SIMT */
+int i2v_op_conv(const float* dev_x, const float* dev_w, const float* dev_bias, const float* dev_res, float* dev_y,
+                int B, int Ti, int Hi, int Wi, int Cin, int Cout, int kt, int kh, int kw, int st, int sh, int sw,
+                int pt, int ph, int pw, int res_ut, int res_uh, int res_uw, int act, int out_mode, int engine,
+                void* stream);
+/* sums[B,C,2] (double) of x[B,V,C] */
+int i2v_op_channel_stats(const float* dev_x, double* dev_sums, int B, int64_t V, int C, void* stream);
+int i2v_op_norm_coeffs(const double* dev_sums, float* dev_coef, int B, int C, int64_t V, int groups, float eps,
+                       const float* dev_gamma, const float* dev_beta, const float* dev_mod, void* stream);
+int i2v_op_modulate(const float* dev_x, const float* dev_coef, const float* dev_gb, const float* dev_r,
+                    const float* dev_coef2, float* dev_out, int B, int T, int H, int W, int C, int ut, int uh, int uw,
+                    int act, void* stream);
+int i2v_op_linear(const float* dev_x, const float* dev_w, const float* dev_bias, float* dev_y, int B, int K, int N,
+                  int act, void* stream);
+int i2v_op_resize_bilinear(const float* dev_img, float* dev_out, int B, int C, int H0, int W0, int H, int W,
+                           void* stream);
+int i2v_op_maxpool3x3s2(const float* dev_x, float* dev_y, int B, int H, int W, int C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* I2V_B200_H_ */

@@ -1,0 +1,100 @@
+"""ctypes wrappers over the single-kernel C-ABI entry points, for the parity tests (GPU only)."""
+import ctypes
+
+import torch
+
+from image2video_synthesis_using_cinns_b200 import lib as _lib
+
+
+def P(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def S():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def to_cl(x):
+    """NCTHW / NCHW -> channels-last contiguous cuda tensor."""
+    if x.dim() == 5:
+        return x.permute(0, 2, 3, 4, 1).contiguous().cuda()
+    return x.permute(0, 2, 3, 1).contiguous().cuda()
+
+
+def from_cl(y):
+    if y.dim() == 5:
+        return y.permute(0, 4, 1, 2, 3).contiguous().cpu()
+    return y.permute(0, 3, 1, 2).contiguous().cpu()
+
+
+def taps(w):
+    co, ci = w.shape[:2]
+    perm = (2, 3, 4, 0, 1) if w.dim() == 5 else (2, 3, 0, 1)
+    return w.permute(*perm).reshape(-1, co, ci).contiguous().cuda()
+
+
+def conv(x_cl, w_taps, bias, res_cl, k, stride, pad, res_up=(1, 1, 1), act=0, out_mode=0, engine=0):
+    """x_cl [B,T,H,W,Cin] cuda; k/stride/pad are (t,h,w) triples."""
+    L = _lib.load()
+    B, Ti, Hi, Wi, Cin = x_cl.shape
+    Cout = w_taps.shape[1]
+    To = (Ti + 2 * pad[0] - k[0]) // stride[0] + 1
+    Ho = (Hi + 2 * pad[1] - k[1]) // stride[1] + 1
+    Wo = (Wi + 2 * pad[2] - k[2]) // stride[2] + 1
+    shape = (B, To, Ho, Wo, Cout) if out_mode == 0 else (B, To, Cout, Ho, Wo)
+    y = torch.empty(shape, dtype=torch.float32, device="cuda")
+    _lib.check(L.i2v_op_conv(P(x_cl), P(w_taps), P(bias), P(res_cl), P(y), B, Ti, Hi, Wi, Cin, Cout, *k, *stride, *pad,
+                             *res_up, act, out_mode, engine, S()), "op_conv")
+    return y
+
+
+def channel_stats(x_cl):
+    L = _lib.load()
+    B, C = x_cl.shape[0], x_cl.shape[-1]
+    V = x_cl.numel() // (B * C)
+    sums = torch.empty(B, C, 2, dtype=torch.float64, device="cuda")
+    _lib.check(L.i2v_op_channel_stats(P(x_cl), P(sums), B, V, C, S()), "op_channel_stats")
+    return sums, V
+
+
+def norm_coeffs(sums, V, groups, gamma=None, beta=None, mod=None, eps=1e-5):
+    L = _lib.load()
+    B, C = sums.shape[:2]
+    coef = torch.empty(B, C, 2, dtype=torch.float32, device="cuda")
+    _lib.check(L.i2v_op_norm_coeffs(P(sums), P(coef), B, C, V, groups, eps, P(gamma), P(beta), P(mod), S()), "op_norm_coeffs")
+    return coef
+
+
+def modulate(x_cl, coef, out_dims, up=(1, 1, 1), gb=None, r=None, coef2=None, act=0):
+    L = _lib.load()
+    B, C = x_cl.shape[0], x_cl.shape[-1]
+    T, H, W = out_dims
+    out = torch.empty(B, T, H, W, C, dtype=torch.float32, device="cuda")
+    _lib.check(L.i2v_op_modulate(P(x_cl), P(coef), P(gb), P(r), P(coef2), P(out), B, T, H, W, C, *up, act, S()), "op_modulate")
+    return out
+
+
+def linear(x, w, b, act=0):
+    L = _lib.load()
+    B, K = x.shape
+    N = w.shape[0]
+    y = torch.empty(B, N, dtype=torch.float32, device="cuda")
+    _lib.check(L.i2v_op_linear(P(x), P(w), P(b), P(y), B, K, N, act, S()), "op_linear")
+    return y
+
+
+def resize(img, H, W):
+    L = _lib.load()
+    B, C, H0, W0 = img.shape
+    out = torch.empty(B, H, W, C, dtype=torch.float32, device="cuda")
+    _lib.check(L.i2v_op_resize_bilinear(P(img), P(out), B, C, H0, W0, H, W, S()), "op_resize")
+    return out
+
+
+def maxpool(x_cl):
+    L = _lib.load()
+    B, H, W, C = x_cl.shape
+    Ho, Wo = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+    y = torch.empty(B, Ho, Wo, C, dtype=torch.float32, device="cuda")
+    _lib.check(L.i2v_op_maxpool3x3s2(P(x_cl), P(y), B, H, W, C, S()), "op_maxpool")
+    return y

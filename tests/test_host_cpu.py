@@ -1,0 +1,109 @@
+"""CPU-side checks: the C-ABI library loads and exports every declared symbol, host logic, loaders."""
+import os
+import re
+
+import pytest
+import torch
+
+from image2video_synthesis_using_cinns_b200 import lib, loader, synthetic
+from image2video_synthesis_using_cinns_b200.config import load_yaml
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    lib.build()
+    return lib.load()
+
+
+def test_library_exports_every_declared_symbol(built):
+    hdr = open(os.path.join(ROOT, "include", "i2v_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(i2v_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(lib.SIGNATURES), declared ^ set(lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(built, name), name
+    assert built.i2v_abi_version() == 1
+
+
+def test_create_rejects_bad_geometry(built):
+    assert not built.i2v_flow_create(20, 64, 63, 512, 2, None)       # zc not padded
+    assert b"flow_create" in built.i2v_last_error()
+    h = built.i2v_flow_create(20, 64, 64, 512, 2, None)
+    assert h
+    assert built.i2v_flow_workspace_bytes(h, 64) > 64 * 20 * 2048 * 4
+    built.i2v_flow_destroy(h)
+
+
+def test_no_cuda_device_fails_loudly(ckpt_cache):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from image2video_synthesis_using_cinns_b200.get_model import Model
+    mp = ckpt_cache(dataset="bair", seed=4, nf=16, n_flows=2, with_encoder=False)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        Model(mp, 16)
+
+
+def test_yaml_missing_keys_read_none(tmp_path):
+    p = tmp_path / "c.yaml"
+    p.write_text("Training:\n  bs: 3\nData:\n  img_size: 64\n")
+    c = load_yaml(str(p))
+    assert c.Training["control"] is None and c.Training.bs == 3 and c.Data["img_size"] == 64
+    assert c.Missing is None
+
+
+def test_pack_flow_layout_roundtrip():
+    """The packed flow tensors reproduce the MLPs: evaluate one coupling from the packed layout on the
+    CPU and compare with the state-dict evaluation."""
+    import oracle_torch as ot
+    gen = torch.Generator().manual_seed(2)
+    for control in (False, True):
+        cc = 64 + (30 if control else 0)
+        sd = synthetic.flow_state_dict(gen, 64, cc, 128, 2, 5, control)
+        t, cond_mode, zc_pad = loader.pack_flow(sd, 5, 64, cc, 128, 2, control)
+        assert zc_pad % 4 == 0 and cond_mode == [int(control and fl % 4 != 0) for fl in range(5)]
+        x = torch.randn(3, 32, generator=gen)
+        c = torch.randn(3, cc, generator=gen)
+        cp = torch.nn.functional.pad(c, (0, zc_pad - cc))
+        for fl in (0, 1, 4):
+            for i in (0, 1):
+                c1 = cp @ t["w1c"].reshape(5, 2, 256, zc_pad)[fl, i].t() + t["b1"].reshape(5, 2, 256)[fl, i]
+                h = torch.nn.functional.leaky_relu(c1 + (0 if cond_mode[fl] else x @ t["w1x"][fl, i].t()), 0.01)
+                for l in range(2):
+                    hs = torch.cat([h[:, n * 128:(n + 1) * 128] @ t["wh"][fl, i, l, n].t() for n in (0, 1)], 1)
+                    h = torch.nn.functional.leaky_relu(hs + t["bh"][fl, i, l], 0.01)
+                st = torch.cat([h[:, n * 128:(n + 1) * 128] @ t["wo"][fl, i, n * 32:(n + 1) * 32].t() for n in (0, 1)], 1)
+                st = st + t["bo"][fl, i]
+                ci = c if cond_mode[fl] else torch.cat((x, c), 1)
+                s = ot._mlp(sd, f"sub_layers.{fl}.coupling.s.{i}", ci)
+                tt = ot._mlp(sd, f"sub_layers.{fl}.coupling.t.{i}", ci)
+                assert torch.allclose(st[:, :32], s, atol=1e-5) and torch.allclose(st[:, 32:], tt, atol=1e-5)
+
+
+def test_pack_decoder_folds_spectral_norm_and_permutes_fc():
+    import oracle_torch as ot
+    gen = torch.Generator().manual_seed(3)
+    sd = synthetic.decoder_state_dict(gen, 16)
+    t = loader.pack_decoder(sd, 16)
+    w = ot.spectral_weight(sd, "g_1.conv_0")
+    assert torch.allclose(t["g_1.conv_0.w"], w.permute(2, 3, 4, 0, 1).reshape(27, w.shape[0], w.shape[1]), atol=1e-6)
+    z = torch.randn(2, 64, generator=gen)
+    ref = torch.nn.functional.linear(z, sd["fc.weight"], sd["fc.bias"]).reshape(2, 256, 1, 4, 4)
+    mine = torch.nn.functional.linear(z, t["fc.w"], t["fc.b"]).reshape(2, 1, 4, 4, 256)
+    assert torch.allclose(mine.permute(0, 4, 1, 2, 3), ref, atol=1e-6)
+
+
+def test_pack_embedder_bn_fold():
+    gen = torch.Generator().manual_seed(4)
+    sd = synthetic.embedder_state_dict(gen, 64, "bn")
+    t = loader.pack_embedder(sd, 64, "bn")
+    x = torch.randn(1, 3, 16, 16, generator=gen)
+    want = torch.nn.functional.batch_norm(
+        torch.nn.functional.conv2d(x, sd["model.conv1.weight"], None, 2, 3), sd["model.bn1.running_mean"],
+        sd["model.bn1.running_var"], sd["model.bn1.weight"], sd["model.bn1.bias"], False, 0.0, 1e-5)
+    w = t["conv1.w"].reshape(7, 7, 64, 3).permute(2, 3, 0, 1)
+    got = torch.nn.functional.conv2d(x, w, t["conv1.b"], 2, 3)
+    assert torch.allclose(got, want, atol=1e-5)
+    assert t["fc.w"].shape == (64, 2048)

@@ -1,0 +1,103 @@
+"""End-to-end parity through the drop-in ``get_model.Model`` surface: against the fixtures recorded
+from the real reference (tests/golden) and against the oracle on fresh inputs."""
+import pytest
+import torch
+
+import oracle_torch as ot
+from golden_util import GOLDEN_CASES, golden_inputs, load_golden, rel_inf
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4   # north_star: within 1e-4 relative fp32 on identical inputs / seeds
+
+
+def _model(mp, vid_length, transfer, **kw):
+    from image2video_synthesis_using_cinns_b200.get_model import Model
+    return Model(mp, vid_length, transfer=transfer, **kw)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_model_matches_reference_fixture(name, ckpt_cache):
+    meta, g = load_golden(name)
+    mp = ckpt_cache(**meta["ck"])
+    m = _model(mp, meta["vid_length"], meta["transfer"])
+    img = m.config.Data["img_size"]
+    x0, q, pos = golden_inputs(meta, img)
+    control = m.flow.control
+    cond = pos if control else None
+    embed = m.flow.embedder.encode(x0.cuda()).mode()
+    assert rel_inf(embed.cpu(), g["embed"]) < TOL
+    torch.manual_seed(meta["seed_residual"])
+    frames = m(x0.cuda(), cond)                       # residual drawn inside, on the CPU RNG (Q5)
+    kt, ks = meta["keep"]
+    assert list(frames.shape) == g["frames_shape"].tolist()
+    assert rel_inf(frames[:, ::kt, :, ::ks, ::ks].cpu(), g["frames"]) < TOL
+    assert rel_inf(frames.double().sum(dim=(2, 3, 4)).cpu(), g["frames_sum"]) < 1e-4
+    _, z = m.sample(x0, cond, residual=g["residual"], return_latent=True)
+    assert rel_inf(z.cpu(), g["z"]) < TOL
+    if "fwd_res" in g:
+        r, ld = m.flow(g["z"].cuda(), [x0.cuda()])
+        assert rel_inf(r.view(meta["B"], -1).cpu(), g["fwd_res"]) < TOL
+        assert rel_inf(ld.cpu(), g["fwd_logdet"]) < TOL
+    if meta["transfer"]:
+        seq, z_ref, mu, res, logdet = m.transfer(q, x0, return_latent=True)
+        assert rel_inf(mu.cpu(), g["t_mu"]) < TOL
+        assert rel_inf(res[:1].cpu(), g["t_res"]) < TOL and rel_inf(logdet.cpu(), g["t_logdet"]) < TOL
+        assert list(seq.shape) == g["t_frames_shape"].tolist()
+        assert rel_inf(seq[:, ::kt, :, ::ks, ::ks].cpu(), g["t_frames"]) < TOL
+
+
+@pytest.mark.parametrize("dataset,kw,B", [
+    ("bair", dict(nf=16, n_flows=5, spade_gain=1.0, enc_channels=[64, 32, 32, 64, 64]), 5),
+    ("dtdb_fire", dict(nf=16, n_flows=3, spade_gain=0.5, enc_channels=[64, 32, 32, 64, 64]), 2),
+    ("iper", dict(nf=32, n_flows=2, spade_gain=1.0, with_encoder=False), 3),
+])
+def test_model_matches_oracle_stagewise(dataset, kw, B, ckpt_cache):
+    mp = ckpt_cache(dataset=dataset, seed=21, **kw)
+    transfer = kw.get("with_encoder", True)
+    m = _model(mp, 16, transfer, micro_batch=2)       # micro_batch < B exercises the batch split
+    om = ot.OracleModel(mp, 16, transfer=transfer)
+    img = m.config.Data["img_size"]
+    g = torch.Generator().manual_seed(99)
+    x0 = torch.rand(B, 3, img, img, generator=g) * 2 - 1
+    z = torch.randn(B, 64, generator=g)
+    # embedder
+    assert rel_inf(m.flow.embedder.encode(x0.cuda()).mode().cpu(), om.embed(x0)) < TOL
+    # decoder alone, with per-block traces from the oracle
+    want = om.decode(x0, z)
+    got = m.decoder(x0.cuda(), z.cuda())
+    assert got.shape == want.shape
+    assert rel_inf(got.cpu(), want) < TOL
+    # full sampling path
+    residual = torch.randn(B, 64, generator=g)
+    wf, wz = om.forward(x0, residual, return_latent=True, batch_slice=False)
+    gf, gz = m.sample(x0, residual=residual, return_latent=True)
+    assert rel_inf(gz.cpu(), wz) < TOL and rel_inf(gf.cpu(), wf) < TOL
+    if transfer:
+        q = torch.rand(1, 16, 3, img, img, generator=g) * 2 - 1
+        ws = om.transfer(q, x0)
+        assert rel_inf(m.transfer(q, x0).cpu(), ws) < TOL
+
+
+def test_batch_slice_quirk_and_long_sequences(ckpt_cache):
+    """Q1: forward() slices the BATCH to vid_length rows and never trims T (get_model.py:75)."""
+    mp = ckpt_cache(dataset="bair", seed=4, nf=16, n_flows=2, with_encoder=False)
+    m = _model(mp, 3, False)
+    x0 = torch.rand(5, 3, 64, 64) * 2 - 1
+    assert m(x0).shape == (3, 16, 3, 64, 64)
+    m24 = _model(mp, 24, False)
+    torch.manual_seed(1)
+    out = m24(x0[:2])
+    assert out.shape == (2, 32, 3, 64, 64)            # two 16-frame decoder passes
+    # chunk 2 is the decoder applied to the last frame of chunk 1 with the same z (get_model.py:71-73)
+    torch.manual_seed(1)
+    seq, z = m24.sample(x0[:2], return_latent=True)
+    again = m24.decoder(seq[:, 15], z)
+    assert torch.equal(again, seq[:, 16:])
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from image2video_synthesis_using_cinns_b200 import lib
+    monkeypatch.setattr(lib, "_lib", None)
+    monkeypatch.setattr(lib, "LIB_PATH", "/nonexistent/libi2v_b200.so")
+    with pytest.raises(RuntimeError, match="no CPU"):
+        lib.load()

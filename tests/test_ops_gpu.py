@@ -1,0 +1,140 @@
+"""Kernel-level parity: each C-ABI op against the same op in fp32 PyTorch on the CPU."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import ops_util as ou
+from golden_util import rel_inf
+
+pytestmark = pytest.mark.gpu
+G = lambda s: torch.Generator().manual_seed(s)
+ACTS = {0: lambda v: v, 1: F.relu, 2: lambda v: F.leaky_relu(v, 0.2), 3: torch.tanh}
+
+CONV_CASES = [
+    # name, x shape (B,C,T,H,W), Cout, k, stride, pad
+    ("3x3x3_same", (2, 32, 4, 8, 8), 48, (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    ("3x3x3_wide", (1, 64, 2, 16, 16), 128, (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    ("1x1x1", (2, 64, 2, 4, 4), 32, (1, 1, 1), (1, 1, 1), (0, 0, 0)),
+    ("3x3x3_strided", (2, 16, 8, 16, 16), 32, (3, 3, 3), (2, 2, 2), (1, 1, 1)),
+    ("3x3x3_stride_s_only", (1, 16, 4, 16, 16), 16, (3, 3, 3), (1, 2, 2), (1, 1, 1)),
+    ("enc_conv1_3x7x7", (1, 3, 15, 32, 32), 64, (3, 7, 7), (2, 2, 2), (1, 3, 3)),
+    ("t1_head", (3, 32, 1, 4, 4), 32, (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    ("cout3_img", (1, 16, 4, 16, 16), 3, (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    ("ragged_m", (1, 16, 3, 5, 7), 20, (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+]
+
+
+@pytest.mark.parametrize("name,xs,cout,k,stride,pad", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv3d(name, xs, cout, k, stride, pad):
+    g = G(sum(map(ord, name)))
+    x = torch.randn(xs, generator=g)
+    w = torch.randn(cout, xs[1], *k, generator=g) / (xs[1] * k[0] * k[1] * k[2]) ** 0.5
+    b = torch.randn(cout, generator=g)
+    want = F.conv3d(x, w, b, stride, pad)
+    got = ou.from_cl(ou.conv(ou.to_cl(x), ou.taps(w), b.cuda(), None, k, stride, pad))
+    assert got.shape == want.shape
+    assert rel_inf(got, want) < 1e-5
+
+
+def test_conv2d_resnet_stem_and_spade():
+    g = G(5)
+    x = torch.randn(2, 3, 64, 64, generator=g)
+    w = torch.randn(64, 3, 7, 7, generator=g) * 0.1
+    want = F.conv2d(x, w, None, 2, 3)
+    got = ou.conv(ou.to_cl(x)[:, None], ou.taps(w), None, None, (1, 7, 7), (1, 2, 2), (0, 3, 3))[:, 0]
+    assert rel_inf(ou.from_cl(got), want) < 1e-5
+    w2 = torch.randn(128, 3, 3, 3, generator=g) * 0.2
+    b2 = torch.randn(128, generator=g)
+    want = F.leaky_relu(F.conv2d(x, w2, b2, 1, 1), 0.2)
+    got = ou.conv(ou.to_cl(x)[:, None], ou.taps(w2), b2.cuda(), None, (1, 3, 3), (1, 1, 1), (0, 1, 1), act=2)[:, 0]
+    assert rel_inf(ou.from_cl(got), want) < 1e-5
+    # strided 1x1 (resnet downsample) and strided 3x3
+    x3 = torch.randn(2, 64, 16, 16, generator=g)
+    w3 = torch.randn(128, 64, 1, 1, generator=g) * 0.1
+    got = ou.conv(ou.to_cl(x3)[:, None], ou.taps(w3), None, None, (1, 1, 1), (1, 2, 2), (0, 0, 0))[:, 0]
+    assert rel_inf(ou.from_cl(got), F.conv2d(x3, w3, None, 2)) < 1e-5
+    w4 = torch.randn(64, 64, 3, 3, generator=g) * 0.05
+    got = ou.conv(ou.to_cl(x3)[:, None], ou.taps(w4), None, None, (1, 3, 3), (1, 2, 2), (0, 1, 1))[:, 0]
+    assert rel_inf(ou.from_cl(got), F.conv2d(x3, w4, None, 2, 1)) < 1e-5
+
+
+@pytest.mark.parametrize("act", [0, 1, 2, 3])
+def test_conv_epilogue_residual_upsample_and_act(act):
+    g = G(11 + act)
+    x = torch.randn(2, 32, 4, 8, 8, generator=g)
+    w = torch.randn(16, 32, 3, 3, 3, generator=g) * 0.05
+    b = torch.randn(16, generator=g)
+    res = torch.randn(2, 16, 2, 4, 4, generator=g)
+    want = ACTS[act](F.conv3d(x, w, b, 1, 1) + F.interpolate(res, scale_factor=2.0))
+    got = ou.conv(ou.to_cl(x), ou.taps(w), b.cuda(), ou.to_cl(res), (3, 3, 3), (1, 1, 1), (1, 1, 1), res_up=(2, 2, 2), act=act)
+    assert rel_inf(ou.from_cl(got), want) < 1e-5
+
+
+def test_conv_frames_layout():
+    g = G(21)
+    x = torch.randn(2, 16, 4, 8, 8, generator=g)
+    w = torch.randn(3, 16, 3, 3, 3, generator=g) * 0.1
+    b = torch.randn(3, generator=g)
+    want = torch.tanh(F.conv3d(x, w, b, 1, 1)).transpose(1, 2)   # decoder.py:117-120
+    got = ou.conv(ou.to_cl(x), ou.taps(w), b.cuda(), None, (3, 3, 3), (1, 1, 1), (1, 1, 1), act=3, out_mode=1)
+    assert rel_inf(got.cpu(), want) < 1e-5
+
+
+@pytest.mark.parametrize("C,shape", [(64, (2, 4, 8, 8)), (256, (1, 1, 4, 4)), (16, (3, 16, 32, 32)), (2048, (2, 1, 2, 2))])
+def test_stats_groupnorm_instancenorm(C, shape):
+    g = G(C)
+    B, T, H, W = shape
+    x = torch.randn(B, C, T, H, W, generator=g) * 2 + 0.7
+    xc = ou.to_cl(x)
+    sums, V = ou.channel_stats(xc)
+    assert rel_inf(sums[..., 0].cpu(), x.double().sum(dim=(2, 3, 4))) < 1e-6
+    # GroupNorm(16, affine) -> ReLU
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    coef = ou.norm_coeffs(sums, V, 16, gamma.cuda(), beta.cuda())
+    got = ou.modulate(xc, coef, (T, H, W), act=1)
+    assert rel_inf(ou.from_cl(got), F.relu(F.group_norm(x, 16, gamma, beta, 1e-5))) < 2e-5
+    # InstanceNorm + AdaIN modulation + lrelu(0.2)
+    mod = torch.randn(B, 2 * C, generator=g)
+    coef = ou.norm_coeffs(sums, V, 0, mod=mod.cuda())
+    got = ou.modulate(xc, coef, (T, H, W), act=2)
+    want = F.leaky_relu(mod[:, :C].reshape(B, C, 1, 1, 1) * F.instance_norm(x, eps=1e-5) + mod[:, C:].reshape(B, C, 1, 1, 1), 0.2)
+    assert rel_inf(ou.from_cl(got), want) < 2e-5
+
+
+def test_modulate_spade_upsample_and_two_branch():
+    g = G(33)
+    B, C = 2, 32
+    x = torch.randn(B, C, 2, 4, 4, generator=g) + 0.3
+    gamma = torch.randn(B, C, 8, 8, generator=g) * 0.5
+    beta = torch.randn(B, C, 8, 8, generator=g) * 0.5
+    xu = F.interpolate(x, scale_factor=2.0)
+    want = F.leaky_relu(F.group_norm(xu, 16, eps=1e-5) * (1 + gamma.unsqueeze(2)) + beta.unsqueeze(2), 0.2)
+    sums, V = ou.channel_stats(ou.to_cl(x))
+    coef = ou.norm_coeffs(sums, V, 16)
+    gb = torch.cat((gamma, beta), 1).permute(0, 2, 3, 1).contiguous().cuda()
+    got = ou.modulate(ou.to_cl(x), coef, (4, 8, 8), up=(2, 2, 2), gb=gb, act=2)
+    assert rel_inf(ou.from_cl(got), want) < 2e-5
+    # relu(IN(a) + IN(b)) and relu(IN(a) + b)  (ResNet bottleneck tails)
+    a, b = torch.randn(B, C, 1, 8, 8, generator=g), torch.randn(B, C, 1, 8, 8, generator=g) * 3
+    sa, V = ou.channel_stats(ou.to_cl(a))
+    sb, _ = ou.channel_stats(ou.to_cl(b))
+    ca, cb = ou.norm_coeffs(sa, V, 0), ou.norm_coeffs(sb, V, 0)
+    got = ou.modulate(ou.to_cl(a), ca, (1, 8, 8), r=ou.to_cl(b), coef2=cb, act=1)
+    assert rel_inf(ou.from_cl(got), F.relu(F.instance_norm(a) + F.instance_norm(b))) < 2e-5
+    got = ou.modulate(ou.to_cl(a), ca, (1, 8, 8), r=ou.to_cl(b), act=1)
+    assert rel_inf(ou.from_cl(got), F.relu(F.instance_norm(a) + b)) < 2e-5
+
+
+def test_linear_resize_maxpool():
+    g = G(44)
+    x, w, b = torch.randn(5, 64, generator=g), torch.randn(300, 64, generator=g), torch.randn(300, generator=g)
+    assert rel_inf(ou.linear(x.cuda(), w.cuda(), b.cuda()).cpu(), F.linear(x, w, b)) < 1e-5
+    x, w = torch.randn(19, 8192, generator=g), torch.randn(128, 8192, generator=g) * 0.01
+    assert rel_inf(ou.linear(x.cuda(), w.cuda(), None).cpu(), F.linear(x, w)) < 1e-5
+    img = torch.rand(3, 3, 64, 64, generator=g) * 2 - 1
+    for s in (4, 8, 16, 32, 64):
+        want = F.interpolate(img, size=(s, s), mode="bilinear", align_corners=True)
+        assert rel_inf(ou.resize(img.cuda(), s, s).permute(0, 3, 1, 2).cpu(), want) < 1e-5
+    assert torch.equal(ou.resize(img.cuda(), 64, 64).permute(0, 3, 1, 2).cpu(), img)
+    x = torch.randn(2, 64, 32, 32, generator=g)
+    assert torch.equal(ou.from_cl(ou.maxpool(ou.to_cl(x))), F.max_pool2d(x, 3, 2, 1))
