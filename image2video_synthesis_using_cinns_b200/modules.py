@@ -99,18 +99,19 @@ class ConditionalFlow(_Native):
         self._register(self.L.i2v_flow_set_tensor, tensors)
 
     def _cond(self, embedding):
-        e = _f32c(embedding.reshape(embedding.shape[0], -1), self.device)
-        if e.shape[1] != self.cond_channels:
-            raise ValueError(f"embedding has {e.shape[1]} channels, flow expects {self.cond_channels}")
+        n = embedding.shape[0]
+        if embedding.numel() != n * self.cond_channels:
+            raise ValueError(f"embedding has {embedding.numel() // max(n, 1)} channels, flow expects {self.cond_channels}")
+        e = _f32c(embedding.reshape(n, self.cond_channels), self.device)
         if self.zc_pad != e.shape[1]:
             e = torch.nn.functional.pad(e, (0, self.zc_pad - e.shape[1]))
         return e
 
     def forward(self, x, embedding, reverse=False):
-        x2 = _f32c(x.reshape(x.shape[0], -1), self.device)
-        B = x2.shape[0]
-        if x2.shape[1] != self.in_channels:
-            raise ValueError(f"flow input has {x2.shape[1]} channels, expected {self.in_channels}")
+        B = x.shape[0]
+        if x.numel() != B * self.in_channels:
+            raise ValueError(f"flow input has {x.numel() // max(B, 1)} channels, expected {self.in_channels}")
+        x2 = _f32c(x.reshape(B, self.in_channels), self.device)
         if B == 0:
             out = x2.new_zeros(0, self.in_channels, 1, 1)
             return out if reverse else (out, x2.new_zeros(0))
