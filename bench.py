@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""Benchmark of the image->video sampling path (BASELINE.json metric: frames/sec, BAIR 64x64 seq16).
+
+    python bench.py --gpus 1 --steps K --warmup W                       # this framework on 1 B200
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...                                # reference algorithm on host cores
+
+A "step" is one pass of the sampling path (embedder -> inverse cINN -> 3-D conv decoder) over one
+batch of synthetic start frames with random-init weights in the reference's checkpoint format
+(BASELINE.json configs[1]: BAIR 64x64, seq_length 16, batch 64 per GPU, fp32 parity arithmetic).
+One JSON line is printed by rank 0:
+
+  value      frames/s with inputs resident in HBM (CUDA events, barrier+sync both sides, max over ranks;
+             N>1: per-GPU batch fixed = weak scaling, the all-gather of finished frames is inside)
+  e2e        same metric through the public API ``Model.forward``-style call with HOST buffers: pinned
+             H2D of start frames + residual and D2H of the frames inside the timed region
+  roofline   the dominant kernel family (decoder/encoder convolutions): algorithmic FLOPs of the conv
+             launches of the timed steps / their summed CUDA-event time, against the measured peak in
+             MEASURED_PEAKS.json
+  cpu_baseline  the oracle port (oracle/oracle_torch.py, = the reference's PyTorch arithmetic) timed on
+             the host cores on a bounded sample (rank 0, N=1 only)
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "frames/sec (BAIR 64x64 seq16)"
+UNIT = "frames/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--dataset", default="bair")
+    ap.add_argument("--batch", type=int, default=64, help="start frames per GPU per step")
+    ap.add_argument("--seq-length", type=int, default=16)
+    ap.add_argument("--micro-batch", type=int, default=16)
+    ap.add_argument("--conv-engine", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ckpt-dir", default=None, help="reuse / create synthetic checkpoints here")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------ helpers
+def synthetic_ckpt(args, rank, barrier):
+    """Full-size synthetic checkpoints in the reference layout (rank 0 writes, everyone reads)."""
+    from image2video_synthesis_using_cinns_b200 import synthetic
+    base = args.ckpt_dir or os.path.join(tempfile.gettempdir(), f"i2v_bench_ckpt_{args.dataset}")
+    done = os.path.join(base, ".done")
+    if rank == 0 and not os.path.exists(done):
+        synthetic.write_synthetic_checkpoints(base, args.dataset, seed=0, with_encoder=False)
+        open(done, "w").close()
+    barrier()
+    return os.path.join(base, "stage2") + "/"
+
+
+def make_inputs(total_batch, img, z_dim):
+    g = torch.Generator().manual_seed(1234)
+    x0 = torch.rand(total_batch, 3, img, img, generator=g) * 2 - 1     # SURVEY 8d synthetic inputs
+    torch.manual_seed(4321)
+    residual = torch.randn(total_batch, z_dim)                          # CPU RNG like get_model.py:59
+    return x0, residual
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i] == "Active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def conv_flops_per_sample(dataset):
+    """Nominal conv FLOPs per 16-frame sample -- for the log only."""
+    return {"bair": 384.8e9, "iper": 384.8e9}.get(dataset, 137.4e9)
+
+
+def cpu_reference_rate(args, mp, n_calls=3, warm=1):
+    """The reference's arithmetic (oracle port) on the host cores: B=1 calls, bounded sample."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_torch as ot     # CPU baseline leg only
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    om = ot.OracleModel(mp, args.seq_length, transfer=False)
+    img = om.opt["Data"]["img_size"]
+    x0, residual = make_inputs(1, img, om.z_dim)
+    times = []
+    for i in range(warm + n_calls):
+        t0 = time.perf_counter()
+        out = om.forward(x0, residual, batch_slice=False)
+        dt = time.perf_counter() - t0
+        if i >= warm:
+            times.append(dt)
+    frames = out.shape[0] * out.shape[1]
+    med = sorted(times)[len(times) // 2]
+    return frames / med, cores, f"{n_calls} x Model.forward(B=1, {args.dataset} {img}x{img}, seq {args.seq_length}) after {warm} warm-up, median"
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    mp = synthetic_ckpt(args, 0, lambda: None)
+    t0 = time.perf_counter()
+    fps, cores, sample = cpu_reference_rate(args, mp, n_calls=max(1, args.steps), warm=max(1, min(args.warmup, 2)))
+    from image2video_synthesis_using_cinns_b200.config import DATASETS
+    img = DATASETS[args.dataset]["img_size"]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * 16 / fps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic start frames, random-init weights (reference checkpoint format)",
+        "config": {"workload": f"{args.dataset.upper()} {img}x{img} seq_length={args.seq_length}, batch=1 per call on host cores "
+                               "(reference PyTorch arithmetic = oracle port; the Python reference tree cannot travel to the GPU box)"},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ B200 arm
+def run_b200(args):
+    import torch.distributed as dist
+    from image2video_synthesis_using_cinns_b200 import lib
+    from image2video_synthesis_using_cinns_b200.get_model import Model
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
+
+    L = lib.load()
+    mp = synthetic_ckpt(args, rank, barrier)
+    model = Model(mp, args.seq_length, device=dev, micro_batch=args.micro_batch, conv_engine=args.conv_engine)
+    img = model.config.Data["img_size"]
+    B = args.batch
+    x0_all, res_all = make_inputs(B * world, img, model.z_dim)        # one global draw, sliced per rank
+    x0_h = x0_all[rank * B:(rank + 1) * B].contiguous().pin_memory()
+    res_h = res_all[rank * B:(rank + 1) * B].contiguous().pin_memory()
+    x0_d, res_d = x0_h.to(dev), res_h.to(dev)
+    passes = -(-args.seq_length // 16)
+    T = 16 * passes
+    gathered = torch.empty(world * B, T, 3, img, img, device=dev) if world > 1 else None
+    out_h = torch.empty(B, T, 3, img, img).pin_memory()
+
+    def step_device():
+        seq = model.sample(x0_d, residual=res_d)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, seq.contiguous())
+        return seq
+
+    def step_e2e():
+        x = x0_h.to(dev, non_blocking=True)
+        r = res_h.to(dev, non_blocking=True)
+        seq = model.sample(x, residual=r)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, seq.contiguous())
+        out_h.copy_(seq, non_blocking=True)
+        return seq
+
+    def timed(fn, steps, profile=False):
+        barrier()
+        torch.cuda.synchronize()
+        n0 = L.i2v_launch_count()
+        if profile:
+            L.i2v_prof_enable(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        prof = None
+        if profile:
+            arr = [(ctypes.c_double * 5)(), (ctypes.c_double * 5)(), (ctypes.c_double * 5)(), (ctypes.c_longlong * 5)()]
+            lib.check(L.i2v_prof_collect(*arr), "prof_collect")
+            L.i2v_prof_enable(0)
+            prof = [list(a) for a in arr]
+        launches = L.i2v_launch_count() - n0
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, launches, prof
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms, launches, prof = timed(step_device, args.steps, profile=True)
+    clocks = sampler.stop() if sampler else None
+    step_e2e()
+    ms_e2e, _, _ = timed(step_e2e, args.steps)
+
+    frames_per_step = world * B * T
+    value = frames_per_step * args.steps / (ms / 1e3)
+    e2e = frames_per_step * args.steps / (ms_e2e / 1e3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak_tf = peaks.get("bf16_tflops_sustained", 1590.0 * 1441.7 / 1690.8)
+        peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback (B200_PROFILING.md)"
+        cms, cfl, cby, cn = prof
+        names = ["conv", "stats", "modulate", "flow", "other"]
+        fam = {names[i]: {"ms": cms[i] / args.steps, "launches": cn[i] / args.steps,
+                          "tflops": (cfl[i] / (cms[i] * 1e-3) / 1e12) if cms[i] > 0 else 0.0,
+                          "gbs": (cby[i] / (cms[i] * 1e-3) / 1e9) if cms[i] > 0 else 0.0} for i in range(5)}
+        achieved = fam["conv"]["tflops"]
+        roofline = {"bound": "tensor", "kernel": "conv (decoder/embedder implicit-GEMM convolutions, all launches of the timed steps)",
+                    "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                    "peak_source": peak_src, "traffic": None,
+                    "share_of_step": fam["conv"]["ms"] / (ms / args.steps), "families": fam}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic start frames U[-1,1], random-init weights in the reference checkpoint format",
+            "config": {"workload": f"{args.dataset.upper()} {img}x{img} seq_length={args.seq_length}, batch={B} per GPU "
+                                   f"(global {B * world}), fp32 parity arithmetic, conv_engine={args.conv_engine}, micro_batch={args.micro_batch}",
+                       "l2": "per-step working set (activations+weights, GBs) exceeds the 126 MB L2; no explicit flush",
+                       "parallelism": f"batch-sharded x{world}, one all-gather of frames" if world > 1 else "single GPU"},
+            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": world * (x0_h.numel() + res_h.numel()) * 4,
+                    "d2h_bytes_per_step": world * out_h.numel() * 4},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            fps, cores, sample = cpu_reference_rate(args, mp)
+            line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

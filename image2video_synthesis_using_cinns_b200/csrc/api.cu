@@ -11,10 +11,40 @@
 #include "../../include/i2v_b200.h"
 #include "common.cuh"
 #include "kernels.h"
+#include "prof.h"
 
 namespace i2v {
 
 static thread_local char g_err[1024] = "";
+
+// ------------------------------------------------------------------ launch accounting / timing
+namespace {
+struct ProfRec { cudaEvent_t a, b; int cat; double flops, bytes; };
+struct ProfState {
+    bool on = false;
+    long long launches[PROF_NCAT] = {0, 0, 0, 0, 0};
+    std::vector<ProfRec> recs;
+    std::vector<cudaEvent_t> pool;
+    size_t pool_used = 0;
+    cudaEvent_t get() {
+        if (pool_used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+        return pool[pool_used++];
+    }
+};
+ProfState g_prof;
+}  // namespace
+
+ProfScope::ProfScope(int cat, double flops, double bytes, cudaStream_t stream) : idx_(-1), stream_(stream) {
+    g_prof.launches[cat]++;
+    if (!g_prof.on) return;
+    ProfRec r{g_prof.get(), g_prof.get(), cat, flops, bytes};
+    cudaEventRecord(r.a, stream);
+    idx_ = (int)g_prof.recs.size();
+    g_prof.recs.push_back(r);
+}
+ProfScope::~ProfScope() {
+    if (idx_ >= 0) cudaEventRecord(g_prof.recs[idx_].b, stream_);
+}
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -121,6 +151,29 @@ extern "C" {
 
 int i2v_abi_version(void) { return I2V_ABI_VERSION; }
 const char* i2v_last_error(void) { return i2v::g_err; }
+
+long long i2v_launch_count(void) {
+    long long n = 0;
+    for (int c = 0; c < PROF_NCAT; ++c) n += g_prof.launches[c];
+    return n;
+}
+void i2v_prof_enable(int on) {
+    g_prof.on = on != 0;
+    g_prof.recs.clear();
+    g_prof.pool_used = 0;
+}
+int i2v_prof_collect(double* ms, double* flops, double* bytes, long long* launches) {
+    for (int c = 0; c < PROF_NCAT; ++c) { ms[c] = 0; flops[c] = 0; bytes[c] = 0; launches[c] = 0; }
+    for (auto& r : g_prof.recs) {
+        I2V_CHECK_CUDA(cudaEventSynchronize(r.b));
+        float t = 0.f;
+        I2V_CHECK_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+        ms[r.cat] += t; flops[r.cat] += r.flops; bytes[r.cat] += r.bytes; launches[r.cat]++;
+    }
+    g_prof.recs.clear();
+    g_prof.pool_used = 0;
+    return 0;
+}
 
 i2v_flow* i2v_flow_create(int n_flows, int d, int zc, int hidden, int depth, const unsigned char* cond_mode) {
     if (n_flows <= 0 || n_flows > 64 || d <= 0 || d % 2 || zc <= 0 || zc % 4 || hidden <= 0 || hidden % 4 || hidden > 512 ||
@@ -294,7 +347,13 @@ void i2v_embedder_destroy(i2v_embedder* h) { delete h; }
 struct i2v_decoder {
     int nf, z_dim, us[2], ut[2], engine;
     TensorTable tt;
+    std::unordered_map<std::string, double> scalars;   // host-side per-layer constants (split scales)
 };
+
+// Activations entering a tensor-core conv are split as fp16(ACT_SPLIT_SCALE * x): they are normalised /
+// modulated values of O(1); 16 keeps |x| < 4094 representable and pushes the fp16 subnormal floor of
+// the low word to ~4e-9.  loader.py folds 1/(ACT_SPLIT_SCALE * s_w) into each layer's "<conv>.ws".
+static constexpr float ACT_SPLIT_SCALE = 16.f;
 
 struct DecBlock { const char* name; int cin, cout, ut, uh, uw; };
 
@@ -365,6 +424,37 @@ static int decoder_run(const i2v_decoder* m, const float* img, const float* z, f
 
     const int eng = m->engine;
     auto G = [&](const std::string& n, size_t e) { return m->tt.get(n, e); };
+    const bool tc = eng >= 1;
+    I2V_REQUIRE(!tc || m->nf % 16 == 0, "decoder: the tensor-core engine needs channel_factor %% 16 == 0 (got %d)", m->nf);
+    // Tensor-core conv on split fp16 operands: x lives in `xbuf` as (hi | lo) halves of n_in elements each.
+    auto conv_tc = [&](const std::string& wname, const float* xbuf, size_t n_in, const float* bias, const float* res, float* y,
+                       int Bc, int Tc, int Hc_, int Wc_, int cin_, int cout_, int kt, int kh, int kw, int rut, int ruh, int ruw,
+                       int act, int out_mode) -> int {
+        const int cpad = (cout_ + 15) / 16 * 16;
+        const size_t wn = (size_t)kt * kh * kw * cpad * cin_;
+        const __half* wh = m->tt.get<__half>(wname + ".wh", wn);
+        const __half* wl = m->tt.get<__half>(wname + ".wl", wn);
+        const float* ws = m->tt.get(wname + ".ws", 1);
+        if (!wh || !wl || !ws) return -3;
+        ConvTcArgs a;
+        a.x_hi = reinterpret_cast<const __half*>(xbuf); a.x_lo = a.x_hi + n_in;
+        a.w_hi = wh; a.w_lo = wl; a.scale_ptr = ws; a.bias = bias; a.res = res; a.y = y;
+        a.B = Bc; a.T = Tc; a.H = Hc_; a.W = Wc_; a.Cin = cin_; a.Cout = cout_; a.cout_pad = cpad;
+        a.kt = kt; a.kh = kh; a.kw = kw; a.res_ut = rut; a.res_uh = ruh; a.res_uw = ruw; a.act = act; a.out_mode = out_mode;
+        a.terms = eng == 1 ? 3 : 1;
+        return launch_conv_tc(a, s);
+    };
+    // fused modulate pass writing either fp32 (SIMT engine) or the fp16 split (tensor-core engine)
+    auto modulate_to = [&](const float* x_, const float* coef_, const float* gb_, float* out_, size_t n_out, int Bc, int Tc,
+                           int Hc_, int Wc_, int C_, int ut_, int uh_, int uw_, int act) -> int {
+        ModArgs ma;
+        ma.x = x_; ma.coef = coef_; ma.gb = gb_; ma.r = nullptr; ma.coef2 = nullptr; ma.out = out_;
+        ma.B = Bc; ma.T = Tc; ma.H = Hc_; ma.W = Wc_; ma.C = C_; ma.ut = ut_; ma.uh = uh_; ma.uw = uw_; ma.act = act;
+        if (tc) {
+            ma.out_hi = reinterpret_cast<__half*>(out_); ma.out_lo = ma.out_hi + n_out; ma.split_scale = ACT_SPLIT_SCALE;
+        }
+        return launch_modulate(ma, s);
+    };
 
     // fc: rows pre-permuted at load so the output is already [B,1,4,4,C] channels-last
     const int C0 = blk[0].cin;
@@ -387,50 +477,85 @@ static int decoder_run(const i2v_decoder* m, const float* img, const float* z, f
         // SPADE maps (normalization_layer.py:20-23)
         I2V_PTR(scw, G(nm + ".spade.conv.w", (size_t)9 * 128 * 3));
         I2V_PTR(scb, G(nm + ".spade.conv.b", 128));
-        I2V_PTR(sgw, G(nm + ".spade.gb.w", (size_t)9 * 2 * cin * 128));
         I2V_PTR(sgb, G(nm + ".spade.gb.b", (size_t)2 * cin));
         I2V_TRY(launch_resize_bilinear_nchw_to_nhwc(img, imgr, B, 3, H, W, Hc, Wc, s));
-        I2V_TRY(conv(0, imgr, scw, scb, nullptr, sh, B, 1, Hc, Wc, 3, 128, 1, 3, 3, 1, 1, 1, 0, 1, 1, 1, 1, 1, ACT_LRELU02, 0, s));
-        I2V_TRY(conv(eng, sh, sgw, sgb, nullptr, gb, B, 1, Hc, Wc, 128, 2 * cin, 1, 3, 3, 1, 1, 1, 0, 1, 1, 1, 1, 1, ACT_NONE, 0, s));
+        if (!tc) {
+            I2V_PTR(sgw, G(nm + ".spade.gb.w", (size_t)9 * 2 * cin * 128));
+            I2V_TRY(conv(0, imgr, scw, scb, nullptr, sh, B, 1, Hc, Wc, 3, 128, 1, 3, 3, 1, 1, 1, 0, 1, 1, 1, 1, 1, ACT_LRELU02, 0, s));
+            I2V_TRY(conv(0, sh, sgw, sgb, nullptr, gb, B, 1, Hc, Wc, 128, 2 * cin, 1, 3, 3, 1, 1, 1, 0, 1, 1, 1, 1, 1, ACT_NONE, 0, s));
+        } else {
+            // 3->128 conv stays on the SIMT engine (Cin = 3) but emits the fp16 split the gamma|beta conv consumes
+            auto it = m->scalars.find(nm + ".spade.sa");
+            I2V_REQUIRE(it != m->scalars.end(), "decoder: scalar '%s.spade.sa' was not registered", nm.c_str());
+            const size_t nsh = (size_t)B * Hc * Wc * 128;
+            ConvArgs ca;
+            ca.x = imgr; ca.w = scw; ca.bias = scb; ca.res = nullptr; ca.y = nullptr;
+            ca.B = B; ca.Ti = 1; ca.Hi = Hc; ca.Wi = Wc; ca.Cin = 3; ca.To = 1; ca.Ho = Hc; ca.Wo = Wc; ca.Cout = 128;
+            ca.kt = 1; ca.kh = 3; ca.kw = 3; ca.st = ca.sh = ca.sw = 1; ca.pt = 0; ca.ph = ca.pw = 1;
+            ca.res_ut = ca.res_uh = ca.res_uw = 1; ca.act = ACT_LRELU02; ca.out_mode = 0;
+            ca.y_hi = reinterpret_cast<__half*>(sh); ca.y_lo = ca.y_hi + nsh; ca.split_scale = (float)it->second;
+            I2V_TRY(launch_conv_simt(ca, s));
+            I2V_TRY(conv_tc(nm + ".spade.gb", sh, nsh, sgb, nullptr, gb, B, 1, Hc, Wc, 128, 2 * cin, 1, 3, 3, 1, 1, 1, ACT_NONE, 0));
+        }
         // a0 = lrelu(GN16(x) * (1+gamma) + beta), upsampled on the fly
         int groups = 16;
         while (cin % groups) --groups;
         I2V_TRY(launch_norm_coeffs(sums, coef, B, cin, vlow, groups, 1e-5f, nullptr, nullptr, nullptr, s));
-        I2V_TRY(modulate(x, coef, gb, nullptr, nullptr, bufp, B, T, Hc, Wc, cin, k.ut, k.uh, k.uw, ACT_LRELU02, s));
+        I2V_TRY(modulate_to(x, coef, gb, bufp, (size_t)B * vhi * cin, B, T, Hc, Wc, cin, k.ut, k.uh, k.uw, ACT_LRELU02));
         // shortcut at low resolution
         const float* xs = x;
         if (cin != cout) {
             I2V_PTR(nsw, G(nm + ".norm_s.w", cin));
             I2V_PTR(nsb, G(nm + ".norm_s.b", cin));
-            I2V_PTR(csw, G(nm + ".conv_s.w", (size_t)cout * cin));
             I2V_TRY(launch_norm_coeffs(sums, coefs, B, cin, vlow, 16, 1e-5f, nsw, nsb, nullptr, s));
-            I2V_TRY(modulate(x, coefs, nullptr, nullptr, nullptr, lowin, B, Tl, Hl, Wl, cin, 1, 1, 1, ACT_NONE, s));
-            I2V_TRY(conv(eng, lowin, csw, nullptr, nullptr, lowout, B, Tl, Hl, Wl, cin, cout, 1, 1, 1, 1, 1, 1, 0, 0, 0, 1, 1, 1,
-                         ACT_NONE, 0, s));
+            I2V_TRY(modulate_to(x, coefs, nullptr, lowin, (size_t)B * vlow * cin, B, Tl, Hl, Wl, cin, 1, 1, 1, ACT_NONE));
+            if (!tc) {
+                I2V_PTR(csw, G(nm + ".conv_s.w", (size_t)cout * cin));
+                I2V_TRY(conv(0, lowin, csw, nullptr, nullptr, lowout, B, Tl, Hl, Wl, cin, cout, 1, 1, 1, 1, 1, 1, 0, 0, 0, 1, 1, 1,
+                             ACT_NONE, 0, s));
+            } else {
+                I2V_TRY(conv_tc(nm + ".conv_s", lowin, (size_t)B * vlow * cin, nullptr, nullptr, lowout, B, Tl, Hl, Wl, cin, cout, 1, 1, 1,
+                                1, 1, 1, ACT_NONE, 0));
+            }
             xs = lowout;
         }
         // dx = conv_0(a0)
-        I2V_PTR(w0, G(nm + ".conv_0.w", (size_t)27 * cmid * cin));
         I2V_PTR(b0, G(nm + ".conv_0.b", cmid));
-        I2V_TRY(conv(eng, bufp, w0, b0, nullptr, bufd, B, T, Hc, Wc, cin, cmid, 3, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, ACT_NONE, 0, s));
+        if (!tc) {
+            I2V_PTR(w0, G(nm + ".conv_0.w", (size_t)27 * cmid * cin));
+            I2V_TRY(conv(0, bufp, w0, b0, nullptr, bufd, B, T, Hc, Wc, cin, cmid, 3, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, ACT_NONE, 0, s));
+        } else {
+            I2V_TRY(conv_tc(nm + ".conv_0", bufp, (size_t)B * vhi * cin, b0, nullptr, bufd, B, T, Hc, Wc, cin, cmid, 3, 3, 3, 1, 1, 1,
+                            ACT_NONE, 0));
+        }
         // a1 = lrelu(AdaIN(dx, z))
         I2V_PTR(aw, G(nm + ".adain.w", (size_t)2 * cmid * zd));
         I2V_PTR(ab, G(nm + ".adain.b", (size_t)2 * cmid));
         I2V_TRY(launch_linear(z, aw, ab, mod, B, zd, 2 * cmid, ACT_NONE, s));
         I2V_TRY(launch_channel_stats(bufd, sums, B, vhi, cmid, s));
         I2V_TRY(launch_norm_coeffs(sums, coef, B, cmid, vhi, 0, 1e-5f, nullptr, nullptr, mod, s));
-        I2V_TRY(modulate(bufd, coef, nullptr, nullptr, nullptr, bufp, B, T, Hc, Wc, cmid, 1, 1, 1, ACT_LRELU02, s));
+        I2V_TRY(modulate_to(bufd, coef, nullptr, bufp, (size_t)B * vhi * cmid, B, T, Hc, Wc, cmid, 1, 1, 1, ACT_LRELU02));
         // out = conv_1(a1) + up(xs)
-        I2V_PTR(w1, G(nm + ".conv_1.w", (size_t)27 * cout * cmid));
         I2V_PTR(b1, G(nm + ".conv_1.b", cout));
-        I2V_TRY(conv(eng, bufp, w1, b1, xs, xn, B, T, Hc, Wc, cmid, cout, 3, 3, 3, 1, 1, 1, 1, 1, 1, k.ut, k.uh, k.uw, ACT_NONE, 0, s));
+        if (!tc) {
+            I2V_PTR(w1, G(nm + ".conv_1.w", (size_t)27 * cout * cmid));
+            I2V_TRY(conv(0, bufp, w1, b1, xs, xn, B, T, Hc, Wc, cmid, cout, 3, 3, 3, 1, 1, 1, 1, 1, 1, k.ut, k.uh, k.uw, ACT_NONE, 0, s));
+        } else {
+            I2V_TRY(conv_tc(nm + ".conv_1", bufp, (size_t)B * vhi * cmid, b1, xs, xn, B, T, Hc, Wc, cmid, cout, 3, 3, 3, k.ut, k.uh, k.uw,
+                            ACT_NONE, 0));
+        }
         float* t = x; x = xn; xn = t;
     }
     // frames = tanh(conv_img(lrelu(x)))  written as [B,T,3,H,W]
-    I2V_PTR(wi, G("conv_img.w", (size_t)27 * 3 * m->nf));
     I2V_PTR(bi, G("conv_img.b", 3));
-    I2V_TRY(modulate(x, nullptr, nullptr, nullptr, nullptr, bufp, B, T, Hc, Wc, m->nf, 1, 1, 1, ACT_LRELU02, s));
-    I2V_TRY(conv(eng, bufp, wi, bi, nullptr, frames, B, T, Hc, Wc, m->nf, 3, 3, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, ACT_TANH, 1, s));
+    I2V_TRY(modulate_to(x, nullptr, nullptr, bufp, (size_t)B * T * Hc * Wc * m->nf, B, T, Hc, Wc, m->nf, 1, 1, 1, ACT_LRELU02));
+    if (!tc) {
+        I2V_PTR(wi, G("conv_img.w", (size_t)27 * 3 * m->nf));
+        I2V_TRY(conv(0, bufp, wi, bi, nullptr, frames, B, T, Hc, Wc, m->nf, 3, 3, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, ACT_TANH, 1, s));
+    } else {
+        I2V_TRY(conv_tc("conv_img", bufp, (size_t)B * T * Hc * Wc * m->nf, bi, nullptr, frames, B, T, Hc, Wc, m->nf, 3, 3, 3, 3, 1, 1, 1,
+                        ACT_TANH, 1));
+    }
     return 0;
 }
 
@@ -442,6 +567,11 @@ i2v_decoder* i2v_decoder_create(int nf, int z_dim, const int us[2], const int ut
     return h;
 }
 int i2v_decoder_set_tensor(i2v_decoder* h, const char* n, const void* p, size_t b) { return h ? h->tt.set(n, p, b) : -1; }
+int i2v_decoder_set_scalar(i2v_decoder* h, const char* n, double v) {
+    I2V_REQUIRE(h && n, "decoder_set_scalar: null argument");
+    h->scalars[n] = v;
+    return 0;
+}
 size_t i2v_decoder_workspace_bytes(const i2v_decoder* h, int batch, int height, int width) {
     Arena ar(nullptr, 0, true);
     if (decoder_run(h, nullptr, nullptr, nullptr, batch, height, width, ar, nullptr, true)) return 0;
@@ -580,6 +710,27 @@ int i2v_op_conv(const float* x, const float* w, const float* bias, const float* 
     I2V_REQUIRE(x && w && y, "op_conv: null argument");
     return conv(engine, x, w, bias, res, y, B, Ti, Hi, Wi, Cin, Cout, kt, kh, kw, st, sh, sw, pt, ph, pw, rut, ruh, ruw, act, out_mode,
                 static_cast<cudaStream_t>(stream));
+}
+int i2v_op_conv_tc(const float* x, const float* w, const float* bias, const float* res, float* y, int B, int T, int H, int W, int Cin,
+                   int Cout, int cout_pad, int kt, int kh, int kw, int rut, int ruh, int ruw, int act, int out_mode, int terms,
+                   float scale_a, float scale_w, void* ws, size_t ws_bytes, void* stream) {
+    I2V_REQUIRE(x && w && y && ws, "op_conv_tc: null argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t nx = (size_t)B * T * H * W * Cin, nw = (size_t)kt * kh * kw * cout_pad * Cin;
+    Arena ar(ws, ws_bytes, false);
+    __half* xh = ar.take<__half>(nx); __half* xl = ar.take<__half>(nx);
+    __half* wh = ar.take<__half>(nw); __half* wl = ar.take<__half>(nw);
+    float* sc = ar.take<float>(1);
+    I2V_REQUIRE(ar.ok(), "op_conv_tc: workspace too small (%zu needed)", ar.peak);
+    I2V_TRY(launch_split_fp16(x, xh, xl, scale_a, (long long)nx, s));
+    I2V_TRY(launch_split_fp16(w, wh, wl, scale_w, (long long)nw, s));
+    const float inv = 1.f / (scale_a * scale_w);
+    I2V_CHECK_CUDA(cudaMemcpyAsync(sc, &inv, sizeof(float), cudaMemcpyHostToDevice, s));
+    ConvTcArgs a;
+    a.x_hi = xh; a.x_lo = xl; a.w_hi = wh; a.w_lo = wl; a.scale_ptr = sc; a.bias = bias; a.res = res; a.y = y;
+    a.B = B; a.T = T; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.cout_pad = cout_pad; a.kt = kt; a.kh = kh; a.kw = kw;
+    a.res_ut = rut; a.res_uh = ruh; a.res_uw = ruw; a.act = act; a.out_mode = out_mode; a.terms = terms;
+    return launch_conv_tc(a, s);
 }
 int i2v_op_channel_stats(const float* x, double* sums, int B, int64_t V, int C, void* stream) {
     return launch_channel_stats(x, sums, B, V, C, static_cast<cudaStream_t>(stream));

@@ -14,8 +14,11 @@
 // GeneratorBlock lives at the pre-upsample resolution, decoder.py:40,102-114), activation.
 //
 // Tile 128x64x16, 256 threads, 8x4 outputs per thread, register-prefetch double buffering.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "kernels.h"
+#include "prof.h"
 
 namespace i2v {
 
@@ -176,7 +179,16 @@ __global__ void __launch_bounds__(NT, 2) conv_simt_kernel(const ConvArgs a) {
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[j] = apply_act(v[j], a.act);
-        if (a.out_mode == 0) {
+        if (a.y_hi != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (nbase + j < a.Cout) {
+                    const float f = v[j] * a.split_scale;
+                    const __half hh = __float2half_rn(f);
+                    a.y_hi[m * a.Cout + nbase + j] = hh;
+                    a.y_lo[m * a.Cout + nbase + j] = __float2half_rn(f - __half2float(hh));
+                }
+        } else if (a.out_mode == 0) {
             float* dst = a.y + m * a.Cout + nbase;
             if (vec_store) {
                 *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
@@ -201,6 +213,9 @@ int launch_conv_simt(const ConvArgs& a, cudaStream_t stream) {
     I2V_REQUIRE(M > 0 && a.Cout > 0 && a.Cin > 0, "conv_simt: empty problem");
     I2V_REQUIRE(a.res == nullptr || (a.To % a.res_ut == 0 && a.Ho % a.res_uh == 0 && a.Wo % a.res_uw == 0),
                 "conv_simt: residual upsample factors must divide the output size");
+    const double K_ = (double)a.kt * a.kh * a.kw * a.Cin;
+    ProfScope ps(PROF_CONV, 2.0 * (double)M * a.Cout * K_,
+                 4.0 * ((double)a.B * a.Ti * a.Hi * a.Wi * a.Cin + (double)M * a.Cout + K_ * a.Cout), stream);
     dim3 grid(ceil_div(M, BM), ceil_div(a.Cout, BN));
     if (a.Cin % 16 == 0)
         conv_simt_kernel<true><<<grid, NT, 0, stream>>>(a);

@@ -27,6 +27,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "prof.h"
 
 namespace i2v {
 
@@ -356,6 +357,8 @@ int launch_flow(const FlowWeights& fw, const float* in, const float* cond, float
         ka.reverse = reverse ? 1 : 0;
         for (int i = 0; i < 64; ++i) ka.cond_mode[i] = (i < fw.n_flows && fw.cond_mode) ? fw.cond_mode[i] : 0;
         I2V_CHECK_CUDA(cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned), stream));
+        const double wbytes = 4.0 * fw.n_flows * 2 * ((double)2 * H * fw.half + (double)fw.depth * 2 * H * H + (double)2 * fw.half * H);
+        ProfScope ps(PROF_FLOW, 2.0 * rows * wbytes / 4.0, wbytes + 4.0 * rows * (2.0 * d + n1), stream);
         void* kargs[] = {&ka};
         I2V_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)flow_kernel, dim3(sms), dim3(FLOW_THREADS), kargs, smem,
                                                    stream));

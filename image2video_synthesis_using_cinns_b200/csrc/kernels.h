@@ -1,5 +1,6 @@
 // Internal kernel launchers (C++); the public C-ABI lives in include/i2v_b200.h.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <cstddef>
 
@@ -18,8 +19,25 @@ struct ConvArgs {
     int res_ut, res_uh, res_uw;
     int act;        // i2v::Act
     int out_mode;   // 0: [B,To,Ho,Wo,Cout]   1: [B,To,Cout,Ho,Wo] (video frames)
+    // optional fp16 split of the result for the tensor-core engine: hi = fp16(s*v), lo = fp16(s*v - hi)
+    __half* y_hi = nullptr; __half* y_lo = nullptr; float split_scale = 1.f;
 };
 int launch_conv_simt(const ConvArgs& a, cudaStream_t stream);
+
+// Tensor-core engine (conv_tc.cu): stride-1 'same' convolution on pre-split fp16 operands.
+struct ConvTcArgs {
+    const __half* x_hi; const __half* x_lo;   // [B,T,H,W,Cin]   activations * s_a, split
+    const __half* w_hi; const __half* w_lo;   // [taps,cout_pad,Cin] weights * s_w, split (rows >= Cout are zero)
+    const float* scale_ptr;                   // device scalar 1/(s_a*s_w)
+    const float* bias; const float* res; float* y;
+    int B, T, H, W, Cin, Cout, cout_pad;
+    int kt, kh, kw;
+    int res_ut, res_uh, res_uw, act, out_mode;
+    int terms;                                // 3: hi*hi+hi*lo+lo*hi (fp32-grade)   1: hi*hi only
+};
+bool conv_tc_supported(int B, int T, int H, int W, int Cin, int Cout, int kt, int kh, int kw);
+int launch_conv_tc(const ConvTcArgs& a, cudaStream_t stream);
+int launch_split_fp16(const float* x, __half* hi, __half* lo, float scale, long long n, cudaStream_t stream);
 
 // ----------------------------------------------------------------------------- normalisation
 // Per-(sample, channel) sums of a channels-last tensor x[B, V, C] -> sums[B, C, 2] (double):
@@ -47,6 +65,8 @@ struct ModArgs {
     int B, T, H, W, C;                        // OUTPUT dims
     int ut, uh, uw;                           // nearest-upsample factors from x to out
     int act;
+    // when out_hi != nullptr the result is written as an fp16 (hi, lo) split of split_scale*v instead of fp32
+    __half* out_hi = nullptr; __half* out_lo = nullptr; float split_scale = 1.f;
 };
 int launch_modulate(const ModArgs& a, cudaStream_t stream);
 

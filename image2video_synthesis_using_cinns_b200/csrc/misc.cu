@@ -1,6 +1,7 @@
 // Small ops of the path: nn.Linear, bilinear start-frame resize, max-pool.
 #include "common.cuh"
 #include "kernels.h"
+#include "prof.h"
 
 namespace i2v {
 
@@ -92,6 +93,7 @@ __global__ void maxpool3x3s2_kernel(const float* __restrict__ x, float* __restri
 int launch_linear(const float* x, const float* w, const float* bias, float* y, int B, int K, int N, int act,
                   cudaStream_t stream) {
     I2V_REQUIRE(K % 4 == 0, "linear: K=%d must be a multiple of 4", K);
+    ProfScope ps(PROF_OTHER, 2.0 * (double)B * K * N, 4.0 * ((double)K * N + (double)B * (K + N)), stream);
     linear_kernel<<<ceil_div((long long)N * 32, 256), 256, 0, stream>>>(x, w, bias, y, B, K, N, act);
     I2V_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -104,6 +106,7 @@ int launch_resize_bilinear_nchw_to_nhwc(const float* img, float* out, int B, int
     const long long n = (long long)B * H * W * C;
     long long blocks = (n + 255) / 256;
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    ProfScope ps(PROF_OTHER, 0, 0, stream);
     resize_bilinear_kernel<<<(int)blocks, 256, 0, stream>>>(img, out, B, C, H0, W0, H, W, sh, sw);
     I2V_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -115,6 +118,7 @@ int launch_maxpool3x3s2(const float* x, float* y, int B, int H, int W, int C, cu
     const long long n = (long long)B * Ho * Wo * (C / 4);
     long long blocks = (n + 255) / 256;
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    ProfScope ps(PROF_OTHER, 0, 0, stream);
     maxpool3x3s2_kernel<<<(int)blocks, 256, 0, stream>>>(x, y, B, H, W, C, Ho, Wo);
     I2V_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -7,8 +7,11 @@
 //                   nearest-upsample index map so the upsampled tensor of decoder.py:102-114 is never
 //                   materialised, SPADE's gamma/beta maps are read as 2-D maps (not repeated over T as
 //                   normalization_layer.py:22-23 does).
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "kernels.h"
+#include "prof.h"
 
 namespace i2v {
 
@@ -130,7 +133,17 @@ __global__ void __launch_bounds__(256) modulate_kernel(const ModArgs a, long lon
         float4 o;
         o.x = apply_act(v[0], a.act); o.y = apply_act(v[1], a.act);
         o.z = apply_act(v[2], a.act); o.w = apply_act(v[3], a.act);
-        reinterpret_cast<float4*>(a.out)[i] = o;
+        if (a.out_hi != nullptr) {
+            const float s = a.split_scale;
+            const float f[4] = {o.x * s, o.y * s, o.z * s, o.w * s};
+            __half hh[4], ll[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { hh[j] = __float2half_rn(f[j]); ll[j] = __float2half_rn(f[j] - __half2float(hh[j])); }
+            reinterpret_cast<uint2*>(a.out_hi)[i] = *reinterpret_cast<const uint2*>(hh);
+            reinterpret_cast<uint2*>(a.out_lo)[i] = *reinterpret_cast<const uint2*>(ll);
+        } else {
+            reinterpret_cast<float4*>(a.out)[i] = o;
+        }
     }
 }
 
@@ -148,6 +161,7 @@ int launch_channel_stats(const float* x, double* sums, int B, long long V, int C
     const int lanes_c = C4 < STATS_THREADS ? C4 : STATS_THREADS;
     const int rows = STATS_THREADS / lanes_c;
     const long long chunk = (long long)rows * STATS_ELEMS_PER_THREAD;
+    ProfScope ps(PROF_STATS, 3.0 * (double)B * V * C, 4.0 * (double)B * V * C, stream);
     dim3 grid(ceil_div(V, chunk), B);
     channel_stats_kernel<<<grid, STATS_THREADS, sizeof(double) * 2 * C, stream>>>(x, sums, V, C, lanes_c, rows);
     I2V_CHECK_CUDA(cudaGetLastError());
@@ -159,6 +173,7 @@ int launch_norm_coeffs(const double* sums, float* coef, int B, int C, long long 
     I2V_REQUIRE(groups == 0 || C % groups == 0, "norm_coeffs: C=%d not divisible by groups=%d", C, groups);
     I2V_REQUIRE((gamma == nullptr) == (beta == nullptr), "norm_coeffs: gamma and beta go together");
     const int n = B * C;
+    ProfScope ps(PROF_OTHER, 0, 0, stream);
     norm_coeffs_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(sums, coef, B, C, (double)V, groups, eps, gamma, beta, mod);
     I2V_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -171,6 +186,8 @@ int launch_modulate(const ModArgs& a, cudaStream_t stream) {
     long long blocks = (total4 + 255) / 256;
     const long long cap = (long long)kNumSMs * 32;
     if (blocks > cap) blocks = cap;
+    ProfScope ps(PROF_MODULATE, 4.0 * (double)total4 * 4,
+                 4.0 * 4 * ((double)total4 * (1.0 + (a.r ? 1.0 : 0.0)) + (double)total4 / ((double)a.ut * a.uh * a.uw)), stream);
     modulate_kernel<<<(int)blocks, 256, 0, stream>>>(a, total4);
     I2V_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -178,6 +195,7 @@ int launch_modulate(const ModArgs& a, cudaStream_t stream) {
 
 int launch_mean_from_sums(const double* sums, float* y, int B, int C, long long V, cudaStream_t stream) {
     const int n = B * C;
+    ProfScope ps(PROF_OTHER, 0, 0, stream);
     mean_from_sums_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(sums, y, n, 1.0 / (double)V);
     I2V_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -96,10 +96,34 @@ def pack_flow(sd, n_flows, d, cond_channels, hidden, depth, control):
 
 # --------------------------------------------------------------------------------------- decoder
 DEC_BLOCKS = ("head_0", "g_0", "g_1", "g_2", "g_3", "g_4")
+ACT_SPLIT_SCALE = 16.0      # must equal ACT_SPLIT_SCALE in csrc/api.cu
 
 
-def pack_decoder(sd, nf):
-    t = {}
+def split_fp16(w, in_scale):
+    """fp32 weights [taps, Cout, Cin] -> (hi, lo, ws) for the tensor-core engine (csrc/conv_tc.cu).
+
+    hi = fp16(s*w), lo = fp16(s*w - hi) with s the power of two that puts max|w| in [2^13, 2^14): both
+    words stay in fp16's normal range for everything that matters and hi+lo carries ~22 significand
+    bits.  Rows are zero-padded to a multiple of 16 (UMMA N granularity).  ws = 1/(in_scale*s) is the
+    exact power-of-two factor the epilogue applies to the fp32 accumulator."""
+    import math
+    m = float(w.abs().max())
+    s = 2.0 ** math.floor(math.log2(2.0 ** 14 / m)) if m > 0 else 1.0
+    ws = w.double() * s
+    hi = ws.to(torch.float16)
+    lo = (ws - hi.double()).to(torch.float16)
+    cout = w.shape[1]
+    cpad = (cout + 15) // 16 * 16
+    if cpad != cout:
+        z = torch.zeros(w.shape[0], cpad - cout, w.shape[2], dtype=torch.float16)
+        hi, lo = torch.cat((hi, z), 1), torch.cat((lo, z), 1)
+    return hi.contiguous(), lo.contiguous(), torch.tensor([1.0 / (in_scale * s)], dtype=torch.float32)
+
+
+def pack_decoder(sd, nf, engine=0):
+    """Returns (tensors, scalars).  engine >= 1 adds the split fp16 weights of the tensor-core engine."""
+    import math
+    t, scalars = {}, {}
     c0 = 16 * nf
     # fc output index n = c*16 + (h*4+w)  ->  channels-last index (h*4+w)*C + c
     fw = sd["fc.weight"].float().reshape(c0, 16, -1).permute(1, 0, 2).reshape(16 * c0, -1)
@@ -124,7 +148,22 @@ def pack_decoder(sd, nf):
         t[f"{name}.adain.b"] = sd[f"{name}.norm_1.linear.bias"].float()
     t["conv_img.w"] = _taps3(sd["conv_img.weight"].float())
     t["conv_img.b"] = sd["conv_img.bias"].float()
-    return {k: v.contiguous() for k, v in t.items()}
+    if engine >= 1:
+        tc = {}
+        for name in DEC_BLOCKS:
+            convs = ["conv_0", "conv_1"] + (["conv_s"] if f"{name}.conv_s.w" in t else [])
+            for c in convs:
+                tc[f"{name}.{c}.wh"], tc[f"{name}.{c}.wl"], tc[f"{name}.{c}.ws"] = split_fp16(t.pop(f"{name}.{c}.w"), ACT_SPLIT_SCALE)
+            # SPADE hidden map h = lrelu(conv(img) + b) with |img| <= 1 after the bilinear resize:
+            # |h| <= max_c (sum|W_c| + |b_c|).  Its split scale targets 2^11 at that bound (x8 input headroom).
+            w, b = t[f"{name}.spade.conv.w"], t[f"{name}.spade.conv.b"]
+            bound = float((w.abs().sum(dim=(0, 2)) + b.abs()).max())
+            sa = 2.0 ** math.floor(math.log2(2.0 ** 11 / max(bound, 1e-30)))
+            scalars[f"{name}.spade.sa"] = sa
+            tc[f"{name}.spade.gb.wh"], tc[f"{name}.spade.gb.wl"], tc[f"{name}.spade.gb.ws"] = split_fp16(t.pop(f"{name}.spade.gb.w"), sa)
+        tc["conv_img.wh"], tc["conv_img.wl"], tc["conv_img.ws"] = split_fp16(t.pop("conv_img.w"), ACT_SPLIT_SCALE)
+        t.update(tc)
+    return {k: v.contiguous() for k, v in t.items()}, scalars
 
 
 # -------------------------------------------------------------------------------------- embedder

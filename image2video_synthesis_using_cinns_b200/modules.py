@@ -194,7 +194,11 @@ class Generator(_Native):
         self.h = self.L.i2v_decoder_create(self.nf, self.z_dim, us, ut, conv_engine)
         if not self.h:
             raise RuntimeError(self.L.i2v_last_error().decode())
-        self._register(self.L.i2v_decoder_set_tensor, loader.pack_decoder(state_dict, self.nf))
+        tensors, scalars = loader.pack_decoder(state_dict, self.nf, conv_engine)
+        self._register(self.L.i2v_decoder_set_tensor, tensors)
+        for name, v in scalars.items():
+            _lib.check(self.L.i2v_decoder_set_scalar(self.h, name.encode(), float(v)), f"set_scalar({name})")
+        self.conv_engine = conv_engine
         self.frames = 8 * self.upsample_t[0] * self.upsample_t[1]
         self.size = 32 * self.upsample_s[0] * self.upsample_s[1]
 

@@ -41,6 +41,15 @@ extern "C" {
 int i2v_abi_version(void);
 const char* i2v_last_error(void);
 
+/* Launch accounting.  i2v_launch_count(): kernels launched by this library since load.
+ * i2v_prof_enable(1) brackets every subsequent launch with CUDA events on its stream;
+ * i2v_prof_collect() waits for them and returns per kernel family (0 conv, 1 stats, 2 modulate,
+ * 3 flow, 4 other; arrays of 5) the summed device time [ms], algorithmic FLOPs, algorithmic bytes
+ * and launch counts since the last collect. */
+long long i2v_launch_count(void);
+void i2v_prof_enable(int on);
+int i2v_prof_collect(double* ms, double* flops, double* bytes, long long* launches);
+
 /* ---------------------------------------------------------------- conditional INN (stage 2) */
 typedef struct i2v_flow i2v_flow;
 /* d: latent width (64); zc: conditioning width padded to a multiple of 4; hidden: MLP width (<=512);
@@ -71,9 +80,13 @@ void i2v_embedder_destroy(i2v_embedder* h);
 /* ---------------------------------------------------------------- 3-D conv decoder (stage 1) */
 typedef struct i2v_decoder i2v_decoder;
 /* nf: Decoder.channel_factor; upsample_s/t: the two config lists (decoder.py:65-66).
- * conv_engine: 0 = fp32 SIMT implicit GEMM everywhere (exact-arithmetic engine). */
+ * conv_engine: 0 = fp32 SIMT implicit GEMM everywhere (exact-arithmetic engine);
+ *              1 = tcgen05 tensor-core engine, error-compensated fp16 split (hi*hi+hi*lo+lo*hi): fp32-grade parity;
+ *              2 = tcgen05 tensor-core engine, single fp16 product (fast mode, ~1e-3). */
 i2v_decoder* i2v_decoder_create(int nf, int z_dim, const int upsample_s[2], const int upsample_t[2], int conv_engine);
 int i2v_decoder_set_tensor(i2v_decoder* h, const char* name, const void* dev_ptr, size_t nbytes);
+/* host-side per-layer constants of the tensor-core engine ("<block>.spade.sa": split scale of SPADE's hidden map) */
+int i2v_decoder_set_scalar(i2v_decoder* h, const char* name, double value);
 size_t i2v_decoder_workspace_bytes(const i2v_decoder* h, int batch, int height, int width);
 /* img: [B,3,H,W] NCHW; z: [B,z_dim]; frames: [B,16,3,H,W] (contiguous; the reference returns the
  * same values as a transposed view, decoder.py:120) */
@@ -99,6 +112,12 @@ int i2v_op_conv(const float* dev_x, const float* dev_w, const float* dev_bias, c
                 int B, int Ti, int Hi, int Wi, int Cin, int Cout, int kt, int kh, int kw, int st, int sh, int sw,
                 int pt, int ph, int pw, int res_ut, int res_uh, int res_uw, int act, int out_mode, int engine,
                 void* stream);
+/* tensor-core conv on fp32 inputs: splits x (scale_a) and w (scale_w; [taps,cout_pad,Cin], rows >= Cout zero) into
+ * fp16 (hi, lo) inside the workspace (>= 4*(|x|+|w|)+2048 bytes), then runs the tcgen05 engine; terms 3 or 1 */
+int i2v_op_conv_tc(const float* dev_x, const float* dev_w, const float* dev_bias, const float* dev_res, float* dev_y,
+                   int B, int T, int H, int W, int Cin, int Cout, int cout_pad, int kt, int kh, int kw, int res_ut,
+                   int res_uh, int res_uw, int act, int out_mode, int terms, float scale_a, float scale_w, void* dev_ws,
+                   size_t ws_bytes, void* stream);
 /* sums[B,C,2] (double) of x[B,V,C] */
 int i2v_op_channel_stats(const float* dev_x, double* dev_sums, int B, int64_t V, int C, void* stream);
 int i2v_op_norm_coeffs(const double* dev_sums, float* dev_coef, int B, int C, int64_t V, int groups, float eps,

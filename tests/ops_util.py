@@ -98,3 +98,21 @@ def maxpool(x_cl):
     y = torch.empty(B, Ho, Wo, C, dtype=torch.float32, device="cuda")
     _lib.check(L.i2v_op_maxpool3x3s2(P(x_cl), P(y), B, H, W, C, S()), "op_maxpool")
     return y
+
+
+def conv_tc(x_cl, w_taps, bias, res_cl, k, res_up=(1, 1, 1), act=0, out_mode=0, terms=3, scale_a=16.0):
+    """Tensor-core engine on fp32 inputs (the op splits them on the device).  w_taps [taps,Cout,Cin]."""
+    import math
+    L = _lib.load()
+    B, T, H, W, Cin = x_cl.shape
+    Cout = w_taps.shape[1]
+    cpad = (Cout + 15) // 16 * 16
+    wp = torch.zeros(w_taps.shape[0], cpad, Cin, device="cuda")
+    wp[:, :Cout] = w_taps
+    scale_w = 2.0 ** math.floor(math.log2(2.0 ** 14 / float(w_taps.abs().max())))
+    shape = (B, T, H, W, Cout) if out_mode == 0 else (B, T, Cout, H, W)
+    y = torch.empty(shape, dtype=torch.float32, device="cuda")
+    ws = torch.empty(4 * (x_cl.numel() + wp.numel()) + 4096, dtype=torch.uint8, device="cuda")
+    _lib.check(L.i2v_op_conv_tc(P(x_cl), P(wp), P(bias), P(res_cl), P(y), B, T, H, W, Cin, Cout, cpad, *k, *res_up, act,
+                                out_mode, terms, scale_a, scale_w, P(ws), ws.numel(), S()), "op_conv_tc")
+    return y

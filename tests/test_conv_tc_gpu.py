@@ -1,0 +1,81 @@
+"""Tensor-core conv engine (tcgen05 + TMA, error-compensated fp16 split) against fp32 PyTorch."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import ops_util as ou
+from golden_util import rel_inf, report
+
+pytestmark = pytest.mark.gpu
+G = lambda s: torch.Generator().manual_seed(s)
+
+CASES = [
+    # name, (B,Cin,T,H,W), Cout, k
+    ("g3_like_w64", (1, 64, 2, 8, 64), 64, (3, 3, 3)),        # box 64x2x1x1, kc=64
+    ("w32_kc64_n128", (2, 128, 2, 32, 32), 128, (3, 3, 3)),   # box 32x4
+    ("w16_n256", (1, 64, 4, 16, 16), 256, (3, 3, 3)),         # box 16x8, N=256
+    ("n512_two_ntiles", (1, 64, 1, 8, 8), 512, (3, 3, 3)),    # 2 N tiles, box 8x8x1x2 (bb=2 > B)
+    ("head_4x4_batchbox", (3, 64, 1, 4, 4), 64, (3, 3, 3)),   # box 4x4x1x8 over the batch dim
+    ("g0_t2", (2, 64, 2, 8, 8), 64, (3, 3, 3)),               # box 8x8x2
+    ("kc32", (1, 32, 2, 16, 16), 32, (3, 3, 3)),              # SWIZZLE_64B rows
+    ("kc16", (1, 16, 2, 16, 16), 16, (3, 3, 3)),              # SWIZZLE_32B rows
+    ("conv_s_1x1x1", (2, 128, 2, 8, 8), 64, (1, 1, 1)),
+    ("spade_gb_2d", (2, 128, 1, 16, 16), 256, (1, 3, 3)),
+    ("w128_row", (1, 32, 2, 4, 128), 32, (3, 3, 3)),          # box 128x1
+    ("long_k", (1, 256, 2, 8, 8), 128, (3, 3, 3)),            # 108 pipeline iterations, ring wraps many times
+]
+
+
+@pytest.mark.parametrize("name,xs,cout,k", CASES, ids=[c[0] for c in CASES])
+def test_conv_tc_matches_fp32(name, xs, cout, k):
+    g = G(sum(map(ord, name)))
+    x = torch.randn(xs, generator=g)
+    w = torch.randn(cout, xs[1], *k, generator=g) / (xs[1] * k[0] * k[1] * k[2]) ** 0.5
+    b = torch.randn(cout, generator=g)
+    pad = tuple(kk // 2 for kk in k)
+    want = F.conv3d(x.double(), w.double(), b.double(), 1, pad)
+    got = ou.from_cl(ou.conv_tc(ou.to_cl(x), ou.taps(w), b.cuda(), None, k))
+    e3 = rel_inf(got, want)
+    simt = rel_inf(ou.from_cl(ou.conv(ou.to_cl(x), ou.taps(w), b.cuda(), None, k, (1, 1, 1), pad)), want)
+    e1 = rel_inf(ou.from_cl(ou.conv_tc(ou.to_cl(x), ou.taps(w), b.cuda(), None, k, terms=1)), want)
+    report("conv_tc:" + name, split3=e3, fp16_single=e1, simt_fp32=simt)
+    assert got.shape == want.shape
+    # fp32-grade: within a small factor of the fp32 SIMT engine's own rounding.  The residual gap is the
+    # tensor core's truncating fp32 accumulate (measured ~1e-5 at K=6912 with ONE accumulator), which the
+    # 4-way TMEM accumulator round-robin cuts down; see DESIGN.md section 5.
+    assert e3 < 6e-6
+    assert e1 < 1e-3           # single fp16 product (fast mode)
+
+
+def test_conv_tc_epilogue_residual_act_and_frames_layout():
+    g = G(7)
+    x = torch.randn(2, 64, 4, 8, 8, generator=g)
+    w = torch.randn(32, 64, 3, 3, 3, generator=g) * 0.03
+    b = torch.randn(32, generator=g)
+    res = torch.randn(2, 32, 2, 4, 4, generator=g)
+    want = F.leaky_relu(F.conv3d(x, w, b, 1, 1) + F.interpolate(res, scale_factor=2.0), 0.2)
+    got = ou.conv_tc(ou.to_cl(x), ou.taps(w), b.cuda(), ou.to_cl(res), (3, 3, 3), res_up=(2, 2, 2), act=2)
+    assert rel_inf(ou.from_cl(got), want) < 1e-5
+    w3 = torch.randn(3, 64, 3, 3, 3, generator=g) * 0.03
+    b3 = torch.randn(3, generator=g)
+    want = torch.tanh(F.conv3d(x, w3, b3, 1, 1)).transpose(1, 2)
+    got = ou.conv_tc(ou.to_cl(x), ou.taps(w3), b3.cuda(), None, (3, 3, 3), act=3, out_mode=1)
+    assert rel_inf(got.cpu(), want) < 1e-5
+
+
+@pytest.mark.parametrize("engine", [1])
+def test_decoder_tensor_core_engine_matches_oracle(engine, ckpt_cache):
+    import oracle_torch as ot
+    from image2video_synthesis_using_cinns_b200.get_model import Model
+    for dataset, nf, B in (("bair", 32, 3), ("dtdb_fire", 16, 2)):
+        mp = ckpt_cache(dataset=dataset, seed=31, nf=nf, n_flows=2, spade_gain=1.0, with_encoder=False)
+        m = Model(mp, 16, conv_engine=engine, micro_batch=2)
+        om = ot.OracleModel(mp, 16)
+        img = m.config.Data["img_size"]
+        g = G(3)
+        x0 = torch.rand(B, 3, img, img, generator=g) * 2 - 1
+        z = torch.randn(B, 64, generator=g)
+        want = om.decode(x0, z)
+        e = rel_inf(m.decoder(x0.cuda(), z.cuda()).cpu(), want)
+        report(f"decoder_tc{engine}:{dataset}", decoder=e)
+        assert e < 1e-4

@@ -86,7 +86,7 @@ def test_pack_decoder_folds_spectral_norm_and_permutes_fc():
     import oracle_torch as ot
     gen = torch.Generator().manual_seed(3)
     sd = synthetic.decoder_state_dict(gen, 16)
-    t = loader.pack_decoder(sd, 16)
+    t, _ = loader.pack_decoder(sd, 16)
     w = ot.spectral_weight(sd, "g_1.conv_0")
     assert torch.allclose(t["g_1.conv_0.w"], w.permute(2, 3, 4, 0, 1).reshape(27, w.shape[0], w.shape[1]), atol=1e-6)
     z = torch.randn(2, 64, generator=gen)
@@ -107,3 +107,18 @@ def test_pack_embedder_bn_fold():
     got = torch.nn.functional.conv2d(x, w, t["conv1.b"], 2, 3)
     assert torch.allclose(got, want, atol=1e-5)
     assert t["fc.w"].shape == (64, 2048)
+
+
+def test_split_fp16_is_fp32_grade():
+    gen = torch.Generator().manual_seed(5)
+    w = torch.randn(27, 20, 64, generator=gen) * 0.03
+    hi, lo, ws = loader.split_fp16(w, 16.0)
+    assert hi.shape == (27, 32, 64) and hi[:, 20:].abs().max() == 0
+    s = 1.0 / (16.0 * float(ws))
+    rec = (hi[:, :20].double() + lo[:, :20].double()) / s
+    assert (rec - w.double()).abs().max() / w.abs().max() < 2 ** -21
+    assert hi.float().abs().max() < 2 ** 14.01 and torch.isfinite(hi.float()).all()
+    sd = synthetic.decoder_state_dict(gen, 16)
+    t, scalars = loader.pack_decoder(sd, 16, engine=1)
+    assert "g_1.conv_0.wh" in t and "g_1.conv_0.w" not in t and "g_1.spade.sa" in scalars
+    assert t["conv_img.wh"].shape == (27, 16, 16)
