@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--conv-engine", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ckpt-dir", default=None, help="reuse / create synthetic checkpoints here")
+    ap.add_argument("--dump-launches", default=None, help="CSV of per-launch device times of the timed steps")
     return ap.parse_args()
 
 
@@ -220,6 +221,8 @@ def run_b200(args):
         torch.cuda.synchronize()
         n0 = L.i2v_launch_count()
         if profile:
+            if args.dump_launches:
+                L.i2v_prof_dump_path(args.dump_launches.encode())
             L.i2v_prof_enable(1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

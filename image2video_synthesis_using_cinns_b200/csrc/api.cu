@@ -32,6 +32,7 @@ struct ProfState {
     }
 };
 ProfState g_prof;
+std::string g_prof_dump_path;
 }  // namespace
 
 ProfScope::ProfScope(int cat, double flops, double bytes, cudaStream_t stream) : idx_(-1), stream_(stream) {
@@ -164,16 +165,22 @@ void i2v_prof_enable(int on) {
 }
 int i2v_prof_collect(double* ms, double* flops, double* bytes, long long* launches) {
     for (int c = 0; c < PROF_NCAT; ++c) { ms[c] = 0; flops[c] = 0; bytes[c] = 0; launches[c] = 0; }
+    FILE* dump = g_prof_dump_path.empty() ? nullptr : fopen(g_prof_dump_path.c_str(), "w");
+    if (dump) fprintf(dump, "idx,family,ms,gflop,mbytes\n");
+    int idx = 0;
     for (auto& r : g_prof.recs) {
         I2V_CHECK_CUDA(cudaEventSynchronize(r.b));
         float t = 0.f;
         I2V_CHECK_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+        if (dump) fprintf(dump, "%d,%d,%.6f,%.6f,%.6f\n", idx++, r.cat, t, r.flops * 1e-9, r.bytes * 1e-6);
         ms[r.cat] += t; flops[r.cat] += r.flops; bytes[r.cat] += r.bytes; launches[r.cat]++;
     }
+    if (dump) fclose(dump);
     g_prof.recs.clear();
     g_prof.pool_used = 0;
     return 0;
 }
+void i2v_prof_dump_path(const char* path) { g_prof_dump_path = path ? path : ""; }
 
 i2v_flow* i2v_flow_create(int n_flows, int d, int zc, int hidden, int depth, const unsigned char* cond_mode) {
     if (n_flows <= 0 || n_flows > 64 || d <= 0 || d % 2 || zc <= 0 || zc % 4 || hidden <= 0 || hidden % 4 || hidden > 512 ||
@@ -713,7 +720,7 @@ int i2v_op_conv(const float* x, const float* w, const float* bias, const float* 
 }
 int i2v_op_conv_tc(const float* x, const float* w, const float* bias, const float* res, float* y, int B, int T, int H, int W, int Cin,
                    int Cout, int cout_pad, int kt, int kh, int kw, int rut, int ruh, int ruw, int act, int out_mode, int terms,
-                   float scale_a, float scale_w, void* ws, size_t ws_bytes, void* stream) {
+                   int variant, float scale_a, float scale_w, void* ws, size_t ws_bytes, void* stream) {
     I2V_REQUIRE(x && w && y && ws, "op_conv_tc: null argument");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t nx = (size_t)B * T * H * W * Cin, nw = (size_t)kt * kh * kw * cout_pad * Cin;
@@ -729,9 +736,10 @@ int i2v_op_conv_tc(const float* x, const float* w, const float* bias, const floa
     ConvTcArgs a;
     a.x_hi = xh; a.x_lo = xl; a.w_hi = wh; a.w_lo = wl; a.scale_ptr = sc; a.bias = bias; a.res = res; a.y = y;
     a.B = B; a.T = T; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.cout_pad = cout_pad; a.kt = kt; a.kh = kh; a.kw = kw;
-    a.res_ut = rut; a.res_uh = ruh; a.res_uw = ruw; a.act = act; a.out_mode = out_mode; a.terms = terms;
+    a.res_ut = rut; a.res_uh = ruh; a.res_uw = ruw; a.act = act; a.out_mode = out_mode; a.terms = terms; a.variant = variant;
     return launch_conv_tc(a, s);
 }
+int i2v_debug_conv_tc_timestamps(void* buf, int ctas) { return conv_tc_set_debug(static_cast<unsigned long long*>(buf), ctas); }
 int i2v_op_channel_stats(const float* x, double* sums, int B, int64_t V, int C, void* stream) {
     return launch_channel_stats(x, sums, B, V, C, static_cast<cudaStream_t>(stream));
 }

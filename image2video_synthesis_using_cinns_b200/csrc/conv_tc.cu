@@ -34,7 +34,18 @@ namespace i2v {
 
 namespace {
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+
+// optional phase timestamps (i2v_debug_set_buffer): 8 x u64 per CTA, %globaltimer in ns
+__device__ unsigned long long* g_dbg = nullptr;
+__device__ int g_dbg_ctas = 0;
+__device__ __forceinline__ void dbg_stamp(int slot) {
+    if (g_dbg != nullptr && (int)blockIdx.x < g_dbg_ctas && blockIdx.y == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_dbg[(size_t)blockIdx.x * 8 + slot] = t;
+    }
+}
 constexpr int TILE_M = 128;
 
 struct ConvTcKArgs {
@@ -46,6 +57,168 @@ struct ConvTcKArgs {
     int n_tile, kc, stages, terms, nacc;
     int res_ut, res_uh, res_uw, act, out_mode;
 };
+
+struct EpiArgs {
+    const float* bias; const float* res; float* y;
+    int T, H, W, Cout, res_ut, res_uh, res_uw, act, out_mode;
+};
+
+// One output row (voxel) per thread: sum `nacc` TMEM accumulators (column stride `acc_stride`), then
+// scale, bias, residual through the nearest-upsample map, activation, store.  tcgen05.ld is warp-collective,
+// so every lane walks all column chunks and only the stores are predicated.
+__device__ __forceinline__ void epilogue_row(const EpiArgs& e, uint32_t tmem_lane_base, int n_tile, int nacc, int acc_stride, int n0,
+                                             float scale, int b, int t, int h, int w, bool valid) {
+    const long long vox = (((long long)b * e.T + t) * e.H + h) * e.W + w;
+    long long roff = 0;
+    if (e.res != nullptr && valid) {
+        const int Tr = e.T / e.res_ut, Hr = e.H / e.res_uh, Wr = e.W / e.res_uw;
+        roff = ((((long long)b * Tr + t / e.res_ut) * Hr + h / e.res_uh) * Wr + w / e.res_uw) * e.Cout;
+    }
+    for (int c0 = 0; c0 < n_tile; c0 += 16) {
+        uint32_t rr[16];
+        float accv[16];
+        ptx::tmem_ld_32x32b_x16(tmem_lane_base + (uint32_t)c0, rr);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) accv[j] = __uint_as_float(rr[j]);
+        for (int ai = 1; ai < nacc; ++ai) {
+            ptx::tmem_ld_32x32b_x16(tmem_lane_base + (uint32_t)(ai * acc_stride + c0), rr);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) accv[j] += __uint_as_float(rr[j]);
+        }
+        const int nb = n0 + c0;
+        if (!valid || nb >= e.Cout) continue;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int n = nb + j;
+            float x = accv[j] * scale;
+            if (n < e.Cout) {
+                if (e.bias != nullptr) x += __ldg(e.bias + n);
+                if (e.res != nullptr) x += __ldg(e.res + roff + n);
+            }
+            v[j] = apply_act(x, e.act);
+        }
+        if (e.out_mode == 0) {
+            float* dst = e.y + vox * e.Cout + nb;
+            if ((e.Cout & 3) == 0 && nb + 15 < e.Cout) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (nb + j < e.Cout) dst[j] = v[j];
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (nb + j < e.Cout) e.y[((((long long)b * e.T + t) * e.Cout + nb + j) * e.H + h) * e.W + w] = v[j];
+        }
+    }
+}
+
+// Coalesced variant for channels-last output: the 32 rows a warp pulls out of TMEM are transposed through a
+// padded shared-memory tile (the drained pipeline buffers) so that global stores, the residual read and the
+// bias read run along the channel dimension (full 128-byte lines).  The epilogue runs on ONE warp per
+// scheduler, i.e. it is bound by dependent-instruction latency, not bandwidth (measured: ~30 us per 256x128
+// tile with per-element index arithmetic): each lane therefore owns a fixed column group, row addresses come
+// from a warp shuffle of the per-lane voxel index, and the row loop is unrolled for memory-level parallelism.
+// `vox_lane` / `roff_lane`: output voxel index and residual element offset of THIS lane's row.
+__device__ __forceinline__ void epilogue_warp_coalesced(const EpiArgs& e, float* stile /* [32][ncols+4] */, uint32_t tmem_lane_base,
+                                                        int col0, int ncols, int nacc, int acc_stride, int n0, float scale, int lane,
+                                                        long long vox_lane, long long roff_lane) {
+    // this warp owns tile columns [col0, col0+ncols) of its 32 rows
+    const int ld = ncols + 4;
+    int c0 = 0;
+    for (; c0 + 32 <= ncols; c0 += 32) {
+        // up to two accumulators in flight per wait: a TMEM load round trip costs hundreds of cycles
+        uint32_t ra[32], rb2[32];
+        float accv[32];
+        ptx::tmem_ld_32x32b_x32(tmem_lane_base + (uint32_t)(col0 + c0), ra);
+        if (nacc > 1) ptx::tmem_ld_32x32b_x32(tmem_lane_base + (uint32_t)(acc_stride + col0 + c0), rb2);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) accv[j] = __uint_as_float(ra[j]) + (nacc > 1 ? __uint_as_float(rb2[j]) : 0.f);
+        if (nacc > 2) {
+            ptx::tmem_ld_32x32b_x32(tmem_lane_base + (uint32_t)(2 * acc_stride + col0 + c0), ra);
+            if (nacc > 3) ptx::tmem_ld_32x32b_x32(tmem_lane_base + (uint32_t)(3 * acc_stride + col0 + c0), rb2);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) accv[j] += __uint_as_float(ra[j]) + (nacc > 3 ? __uint_as_float(rb2[j]) : 0.f);
+        }
+        float4* dst = reinterpret_cast<float4*>(stile + lane * ld + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            dst[j] = make_float4(accv[4 * j] * scale, accv[4 * j + 1] * scale, accv[4 * j + 2] * scale, accv[4 * j + 3] * scale);
+    }
+    for (; c0 < ncols; c0 += 16) {
+        uint32_t rr[16];
+        float accv[16];
+        ptx::tmem_ld_32x32b_x16(tmem_lane_base + (uint32_t)(col0 + c0), rr);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) accv[j] = __uint_as_float(rr[j]);
+        for (int ai = 1; ai < nacc; ++ai) {
+            ptx::tmem_ld_32x32b_x16(tmem_lane_base + (uint32_t)(ai * acc_stride + col0 + c0), rr);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) accv[j] += __uint_as_float(rr[j]);
+        }
+        float4* dst = reinterpret_cast<float4*>(stile + lane * ld + c0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            dst[j] = make_float4(accv[4 * j] * scale, accv[4 * j + 1] * scale, accv[4 * j + 2] * scale, accv[4 * j + 3] * scale);
+    }
+    __syncwarp();
+    // lane -> (row sub-index, column group); c4n float4 per row
+    const int c4n = ncols >> 2;
+    const int lanes_per_row = c4n < 32 ? c4n : 32;
+    const int rows_per_iter = 32 / lanes_per_row;
+    const int rsub = lane / lanes_per_row, cl = lane - rsub * lanes_per_row;
+    const bool vec_ok = (e.Cout & 3) == 0;
+    for (int cg = cl; cg < c4n; cg += 32) {          // more than one pass only when the slice is wider than 128
+        const int c = cg * 4, n = n0 + col0 + c;
+        const bool full4 = vec_ok && n + 3 < e.Cout;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e.bias != nullptr && n < e.Cout) {
+            if (full4) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+            else {
+                b4.x = __ldg(e.bias + n);
+                if (n + 1 < e.Cout) b4.y = __ldg(e.bias + n + 1);
+                if (n + 2 < e.Cout) b4.z = __ldg(e.bias + n + 2);
+                if (n + 3 < e.Cout) b4.w = __ldg(e.bias + n + 3);
+            }
+        }
+#pragma unroll 4
+        for (int i = 0; i < 32; i += rows_per_iter) {
+            const int r = (i + rsub) & 31;
+            const long long vox = __shfl_sync(0xffffffffu, vox_lane, r);
+            const long long roff = __shfl_sync(0xffffffffu, roff_lane, r);
+            if (n >= e.Cout || rsub >= rows_per_iter) continue;     // spare lanes when c4n does not divide 32
+            const float4 a4 = *reinterpret_cast<const float4*>(stile + r * ld + c);
+            float v[4] = {a4.x + b4.x, a4.y + b4.y, a4.z + b4.z, a4.w + b4.w};
+            if (full4) {
+                if (e.res != nullptr) {
+                    const float4 r4 = __ldg(reinterpret_cast<const float4*>(e.res + roff + n));
+                    v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
+                }
+                *reinterpret_cast<float4*>(e.y + vox * e.Cout + n) =
+                    make_float4(apply_act(v[0], e.act), apply_act(v[1], e.act), apply_act(v[2], e.act), apply_act(v[3], e.act));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (n + j < e.Cout) {
+                        float x = v[j];
+                        if (e.res != nullptr) x += __ldg(e.res + roff + n + j);
+                        e.y[vox * e.Cout + n + j] = apply_act(x, e.act);
+                    }
+            }
+        }
+    }
+    __syncwarp();
+}
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
@@ -118,27 +291,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
         if (lane == 0) {
             const uint32_t idesc = ptx::make_idesc_f16(TILE_M, a.n_tile);
             const int ksteps = a.kc / 16;
+            const uint64_t dproto = ptx::make_kmajor_desc(0, rb);
+            const uint32_t dlo = (uint32_t)dproto, dhi = (uint32_t)(dproto >> 32);
             for (int it = 0; it < iters; ++it) {
                 const int s = it % a.stages;
                 const uint32_t ph = (uint32_t)(it / a.stages) & 1u;
                 ptx::mbar_wait(full + s, ph);
                 ptx::tc_fence_after();
                 const uint32_t sa = ptx::smem_u32(smem + (size_t)s * stage_bytes);
-                const uint32_t sb = sa + 2 * a_bytes;
+                // descriptors differ only in their 14-bit start-address field: one 32-bit add per operand
+                // (the single issuing thread must stay well ahead of the tensor pipe)
+                const uint32_t lah = dlo + (sa >> 4), lal = lah + (a_bytes >> 4);
+                const uint32_t lbh = lah + ((2 * a_bytes) >> 4), lbl = lbh + (b_bytes >> 4);
                 // round-robin over `nacc` TMEM accumulators: the tensor core's fp32 accumulate truncates, so
                 // the chain of dependent adds per accumulator is cut nacc-fold and the partial sums are
                 // combined with round-to-nearest fp32 adds in the epilogue
                 const uint32_t tacc = tmem_base + (uint32_t)((it % a.nacc) * a.n_tile);
-                for (int k = 0; k < ksteps; ++k) {
-                    const uint32_t off = (uint32_t)k * 32u;       // 16 fp16 along K inside the swizzle span
-                    const uint64_t dAh = ptx::make_kmajor_desc(sa + off, rb);
-                    const uint64_t dBh = ptx::make_kmajor_desc(sb + off, rb);
-                    ptx::mma_f16_ss(tacc, dAh, dBh, idesc, (it >= a.nacc || k > 0) ? 1u : 0u);
-                    if (a.terms > 1) {
-                        const uint64_t dAl = ptx::make_kmajor_desc(sa + a_bytes + off, rb);
-                        const uint64_t dBl = ptx::make_kmajor_desc(sb + b_bytes + off, rb);
-                        ptx::mma_f16_ss(tacc, dAh, dBl, idesc, 1u);
-                        ptx::mma_f16_ss(tacc, dAl, dBh, idesc, 1u);
+                uint32_t acc_flag = it >= a.nacc ? 1u : 0u;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (k < ksteps) {
+                        const uint32_t o = (uint32_t)k * 2u;          // 16 fp16 = 32 B along K, in 16-byte units
+                        ptx::mma_f16_ss(tacc, ptx::desc64(lah + o, dhi), ptx::desc64(lbh + o, dhi), idesc, acc_flag);
+                        acc_flag = 1u;
+                        if (a.terms > 1) {
+                            ptx::mma_f16_ss(tacc, ptx::desc64(lah + o, dhi), ptx::desc64(lbl + o, dhi), idesc, 1u);
+                            ptx::mma_f16_ss(tacc, ptx::desc64(lal + o, dhi), ptx::desc64(lbh + o, dhi), idesc, 1u);
+                        }
                     }
                 }
                 ptx::mma_commit(empty + s);        // frees the smem stage once these MMAs have read it
@@ -149,70 +328,235 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
         // ================================ epilogue (4 warps, one TMEM lane quarter each)
         ptx::mbar_wait(tmem_full, 0);
         ptx::tc_fence_after();
-        const int q = warp & 3;
+        const int q = warp & 3, half = (warp - 2) >> 2;       // two warps per TMEM lane quarter: column halves
         const int m = q * 32 + lane;
         int r = m;
         const int wi = r % a.bw; r /= a.bw;
         const int hi = r % a.bh; r /= a.bh;
         const int ti = r % a.bt;
         const int bi = r / a.bt;
-        const int b = b0 + bi, t = t0 + ti, h = h0 + hi, w = w0 + wi;
-        const bool valid = b < a.B;
-        const float scale = __ldg(a.scale_ptr);
-        const long long vox = (((long long)b * a.T + t) * a.H + h) * a.W + w;
-        long long roff = 0;
-        if (a.res != nullptr && valid) {
+        EpiArgs e{a.bias, a.res, a.y, a.T, a.H, a.W, a.Cout, a.res_ut, a.res_uh, a.res_uw, a.act, a.out_mode};
+        // column split between the two warps of a quarter (multiples of 16)
+        const int nh0 = ((a.n_tile / 16 + 1) / 2) * 16;
+        const int col0 = half == 0 ? 0 : nh0, ncols = half == 0 ? nh0 : a.n_tile - nh0;
+        const size_t stile_bytes = (size_t)32 * (nh0 + 4) * sizeof(float);
+        // coalesced path needs every row of the tile to be a real voxel (no batch-dimension overhang)
+        if (a.out_mode == 0 && b0 + a.bb <= a.B && 8 * stile_bytes <= (size_t)a.stages * stage_bytes) {
+            float* stile = reinterpret_cast<float*>(smem + (size_t)(warp - 2) * stile_bytes);
             const int Tr = a.T / a.res_ut, Hr = a.H / a.res_uh, Wr = a.W / a.res_uw;
-            roff = ((((long long)b * Tr + t / a.res_ut) * Hr + h / a.res_uh) * Wr + w / a.res_uw) * a.Cout;
-        }
-        for (int c0 = 0; c0 < a.n_tile; c0 += 16) {
-            uint32_t rr[16];
-            float accv[16];
-            ptx::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, rr);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) accv[j] = __uint_as_float(rr[j]);
-            for (int ai = 1; ai < a.nacc; ++ai) {
-                ptx::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ai * a.n_tile + c0), rr);
-                ptx::tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 16; ++j) accv[j] += __uint_as_float(rr[j]);
-            }
-            const int nb = n0 + c0;
-            if (!valid || nb >= a.Cout) continue;
-            float v[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int n = nb + j;
-                float x = accv[j] * scale;
-                if (n < a.Cout) {
-                    if (a.bias != nullptr) x += __ldg(a.bias + n);
-                    if (a.res != nullptr) x += __ldg(a.res + roff + n);
-                }
-                v[j] = apply_act(x, a.act);
-            }
-            if (a.out_mode == 0) {
-                float* dst = a.y + vox * a.Cout + nb;
-                if ((a.Cout & 3) == 0 && nb + 15 < a.Cout) {
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4)
-                        *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (nb + j < a.Cout) dst[j] = v[j];
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (nb + j < a.Cout)
-                        a.y[((((long long)b * a.T + t) * a.Cout + nb + j) * a.H + h) * a.W + w] = v[j];
-            }
+            const long long vox_lane = (((long long)(b0 + bi) * a.T + t0 + ti) * a.H + h0 + hi) * a.W + w0 + wi;
+            const long long roff_lane =
+                ((((long long)(b0 + bi) * Tr + (t0 + ti) / a.res_ut) * Hr + (h0 + hi) / a.res_uh) * Wr + (w0 + wi) / a.res_uw) * a.Cout;
+            if (ncols > 0)
+                epilogue_warp_coalesced(e, stile, tmem_base + ((uint32_t)(q * 32) << 16), col0, ncols, a.nacc, a.n_tile, n0,
+                                        __ldg(a.scale_ptr), lane, vox_lane, roff_lane);
+        } else if (half == 0) {
+            epilogue_row(e, tmem_base + ((uint32_t)(q * 32) << 16), a.n_tile, a.nacc, a.n_tile, n0, __ldg(a.scale_ptr), b0 + bi,
+                         t0 + ti, h0 + hi, w0 + wi, b0 + bi < a.B);
         }
     }
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 1) ptx::tmem_dealloc(tmem_base, ncols);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// v2: 256-row tile + H-halo.  The v1 kernel re-loads the activation box once per tap and is bound by
+// L2->SM bandwidth (ncu: 9.4 TB/s of xbar reads, tensor pipe 35 % on g_3.conv_0).  Here a CTA owns a
+// (bw x bh2) patch of ONE (b, t) plane = 2 sub-tiles of 128 voxels, and per (kt, kw, channel-chunk) stage
+// loads the patch ONCE with a 1-row halo above and below: box (kc, bw, bh2+2).  Because every row of the
+// box is a contiguous run of bw voxels, the A operand of sub-tile j under tap kh is the 128-row window
+// starting at box row (j*bh2/2 + kh)*bw -- a multiple of 8 rows, i.e. a 1024-byte aligned K-major SW64/
+// SW128 descriptor.  One A load therefore serves 3 kh taps x 2 sub-tiles, and one weight load (the 3 kh taps
+// of (kt, kw), fetched as a single 5-D box) serves both sub-tiles: half the L2 traffic per MMA of v1.
+struct ConvTcHArgs {
+    const float* bias; const float* res; const float* scale_ptr; float* y;
+    int B, T, H, W, Cin, Cout;
+    int kt, kw;                   // kh == 3
+    int bw, bh2;                  // patch: bw x bh2 voxels (= 256)
+    int tiles_w, tiles_h;
+    int n_tile, kc, stages, terms, nacc;
+    int res_ut, res_uh, res_uw, act, out_mode;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
+                    const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl, const ConvTcHArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t rb = (uint32_t)a.kc * 2;
+    const uint32_t a_rows = (uint32_t)(a.bw * (a.bh2 + 2));
+    const uint32_t a_bytes = (a_rows * rb + 1023u) & ~1023u;
+    const uint32_t b_tap = (uint32_t)a.n_tile * rb;                 // multiple of 1024 (host-checked)
+    const uint32_t b_bytes = 3 * b_tap;
+    const uint32_t mult = a.terms > 1 ? 2u : 1u;                    // lo words only exist in the 3-term mode
+    const uint32_t off_alo = a_bytes, off_bhi = mult * a_bytes, off_blo = mult * a_bytes + b_bytes;
+    const uint32_t stage_bytes = mult * (a_bytes + b_bytes);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)a.stages * stage_bytes);
+    uint64_t* empty = full + a.stages;
+    uint64_t* tmem_full = empty + a.stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) dbg_stamp(0);                       // CTA start
+    int tile = blockIdx.x;
+    const int tw = tile % a.tiles_w; tile /= a.tiles_w;
+    const int th = tile % a.tiles_h; tile /= a.tiles_h;
+    const int t = tile % a.T;
+    const int b = tile / a.T;
+    const int w0 = tw * a.bw, h0 = th * a.bh2;
+    const int n0 = blockIdx.y * a.n_tile;
+    const int cchunks = a.Cin / a.kc;
+    const int iters = a.kt * a.kw * cchunks;
+    const int bh_sub = a.bh2 / 2;
+    uint32_t ncols = 32;
+    while (ncols < (uint32_t)(2 * a.n_tile * a.nacc)) ncols <<= 1;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&mAh); ptx::prefetch_tensormap(&mBh);
+        if (a.terms > 1) { ptx::prefetch_tensormap(&mAl); ptx::prefetch_tensormap(&mBl); }
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < a.stages; ++s) { ptx::mbar_init(full + s, 1); ptx::mbar_init(empty + s, 1); }
+            ptx::mbar_init(tmem_full, 1);
+            ptx::fence_barrier_init();
+        }
+        __syncwarp();
+        ptx::tmem_alloc(tmem_slot, ncols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) dbg_stamp(1);                       // prologue done
+
+    // temporal taps that fall outside [0, T) contribute only zero padding: both pipeline ends skip them
+    auto tap_t = [&](int it, int& dt, int& dw, int& c0) -> bool {
+        const int tk = it / cchunks;
+        c0 = (it - tk * cchunks) * a.kc;
+        dw = tk % a.kw; dt = tk / a.kw;
+        const int ct = t + dt - a.kt / 2;
+        return ct >= 0 && ct < a.T;
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint32_t tx = (a.terms > 1 ? 2u : 1u) * (a_rows * rb + b_bytes);
+            int n = 0;
+            for (int it = 0; it < iters; ++it) {
+                int dt, dw, c0;
+                if (!tap_t(it, dt, dw, c0)) continue;
+                const int s = n % a.stages;
+                const uint32_t ph = (uint32_t)(n / a.stages) & 1u;
+                ++n;
+                ptx::mbar_wait(empty + s, ph ^ 1u);
+                uint8_t* st = smem + (size_t)s * stage_bytes;
+                const int cw = w0 + dw - a.kw / 2, ch = h0 - 1, ct = t + dt - a.kt / 2;
+                ptx::mbar_expect_tx(full + s, tx);
+                ptx::tma_load_5d(st, &mAh, full + s, c0, cw, ch, ct, b);
+                ptx::tma_load_5d(st + off_bhi, &mBh, full + s, c0, n0, dw, 0, dt);
+                if (a.terms > 1) {
+                    ptx::tma_load_5d(st + off_alo, &mAl, full + s, c0, cw, ch, ct, b);
+                    ptx::tma_load_5d(st + off_blo, &mBl, full + s, c0, n0, dw, 0, dt);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = ptx::make_idesc_f16(TILE_M, a.n_tile);
+            const int ksteps = a.kc / 16;
+            const uint64_t dproto = ptx::make_kmajor_desc(0, rb);
+            const uint32_t dlo = (uint32_t)dproto, dhi = (uint32_t)(dproto >> 32);
+            const uint32_t sub_step = (uint32_t)(bh_sub * a.bw) * rb >> 4, kh_step = (uint32_t)a.bw * rb >> 4;
+            int n = 0;
+            for (int it = 0; it < iters; ++it) {
+                int dt, dw, c0;
+                if (!tap_t(it, dt, dw, c0)) continue;
+                const int s = n % a.stages;
+                const uint32_t ph = (uint32_t)(n / a.stages) & 1u;
+                ptx::mbar_wait(full + s, ph);
+                if (n == 0) dbg_stamp(2);                     // first stage landed
+                ptx::tc_fence_after();
+                const uint32_t sa = ptx::smem_u32(smem + (size_t)s * stage_bytes);
+                const uint32_t lah = dlo + (sa >> 4), lal = lah + (off_alo >> 4);
+                const uint32_t lbh = lah + (off_bhi >> 4), lbl = lah + (off_blo >> 4);
+                const int ai = n % a.nacc;
+                const uint32_t fresh = n < a.nacc ? 0u : 1u;     // first visit of this accumulator pair -> overwrite
+                // issue order (kh, k, term, sub): back-to-back MMAs target different TMEM accumulators, so a short
+                // (N = 64) MMA never waits on the one before it
+                const uint32_t tacc0 = tmem_base + (uint32_t)(ai * a.n_tile), tacc1 = tacc0 + (uint32_t)(a.nacc * a.n_tile);
+                uint32_t acc_flag = fresh;
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh) {
+                    const uint32_t ao = (uint32_t)kh * kh_step, bo = (uint32_t)kh * (b_tap >> 4);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (k < ksteps) {
+                            const uint32_t o = (uint32_t)k * 2u;
+                            const uint64_t dAh0 = ptx::desc64(lah + ao + o, dhi), dAh1 = ptx::desc64(lah + ao + sub_step + o, dhi);
+                            const uint64_t dBh = ptx::desc64(lbh + bo + o, dhi);
+                            ptx::mma_f16_ss(tacc0, dAh0, dBh, idesc, acc_flag);
+                            ptx::mma_f16_ss(tacc1, dAh1, dBh, idesc, acc_flag);
+                            acc_flag = 1u;
+                            if (a.terms > 1) {
+                                const uint64_t dBl = ptx::desc64(lbl + bo + o, dhi);
+                                ptx::mma_f16_ss(tacc0, dAh0, dBl, idesc, 1u);
+                                ptx::mma_f16_ss(tacc1, dAh1, dBl, idesc, 1u);
+                                ptx::mma_f16_ss(tacc0, ptx::desc64(lal + ao + o, dhi), dBh, idesc, 1u);
+                                ptx::mma_f16_ss(tacc1, ptx::desc64(lal + ao + sub_step + o, dhi), dBh, idesc, 1u);
+                            }
+                        }
+                    }
+                }
+                ptx::mma_commit(empty + s);
+                ++n;
+            }
+            ptx::mma_commit(tmem_full);
+            dbg_stamp(3);                                     // last MMA issued
+        }
+    } else {
+        ptx::mbar_wait(tmem_full, 0);
+        if (threadIdx.x == 64) dbg_stamp(4);                  // accumulators complete
+        ptx::tc_fence_after();
+        int n_valid = 0;
+        for (int dt = 0; dt < a.kt; ++dt) {
+            const int ct = t + dt - a.kt / 2;
+            if (ct >= 0 && ct < a.T) n_valid += a.kw * cchunks;
+        }
+        const int nacc_used = n_valid < a.nacc ? n_valid : a.nacc;
+        const int q = warp & 3, half = (warp - 2) >> 2;       // two warps per TMEM lane quarter: column halves
+        const int m = q * 32 + lane;
+        const int wi = m % a.bw, hi = m / a.bw;
+        const float scale = __ldg(a.scale_ptr);
+        EpiArgs e{a.bias, a.res, a.y, a.T, a.H, a.W, a.Cout, a.res_ut, a.res_uh, a.res_uw, a.act, a.out_mode};
+        const int nh0 = ((a.n_tile / 16 + 1) / 2) * 16;
+        const int col0 = half == 0 ? 0 : nh0, ncols = half == 0 ? nh0 : a.n_tile - nh0;
+        const size_t stile_bytes = (size_t)32 * (nh0 + 4) * sizeof(float);
+        if (a.out_mode == 0 && 8 * stile_bytes <= (size_t)a.stages * stage_bytes) {
+            // pipeline buffers are drained (every TMA landed, every MMA retired): reuse them as transpose tiles
+            float* stile = reinterpret_cast<float*>(smem + (size_t)(warp - 2) * stile_bytes);
+            const int Tr = a.T / a.res_ut, Hr = a.H / a.res_uh, Wr = a.W / a.res_uw;
+            for (int sub = 0; sub < 2; ++sub) {
+                const int ww = w0 + wi, hh = h0 + sub * bh_sub + hi;
+                const long long vox_lane = (((long long)b * a.T + t) * a.H + hh) * a.W + ww;
+                const long long roff_lane = ((((long long)b * Tr + t / a.res_ut) * Hr + hh / a.res_uh) * Wr + ww / a.res_uw) * a.Cout;
+                if (ncols > 0)
+                    epilogue_warp_coalesced(e, stile, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * a.nacc * a.n_tile), col0,
+                                            ncols, nacc_used, a.n_tile, n0, scale, lane, vox_lane, roff_lane);
+            }
+        } else if (half == 0) {
+            for (int sub = 0; sub < 2; ++sub)
+                epilogue_row(e, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * a.nacc * a.n_tile), a.n_tile, nacc_used,
+                             a.n_tile, n0, scale, b, t, h0 + sub * bh_sub + hi, w0 + wi, true);
+        }
+    }
+    if (threadIdx.x == 64) dbg_stamp(5);                      // epilogue stores issued
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, ncols);
+    if (threadIdx.x == 0) dbg_stamp(6);                       // CTA end
 }
 
 __global__ void split_fp16_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, float scale,
@@ -258,6 +602,12 @@ bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 }  // namespace
 
+int conv_tc_set_debug(unsigned long long* buf, int ctas) {
+    I2V_CHECK_CUDA(cudaMemcpyToSymbol(g_dbg, &buf, sizeof(buf)));
+    I2V_CHECK_CUDA(cudaMemcpyToSymbol(g_dbg_ctas, &ctas, sizeof(ctas)));
+    return 0;
+}
+
 bool conv_tc_supported(int B, int T, int H, int W, int Cin, int Cout, int kt, int kh, int kw) {
     (void)B; (void)Cout;
     if (!(kt == 1 || kt == 3) || !(kh == 1 || kh == 3) || !(kw == 1 || kw == 3)) return false;
@@ -275,11 +625,88 @@ int launch_split_fp16(const float* x, __half* hi, __half* lo, float scale, long 
     return 0;
 }
 
+// v2 eligibility + launch.  Returns 1 if the shape is not eligible (caller falls through to v1).
+static int launch_conv_tc_halo(const ConvTcArgs& h, cudaStream_t stream) {
+    if (h.kh != 3 || h.W < 16 || h.H * h.W < 256) return 1;
+    ConvTcHArgs a;
+    a.bw = h.W < 128 ? h.W : 128;
+    a.bh2 = 256 / a.bw;
+    if (a.bh2 < 2 || h.H % a.bh2 != 0) return 1;
+    const int n_cap = h.terms == 3 ? 128 : 256;
+    a.n_tile = h.cout_pad < n_cap ? h.cout_pad : n_cap;
+    // channel chunk: the largest of 64/32/16 that divides Cin, keeps tap slabs 1024B-aligned and fits >= 2 stages
+    const int mult = h.terms > 1 ? 2 : 1;
+    int kc = 0, stages = 0;
+    size_t stage_bytes = 0;
+    for (int cand : {64, 32, 16}) {
+        if (h.Cin % cand) continue;
+        const size_t rb = (size_t)cand * 2;
+        if ((a.n_tile * rb) % 1024 != 0) continue;
+        const size_t a_bytes = ((size_t)a.bw * (a.bh2 + 2) * rb + 1023) & ~(size_t)1023;
+        const size_t sb = mult * (a_bytes + 3 * a.n_tile * rb);
+        const int st = (int)((220 * 1024 - 2048) / sb);
+        if (st >= 2) { kc = cand; stages = st > 6 ? 6 : st; stage_bytes = sb; break; }
+    }
+    if (kc == 0) return 1;
+    a.kc = kc; a.stages = stages; a.terms = h.terms;
+    int nacc = 512 / (2 * a.n_tile);
+    if (nacc > 4) nacc = 4;
+    const int iters = h.kt * h.kw * (h.Cin / kc);
+    if (nacc > iters) nacc = iters;
+    if (nacc < 1) return 1;
+    a.nacc = nacc;
+    a.bias = h.bias; a.res = h.res; a.scale_ptr = h.scale_ptr; a.y = h.y;
+    a.B = h.B; a.T = h.T; a.H = h.H; a.W = h.W; a.Cin = h.Cin; a.Cout = h.Cout; a.kt = h.kt; a.kw = h.kw;
+    a.tiles_w = h.W / a.bw; a.tiles_h = h.H / a.bh2;
+    a.res_ut = h.res_ut; a.res_uh = h.res_uh; a.res_uw = h.res_uw; a.act = h.act; a.out_mode = h.out_mode;
+    const int rb = kc * 2;
+
+    CUtensorMap mAh, mAl, mBh, mBl;
+    {
+        const cuuint64_t dims[5] = {(cuuint64_t)h.Cin, (cuuint64_t)h.W, (cuuint64_t)h.H, (cuuint64_t)h.T, (cuuint64_t)h.B};
+        const cuuint64_t st[4] = {(cuuint64_t)h.Cin * 2, (cuuint64_t)h.W * h.Cin * 2, (cuuint64_t)h.H * h.W * h.Cin * 2,
+                                  (cuuint64_t)h.T * h.H * h.W * h.Cin * 2};
+        const cuuint32_t box[5] = {(cuuint32_t)kc, (cuuint32_t)a.bw, (cuuint32_t)(a.bh2 + 2), 1, 1};
+        if (int rc = encode_map(&mAh, h.x_hi, 5, dims, st, box, rb)) return rc;
+        if (int rc = encode_map(&mAl, h.terms > 1 ? h.x_lo : h.x_hi, 5, dims, st, box, rb)) return rc;
+    }
+    {
+        // weights [kt][kh][kw][cout_pad][Cin] viewed as (Cin, cout_pad, kw, kh, kt) (strides ascending): the 3 kh taps of
+        // one (kt, kw) arrive as a single box -> smem [kh][n][kc]
+        const cuuint64_t row = (cuuint64_t)h.cout_pad * h.Cin * 2;
+        const cuuint64_t dims[5] = {(cuuint64_t)h.Cin, (cuuint64_t)h.cout_pad, (cuuint64_t)h.kw, 3, (cuuint64_t)h.kt};
+        const cuuint64_t st[4] = {(cuuint64_t)h.Cin * 2, row, row * h.kw, row * h.kw * 3};
+        const cuuint32_t box[5] = {(cuuint32_t)kc, (cuuint32_t)a.n_tile, 1, 3, 1};
+        if (int rc = encode_map(&mBh, h.w_hi, 5, dims, st, box, rb)) return rc;
+        if (int rc = encode_map(&mBl, h.terms > 1 ? h.w_lo : h.w_hi, 5, dims, st, box, rb)) return rc;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        I2V_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+    const long long M = (long long)h.B * h.T * h.H * h.W;
+    const double K_ = (double)h.kt * h.kh * h.kw * h.Cin;
+    ProfScope ps(PROF_CONV, 2.0 * (double)M * h.Cout * K_, 4.0 * ((double)M * h.Cin + (double)M * h.Cout + K_ * h.Cout), stream);
+    dim3 grid((unsigned)((long long)a.tiles_w * a.tiles_h * h.T * h.B), (unsigned)((h.cout_pad + a.n_tile - 1) / a.n_tile));
+    conv_tc_halo_kernel<<<grid, TC_THREADS, smem, stream>>>(mAh, mAl, mBh, mBl, a);
+    I2V_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int launch_conv_tc(const ConvTcArgs& h, cudaStream_t stream) {
     I2V_REQUIRE(conv_tc_supported(h.B, h.T, h.H, h.W, h.Cin, h.Cout, h.kt, h.kh, h.kw),
                 "conv_tc: unsupported shape B=%d T=%d H=%d W=%d Cin=%d k=(%d,%d,%d)", h.B, h.T, h.H, h.W, h.Cin, h.kt, h.kh, h.kw);
     I2V_REQUIRE(h.terms == 1 || h.terms == 3, "conv_tc: terms must be 1 or 3");
     I2V_REQUIRE(h.cout_pad % 16 == 0 && h.cout_pad >= h.Cout, "conv_tc: weights must be padded to a multiple of 16 output rows");
+    I2V_REQUIRE(h.res == nullptr || (h.T % h.res_ut == 0 && h.H % h.res_uh == 0 && h.W % h.res_uw == 0),
+                "conv_tc: residual upsample factors must divide the output size");
+    if (h.variant != 1) {
+        const int rc = launch_conv_tc_halo(h, stream);
+        if (rc <= 0) return rc;     // launched (0) or failed (<0); 1 = shape not eligible -> v1 below
+        I2V_REQUIRE(h.variant != 2, "conv_tc: shape not eligible for the halo kernel");
+    }
     ConvTcKArgs a;
     a.bias = h.bias; a.res = h.res; a.scale_ptr = h.scale_ptr; a.y = h.y;
     a.B = h.B; a.T = h.T; a.H = h.H; a.W = h.W; a.Cin = h.Cin; a.Cout = h.Cout;

@@ -34,9 +34,11 @@ struct ConvTcArgs {
     int kt, kh, kw;
     int res_ut, res_uh, res_uw, act, out_mode;
     int terms;                                // 3: hi*hi+hi*lo+lo*hi (fp32-grade)   1: hi*hi only
+    int variant = 0;                          // 0: auto (halo kernel when eligible)  1: force v1  2: force halo kernel
 };
 bool conv_tc_supported(int B, int T, int H, int W, int Cin, int Cout, int kt, int kh, int kw);
 int launch_conv_tc(const ConvTcArgs& a, cudaStream_t stream);
+int conv_tc_set_debug(unsigned long long* buf, int ctas);   // phase timestamps of the halo kernel (profiling aid)
 int launch_split_fp16(const float* x, __half* hi, __half* lo, float scale, long long n, cudaStream_t stream);
 
 // ----------------------------------------------------------------------------- normalisation

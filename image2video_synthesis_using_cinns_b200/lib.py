@@ -82,6 +82,7 @@ SIGNATURES = {
     "i2v_launch_count": (_c.c_longlong, []),
     "i2v_prof_enable": (None, [_I]),
     "i2v_prof_collect": (_I, [_P, _P, _P, _P]),
+    "i2v_prof_dump_path": (None, [_c.c_char_p]),
     "i2v_flow_create": (_P, [_I, _I, _I, _I, _I, _P]),
     "i2v_flow_set_tensor": (_I, [_P, _c.c_char_p, _P, _SZ]),
     "i2v_flow_workspace_bytes": (_SZ, [_P, _I]),
@@ -105,7 +106,8 @@ SIGNATURES = {
     "i2v_encoder3d_forward": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _SZ, _P]),
     "i2v_encoder3d_destroy": (None, [_P]),
     "i2v_op_conv": (_I, [_P] * 5 + [_I] * 21 + [_P]),
-    "i2v_op_conv_tc": (_I, [_P] * 5 + [_I] * 16 + [_F, _F, _P, _SZ, _P]),
+    "i2v_op_conv_tc": (_I, [_P] * 5 + [_I] * 17 + [_F, _F, _P, _SZ, _P]),
+    "i2v_debug_conv_tc_timestamps": (_I, [_P, _I]),
     "i2v_op_channel_stats": (_I, [_P, _P, _I, _I64, _I, _P]),
     "i2v_op_norm_coeffs": (_I, [_P, _P, _I, _I, _I64, _I, _F, _P, _P, _P, _P]),
     "i2v_op_modulate": (_I, [_P] * 6 + [_I] * 9 + [_P]),

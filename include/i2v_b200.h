@@ -49,6 +49,8 @@ const char* i2v_last_error(void);
 long long i2v_launch_count(void);
 void i2v_prof_enable(int on);
 int i2v_prof_collect(double* ms, double* flops, double* bytes, long long* launches);
+/* when set (non-NULL, non-empty) i2v_prof_collect also writes one CSV row per launch to this path */
+void i2v_prof_dump_path(const char* path);
 
 /* ---------------------------------------------------------------- conditional INN (stage 2) */
 typedef struct i2v_flow i2v_flow;
@@ -113,11 +115,16 @@ int i2v_op_conv(const float* dev_x, const float* dev_w, const float* dev_bias, c
                 int pt, int ph, int pw, int res_ut, int res_uh, int res_uw, int act, int out_mode, int engine,
                 void* stream);
 /* tensor-core conv on fp32 inputs: splits x (scale_a) and w (scale_w; [taps,cout_pad,Cin], rows >= Cout zero) into
- * fp16 (hi, lo) inside the workspace (>= 4*(|x|+|w|)+2048 bytes), then runs the tcgen05 engine; terms 3 or 1 */
+ * fp16 (hi, lo) inside the workspace (>= 4*(|x|+|w|)+2048 bytes), then runs the tcgen05 engine; terms 3 or 1;
+ * variant 0 = auto, 1 = per-tap box kernel, 2 = 256-row H-halo kernel (fails if the shape is not eligible) */
 int i2v_op_conv_tc(const float* dev_x, const float* dev_w, const float* dev_bias, const float* dev_res, float* dev_y,
                    int B, int T, int H, int W, int Cin, int Cout, int cout_pad, int kt, int kh, int kw, int res_ut,
-                   int res_uh, int res_uw, int act, int out_mode, int terms, float scale_a, float scale_w, void* dev_ws,
-                   size_t ws_bytes, void* stream);
+                   int res_uh, int res_uw, int act, int out_mode, int terms, int variant, float scale_a, float scale_w,
+                   void* dev_ws, size_t ws_bytes, void* stream);
+/* profiling aid: when dev_buf != NULL the halo conv kernel writes 8 x uint64 %globaltimer stamps per CTA (first `ctas`
+ * CTAs of grid row 0): 0 start, 1 prologue done, 2 first stage landed, 3 last MMA issued, 4 accumulators complete,
+ * 5 epilogue stores issued, 6 CTA end */
+int i2v_debug_conv_tc_timestamps(void* dev_buf, int ctas);
 /* sums[B,C,2] (double) of x[B,V,C] */
 int i2v_op_channel_stats(const float* dev_x, double* dev_sums, int B, int64_t V, int C, void* stream);
 int i2v_op_norm_coeffs(const double* dev_sums, float* dev_coef, int B, int C, int64_t V, int groups, float eps,

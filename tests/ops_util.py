@@ -100,7 +100,7 @@ def maxpool(x_cl):
     return y
 
 
-def conv_tc(x_cl, w_taps, bias, res_cl, k, res_up=(1, 1, 1), act=0, out_mode=0, terms=3, scale_a=16.0):
+def conv_tc(x_cl, w_taps, bias, res_cl, k, res_up=(1, 1, 1), act=0, out_mode=0, terms=3, scale_a=16.0, variant=0):
     """Tensor-core engine on fp32 inputs (the op splits them on the device).  w_taps [taps,Cout,Cin]."""
     import math
     L = _lib.load()
@@ -114,5 +114,5 @@ def conv_tc(x_cl, w_taps, bias, res_cl, k, res_up=(1, 1, 1), act=0, out_mode=0, 
     y = torch.empty(shape, dtype=torch.float32, device="cuda")
     ws = torch.empty(4 * (x_cl.numel() + wp.numel()) + 4096, dtype=torch.uint8, device="cuda")
     _lib.check(L.i2v_op_conv_tc(P(x_cl), P(wp), P(bias), P(res_cl), P(y), B, T, H, W, Cin, Cout, cpad, *k, *res_up, act,
-                                out_mode, terms, scale_a, scale_w, P(ws), ws.numel(), S()), "op_conv_tc")
+                                out_mode, terms, variant, scale_a, scale_w, P(ws), ws.numel(), S()), "op_conv_tc")
     return y
