@@ -423,6 +423,8 @@ static int decoder_run(const i2v_decoder* m, const float* img, const float* z, f
     float* lowin = ar.take<float>(max_low_in);
     float* lowout = ar.take<float>(max_low_out);
     double* sums = ar.take<double>((size_t)B * cmax * 2);
+    double* sums_mid = ar.take<double>((size_t)B * cmax * 2);
+    double* sums_next = ar.take<double>((size_t)B * cmax * 2);
     float* coef = ar.take<float>((size_t)B * cmax * 2);
     float* coefs = ar.take<float>((size_t)B * cmax * 2);
     float* mod = ar.take<float>((size_t)B * 2 * cmax);
@@ -436,7 +438,7 @@ static int decoder_run(const i2v_decoder* m, const float* img, const float* z, f
     // Tensor-core conv on split fp16 operands: x lives in `xbuf` as (hi | lo) halves of n_in elements each.
     auto conv_tc = [&](const std::string& wname, const float* xbuf, size_t n_in, const float* bias, const float* res, float* y,
                        int Bc, int Tc, int Hc_, int Wc_, int cin_, int cout_, int kt, int kh, int kw, int rut, int ruh, int ruw,
-                       int act, int out_mode) -> int {
+                       int act, int out_mode, double* stats_out = nullptr) -> int {
         const int cpad = (cout_ + 15) / 16 * 16;
         const size_t wn = (size_t)kt * kh * kw * cpad * cin_;
         const __half* wh = m->tt.get<__half>(wname + ".wh", wn);
@@ -449,6 +451,8 @@ static int decoder_run(const i2v_decoder* m, const float* img, const float* z, f
         a.B = Bc; a.T = Tc; a.H = Hc_; a.W = Wc_; a.Cin = cin_; a.Cout = cout_; a.cout_pad = cpad;
         a.kt = kt; a.kh = kh; a.kw = kw; a.res_ut = rut; a.res_uh = ruh; a.res_uw = ruw; a.act = act; a.out_mode = out_mode;
         a.terms = eng == 1 ? 3 : 1;
+        a.stats = stats_out;
+        if (stats_out) I2V_CHECK_CUDA(cudaMemsetAsync(stats_out, 0, sizeof(double) * 2 * (size_t)Bc * cout_, s));
         return launch_conv_tc(a, s);
     };
     // fused modulate pass writing either fp32 (SIMT engine) or the fp16 split (tensor-core engine)
@@ -471,6 +475,7 @@ static int decoder_run(const i2v_decoder* m, const float* img, const float* z, f
 
     float* x = xa; float* xn = xb;
     T = 1; Hc = 4; Wc = 4;
+    bool have_in_stats = false;     // statistics of x already produced by the previous conv_1's epilogue
     for (int i = 0; i < 6; ++i) {
         const DecBlock& k = blk[i];
         const std::string nm = k.name;
@@ -479,8 +484,9 @@ static int decoder_run(const i2v_decoder* m, const float* img, const float* z, f
         T *= k.ut; Hc *= k.uh; Wc *= k.uw;
         const long long vlow = (long long)Tl * Hl * Wl, vhi = (long long)T * Hc * Wc;
 
-        // statistics of the block input (pre-upsample)
-        I2V_TRY(launch_channel_stats(x, sums, B, vlow, cin, s));
+        // statistics of the block input (pre-upsample): fused into the producing conv when possible
+        if (!have_in_stats) I2V_TRY(launch_channel_stats(x, sums, B, vlow, cin, s));
+        const bool fuse = tc && conv_tc_fuses_stats(T, Hc, Wc);
         // SPADE maps (normalization_layer.py:20-23)
         I2V_PTR(scw, G(nm + ".spade.conv.w", (size_t)9 * 128 * 3));
         I2V_PTR(scb, G(nm + ".spade.conv.b", 128));
@@ -533,14 +539,14 @@ static int decoder_run(const i2v_decoder* m, const float* img, const float* z, f
             I2V_TRY(conv(0, bufp, w0, b0, nullptr, bufd, B, T, Hc, Wc, cin, cmid, 3, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, ACT_NONE, 0, s));
         } else {
             I2V_TRY(conv_tc(nm + ".conv_0", bufp, (size_t)B * vhi * cin, b0, nullptr, bufd, B, T, Hc, Wc, cin, cmid, 3, 3, 3, 1, 1, 1,
-                            ACT_NONE, 0));
+                            ACT_NONE, 0, fuse ? sums_mid : nullptr));
         }
         // a1 = lrelu(AdaIN(dx, z))
         I2V_PTR(aw, G(nm + ".adain.w", (size_t)2 * cmid * zd));
         I2V_PTR(ab, G(nm + ".adain.b", (size_t)2 * cmid));
         I2V_TRY(launch_linear(z, aw, ab, mod, B, zd, 2 * cmid, ACT_NONE, s));
-        I2V_TRY(launch_channel_stats(bufd, sums, B, vhi, cmid, s));
-        I2V_TRY(launch_norm_coeffs(sums, coef, B, cmid, vhi, 0, 1e-5f, nullptr, nullptr, mod, s));
+        if (!fuse) I2V_TRY(launch_channel_stats(bufd, sums_mid, B, vhi, cmid, s));
+        I2V_TRY(launch_norm_coeffs(sums_mid, coef, B, cmid, vhi, 0, 1e-5f, nullptr, nullptr, mod, s));
         I2V_TRY(modulate_to(bufd, coef, nullptr, bufp, (size_t)B * vhi * cmid, B, T, Hc, Wc, cmid, 1, 1, 1, ACT_LRELU02));
         // out = conv_1(a1) + up(xs)
         I2V_PTR(b1, G(nm + ".conv_1.b", cout));
@@ -548,9 +554,13 @@ static int decoder_run(const i2v_decoder* m, const float* img, const float* z, f
             I2V_PTR(w1, G(nm + ".conv_1.w", (size_t)27 * cout * cmid));
             I2V_TRY(conv(0, bufp, w1, b1, xs, xn, B, T, Hc, Wc, cmid, cout, 3, 3, 3, 1, 1, 1, 1, 1, 1, k.ut, k.uh, k.uw, ACT_NONE, 0, s));
         } else {
+            // the next block normalises this output: its statistics ride in the epilogue (not needed after g_4)
+            const bool fuse_out = fuse && i < 5;
             I2V_TRY(conv_tc(nm + ".conv_1", bufp, (size_t)B * vhi * cmid, b1, xs, xn, B, T, Hc, Wc, cmid, cout, 3, 3, 3, k.ut, k.uh, k.uw,
-                            ACT_NONE, 0));
+                            ACT_NONE, 0, fuse_out ? sums_next : nullptr));
+            have_in_stats = fuse_out;
         }
+        if (have_in_stats) { double* tsw = sums; sums = sums_next; sums_next = tsw; }
         float* t = x; x = xn; xn = t;
     }
     // frames = tanh(conv_img(lrelu(x)))  written as [B,T,3,H,W]

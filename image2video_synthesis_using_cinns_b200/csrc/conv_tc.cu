@@ -1,3 +1,33 @@
+__device__ __forceinline__ void flush_stats(double* stats_b, int Cout, int n0, int col0, int ncols, int lane, const float (&ssum)[4],
+                                            const float (&ssq)[4]) {
+    const int c4n = ncols >> 2;
+    const int lanes_per_row = c4n < 32 ? c4n : 32;
+    const int rsub = lane / lanes_per_row, cl = lane - rsub * lanes_per_row;
+    float s[4], q[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { s[j] = ssum[j]; q[j] = ssq[j]; }
+    // lanes that own the same column group (different row phases) combine first: fewer same-address atomics
+    if ((lanes_per_row & (lanes_per_row - 1)) == 0) {
+        for (int off = lanes_per_row; off < 32; off <<= 1) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                s[j] += __shfl_xor_sync(0xffffffffu, s[j], off);
+                q[j] += __shfl_xor_sync(0xffffffffu, q[j], off);
+            }
+        }
+        if (rsub != 0) return;
+    } else if (rsub >= 32 / lanes_per_row) {
+        return;
+    }
+    const int n = n0 + col0 + cl * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (n + j < Cout) {
+            atomicAdd(stats_b + 2 * (size_t)(n + j), (double)s[j]);
+            atomicAdd(stats_b + 2 * (size_t)(n + j) + 1, (double)q[j]);
+        }
+}
+
 // Tensor-core convolution engine for sm_100a: stride-1 "same" Conv3d/Conv2d as an implicit GEMM on
 // tcgen05.mma with TMEM accumulators, operands staged by TMA, fp32-grade accuracy from an
 // error-compensated fp16 split.
@@ -49,7 +79,7 @@ __device__ __forceinline__ void dbg_stamp(int slot) {
 constexpr int TILE_M = 128;
 
 struct ConvTcKArgs {
-    const float* bias; const float* res; const float* scale_ptr; float* y;
+    const float* bias; const float* res; const float* scale_ptr; float* y; double* stats;
     int B, T, H, W, Cin, Cout;
     int kt, kh, kw;
     int bw, bh, bt, bb;
@@ -128,7 +158,8 @@ __device__ __forceinline__ void epilogue_row(const EpiArgs& e, uint32_t tmem_lan
 // `vox_lane` / `roff_lane`: output voxel index and residual element offset of THIS lane's row.
 __device__ __forceinline__ void epilogue_warp_coalesced(const EpiArgs& e, float* stile /* [32][ncols+4] */, uint32_t tmem_lane_base,
                                                         int col0, int ncols, int nacc, int acc_stride, int n0, float scale, int lane,
-                                                        long long vox_lane, long long roff_lane) {
+                                                        long long vox_lane, long long roff_lane, bool want_stats, float (&ssum)[4],
+                                                        float (&ssq)[4]) {
     // this warp owns tile columns [col0, col0+ncols) of its 32 rows
     const int ld = ncols + 4;
     int c0 = 0;
@@ -204,20 +235,43 @@ __device__ __forceinline__ void epilogue_warp_coalesced(const EpiArgs& e, float*
                     const float4 r4 = __ldg(reinterpret_cast<const float4*>(e.res + roff + n));
                     v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
                 }
-                *reinterpret_cast<float4*>(e.y + vox * e.Cout + n) =
-                    make_float4(apply_act(v[0], e.act), apply_act(v[1], e.act), apply_act(v[2], e.act), apply_act(v[3], e.act));
+                const float4 o4 = make_float4(apply_act(v[0], e.act), apply_act(v[1], e.act), apply_act(v[2], e.act), apply_act(v[3], e.act));
+                *reinterpret_cast<float4*>(e.y + vox * e.Cout + n) = o4;
+                if (want_stats) {   // per-(sample, channel) sum / sum of squares of the stored values (feeds the next norm)
+                    ssum[0] += o4.x; ssum[1] += o4.y; ssum[2] += o4.z; ssum[3] += o4.w;
+                    ssq[0] = fmaf(o4.x, o4.x, ssq[0]); ssq[1] = fmaf(o4.y, o4.y, ssq[1]);
+                    ssq[2] = fmaf(o4.z, o4.z, ssq[2]); ssq[3] = fmaf(o4.w, o4.w, ssq[3]);
+                }
             } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     if (n + j < e.Cout) {
                         float x = v[j];
                         if (e.res != nullptr) x += __ldg(e.res + roff + n + j);
-                        e.y[vox * e.Cout + n + j] = apply_act(x, e.act);
+                        x = apply_act(x, e.act);
+                        e.y[vox * e.Cout + n + j] = x;
+                        if (want_stats) { ssum[j] += x; ssq[j] = fmaf(x, x, ssq[j]); }
                     }
             }
         }
     }
     __syncwarp();
+}
+
+// flush a lane's column-group partial sums into stats[b, c, {sum, sumsq}] (double, device-wide atomics)
+__device__ __forceinline__ void flush_stats(double* stats_b, int Cout, int n0, int col0, int ncols, int lane, const float (&ssum)[4],
+                                            const float (&ssq)[4]) {
+    const int c4n = ncols >> 2;
+    const int lanes_per_row = c4n < 32 ? c4n : 32;
+    const int rsub = lane / lanes_per_row, cl = lane - rsub * lanes_per_row;
+    if (rsub >= 32 / lanes_per_row) return;
+    const int n = n0 + col0 + cl * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (n + j < Cout) {
+            atomicAdd(stats_b + 2 * (size_t)(n + j), (double)ssum[j]);
+            atomicAdd(stats_b + 2 * (size_t)(n + j) + 1, (double)ssq[j]);
+        }
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -347,9 +401,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
             const long long vox_lane = (((long long)(b0 + bi) * a.T + t0 + ti) * a.H + h0 + hi) * a.W + w0 + wi;
             const long long roff_lane =
                 ((((long long)(b0 + bi) * Tr + (t0 + ti) / a.res_ut) * Hr + (h0 + hi) / a.res_uh) * Wr + (w0 + wi) / a.res_uw) * a.Cout;
-            if (ncols > 0)
+            if (ncols > 0) {
+                float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};
+                const bool want_stats = a.stats != nullptr;     // host guarantees bb == 1 (one sample per tile) and ncols <= 128
                 epilogue_warp_coalesced(e, stile, tmem_base + ((uint32_t)(q * 32) << 16), col0, ncols, a.nacc, a.n_tile, n0,
-                                        __ldg(a.scale_ptr), lane, vox_lane, roff_lane);
+                                        __ldg(a.scale_ptr), lane, vox_lane, roff_lane, want_stats, ssum, ssq);
+                if (want_stats) flush_stats(a.stats + (size_t)b0 * a.Cout * 2, a.Cout, n0, col0, ncols, lane, ssum, ssq);
+            }
         } else if (half == 0) {
             epilogue_row(e, tmem_base + ((uint32_t)(q * 32) << 16), a.n_tile, a.nacc, a.n_tile, n0, __ldg(a.scale_ptr), b0 + bi,
                          t0 + ti, h0 + hi, w0 + wi, b0 + bi < a.B);
@@ -370,7 +428,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
 // SW128 descriptor.  One A load therefore serves 3 kh taps x 2 sub-tiles, and one weight load (the 3 kh taps
 // of (kt, kw), fetched as a single 5-D box) serves both sub-tiles: half the L2 traffic per MMA of v1.
 struct ConvTcHArgs {
-    const float* bias; const float* res; const float* scale_ptr; float* y;
+    const float* bias; const float* res; const float* scale_ptr; float* y; double* stats;
     int B, T, H, W, Cin, Cout;
     int kt, kw;                   // kh == 3
     int bw, bh2;                  // patch: bw x bh2 voxels (= 256)
@@ -538,14 +596,17 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
             // pipeline buffers are drained (every TMA landed, every MMA retired): reuse them as transpose tiles
             float* stile = reinterpret_cast<float*>(smem + (size_t)(warp - 2) * stile_bytes);
             const int Tr = a.T / a.res_ut, Hr = a.H / a.res_uh, Wr = a.W / a.res_uw;
+            float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};
+            const bool want_stats = a.stats != nullptr;
             for (int sub = 0; sub < 2; ++sub) {
                 const int ww = w0 + wi, hh = h0 + sub * bh_sub + hi;
                 const long long vox_lane = (((long long)b * a.T + t) * a.H + hh) * a.W + ww;
                 const long long roff_lane = ((((long long)b * Tr + t / a.res_ut) * Hr + hh / a.res_uh) * Wr + ww / a.res_uw) * a.Cout;
                 if (ncols > 0)
                     epilogue_warp_coalesced(e, stile, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * a.nacc * a.n_tile), col0,
-                                            ncols, nacc_used, a.n_tile, n0, scale, lane, vox_lane, roff_lane);
+                                            ncols, nacc_used, a.n_tile, n0, scale, lane, vox_lane, roff_lane, want_stats, ssum, ssq);
             }
+            if (want_stats && ncols > 0) flush_stats(a.stats + (size_t)b * a.Cout * 2, a.Cout, n0, col0, ncols, lane, ssum, ssq);
         } else if (half == 0) {
             for (int sub = 0; sub < 2; ++sub)
                 epilogue_row(e, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * a.nacc * a.n_tile), a.n_tile, nacc_used,
@@ -608,6 +669,10 @@ int conv_tc_set_debug(unsigned long long* buf, int ctas) {
     return 0;
 }
 
+// True when the epilogue of launch_conv_tc can also produce the per-(sample, channel) sums of its output
+// (every 128/256-row tile lies inside one sample and takes the coalesced channels-last path).
+bool conv_tc_fuses_stats(int T, int H, int W) { return (long long)T * H * W >= 128; }
+
 bool conv_tc_supported(int B, int T, int H, int W, int Cin, int Cout, int kt, int kh, int kw) {
     (void)B; (void)Cout;
     if (!(kt == 1 || kt == 3) || !(kh == 1 || kh == 3) || !(kw == 1 || kw == 3)) return false;
@@ -655,7 +720,8 @@ static int launch_conv_tc_halo(const ConvTcArgs& h, cudaStream_t stream) {
     if (nacc > iters) nacc = iters;
     if (nacc < 1) return 1;
     a.nacc = nacc;
-    a.bias = h.bias; a.res = h.res; a.scale_ptr = h.scale_ptr; a.y = h.y;
+    a.bias = h.bias; a.res = h.res; a.scale_ptr = h.scale_ptr; a.y = h.y; a.stats = h.stats;
+    I2V_REQUIRE(h.stats == nullptr || (h.out_mode == 0 && a.n_tile <= 256), "conv_tc: fused statistics need channels-last output");
     a.B = h.B; a.T = h.T; a.H = h.H; a.W = h.W; a.Cin = h.Cin; a.Cout = h.Cout; a.kt = h.kt; a.kw = h.kw;
     a.tiles_w = h.W / a.bw; a.tiles_h = h.H / a.bh2;
     a.res_ut = h.res_ut; a.res_uh = h.res_uh; a.res_uw = h.res_uw; a.act = h.act; a.out_mode = h.out_mode;
@@ -686,6 +752,11 @@ static int launch_conv_tc_halo(const ConvTcArgs& h, cudaStream_t stream) {
         attr_set = true;
     }
     const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+    {
+        const size_t nh0 = (size_t)((a.n_tile / 16 + 1) / 2) * 16;
+        I2V_REQUIRE(h.stats == nullptr || 8 * 32 * (nh0 + 4) * sizeof(float) <= (size_t)stages * stage_bytes,
+                    "conv_tc: transpose tiles do not fit the pipeline buffers, fused statistics unavailable");
+    }
     const long long M = (long long)h.B * h.T * h.H * h.W;
     const double K_ = (double)h.kt * h.kh * h.kw * h.Cin;
     ProfScope ps(PROF_CONV, 2.0 * (double)M * h.Cout * K_, 4.0 * ((double)M * h.Cin + (double)M * h.Cout + K_ * h.Cout), stream);
@@ -708,7 +779,7 @@ int launch_conv_tc(const ConvTcArgs& h, cudaStream_t stream) {
         I2V_REQUIRE(h.variant != 2, "conv_tc: shape not eligible for the halo kernel");
     }
     ConvTcKArgs a;
-    a.bias = h.bias; a.res = h.res; a.scale_ptr = h.scale_ptr; a.y = h.y;
+    a.bias = h.bias; a.res = h.res; a.scale_ptr = h.scale_ptr; a.y = h.y; a.stats = h.stats;
     a.B = h.B; a.T = h.T; a.H = h.H; a.W = h.W; a.Cin = h.Cin; a.Cout = h.Cout;
     a.kt = h.kt; a.kh = h.kh; a.kw = h.kw;
     a.kc = h.Cin % 64 == 0 ? 64 : (h.Cin % 32 == 0 ? 32 : 16);
@@ -720,6 +791,8 @@ int launch_conv_tc(const ConvTcArgs& h, cudaStream_t stream) {
     a.bb = rem;
     a.tiles_w = h.W / a.bw; a.tiles_h = h.H / a.bh; a.tiles_t = h.T / a.bt;
     const int tiles_b = (h.B + a.bb - 1) / a.bb;
+    I2V_REQUIRE(h.stats == nullptr || (a.bb == 1 && h.out_mode == 0),
+                "conv_tc: fused statistics need one sample per tile (ask conv_tc_fuses_stats first)");
     // fp32-grade mode keeps N <= 128 so that four TMEM accumulators fit (see the MMA issuer)
     const int n_cap = h.terms == 3 ? 128 : 256;
     a.n_tile = h.cout_pad < n_cap ? h.cout_pad : n_cap;
@@ -743,6 +816,11 @@ int launch_conv_tc(const ConvTcArgs& h, cudaStream_t stream) {
     I2V_REQUIRE(stages >= 2, "conv_tc: tile does not fit two pipeline stages");
     a.stages = stages;
     const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+    {
+        const size_t nh0 = (size_t)((a.n_tile / 16 + 1) / 2) * 16;
+        I2V_REQUIRE(h.stats == nullptr || 8 * 32 * (nh0 + 4) * sizeof(float) <= (size_t)stages * stage_bytes,
+                    "conv_tc: transpose tiles do not fit the pipeline buffers, fused statistics unavailable");
+    }
 
     CUtensorMap mAh, mAl, mBh, mBl;
     {

@@ -30,12 +30,14 @@ struct ConvTcArgs {
     const __half* w_hi; const __half* w_lo;   // [taps,cout_pad,Cin] weights * s_w, split (rows >= Cout are zero)
     const float* scale_ptr;                   // device scalar 1/(s_a*s_w)
     const float* bias; const float* res; float* y;
+    double* stats = nullptr;                  // optional fused output statistics [B, Cout, 2] (must be zeroed by the caller)
     int B, T, H, W, Cin, Cout, cout_pad;
     int kt, kh, kw;
     int res_ut, res_uh, res_uw, act, out_mode;
     int terms;                                // 3: hi*hi+hi*lo+lo*hi (fp32-grade)   1: hi*hi only
     int variant = 0;                          // 0: auto (halo kernel when eligible)  1: force v1  2: force halo kernel
 };
+bool conv_tc_fuses_stats(int T, int H, int W);
 bool conv_tc_supported(int B, int T, int H, int W, int Cin, int Cout, int kt, int kh, int kw);
 int launch_conv_tc(const ConvTcArgs& a, cudaStream_t stream);
 int conv_tc_set_debug(unsigned long long* buf, int ctas);   // phase timestamps of the halo kernel (profiling aid)

@@ -184,11 +184,13 @@ class Generator(_Native):
 
     _destroy = "i2v_decoder_destroy"
 
-    def __init__(self, state_dict, dic, device="cuda", conv_engine=0, micro_batch=16):
+    def __init__(self, state_dict, dic, device="cuda", conv_engine=1, micro_batch=16):
         super().__init__(device)
         self.nf, self.z_dim = dic["channel_factor"], dic["z_dim"]
         self.upsample_s, self.upsample_t = list(dic["upsample_s"]), list(dic["upsample_t"])
         self.micro_batch = micro_batch
+        if conv_engine >= 1 and self.nf % 16 != 0:
+            conv_engine = 0      # tensor-core tiles need channel counts that are multiples of 16
         us = (ctypes.c_int * 2)(*self.upsample_s)
         ut = (ctypes.c_int * 2)(*self.upsample_t)
         self.h = self.L.i2v_decoder_create(self.nf, self.z_dim, us, ut, conv_engine)

@@ -15,11 +15,12 @@ def _model(mp, vid_length, transfer, **kw):
     return Model(mp, vid_length, transfer=transfer, **kw)
 
 
+@pytest.mark.parametrize("engine", [1, 0], ids=["tensorcore", "simt"])
 @pytest.mark.parametrize("name", GOLDEN_CASES)
-def test_model_matches_reference_fixture(name, ckpt_cache):
+def test_model_matches_reference_fixture(name, engine, ckpt_cache):
     meta, g = load_golden(name)
     mp = ckpt_cache(**meta["ck"])
-    m = _model(mp, meta["vid_length"], meta["transfer"])
+    m = _model(mp, meta["vid_length"], meta["transfer"], conv_engine=engine)
     img = m.config.Data["img_size"]
     x0, q, pos = golden_inputs(meta, img)
     control = m.flow.control
@@ -38,7 +39,7 @@ def test_model_matches_reference_fixture(name, ckpt_cache):
     # frames bar: 1e-4, or the reference's own noise floor where the 64x64 InstanceNorm embedder
     # makes it less stable than that (golden_util.conditioned_tolerance)
     tol_f = conditioned_tolerance(lambda a: om.forward(a, g["residual"], cond, batch_slice=False), (x0,))
-    report("fixture:" + name, embed=e_embed, z=e_z, frames=e_frames, frames_tol=tol_f)
+    report(f"fixture:{name}:engine{engine}", embed=e_embed, z=e_z, frames=e_frames, frames_tol=tol_f)
     assert e_frames < tol_f
     assert rel_inf(frames.double().sum(dim=(2, 3, 4)).cpu(), g["frames_sum"]) < 1e-4
     assert e_z < TOL
