@@ -1,0 +1,63 @@
+"""N>1 host logic on CPU: batch sharding + gather (gloo, world_size 2) equals the single-process result."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from image2video_synthesis_using_cinns_b200.dist import shard_bounds, sharded_sample
+
+
+def test_shard_bounds_cover_everything():
+    for n in (0, 1, 5, 64, 65, 513):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _fake_sample(x, r, c):
+    # stands in for Model.sample: per-sample, deterministic, (b, T=2, C=1, H=1, W=3)
+    base = x.sum(dim=(1, 2, 3)).reshape(-1, 1) + r.sum(1, keepdim=True)
+    if c is not None:
+        base = base + c.sum(1, keepdim=True)
+    return (base[:, None, None, None, :] * torch.arange(1, 7.0).reshape(1, 2, 1, 1, 3)).contiguous()
+
+
+def _worker(rank, world, port, n, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(n, 3, 4, 4, generator=g)
+    r = torch.randn(n, 8, generator=g)
+    c = torch.rand(n, 3, generator=g)
+    out = sharded_sample(_fake_sample, x, r, c)
+    if rank == 0:
+        q.put(out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [5, 1])
+def test_sharded_sample_matches_single_process(n):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(n, 3, 4, 4, generator=g)
+    r = torch.randn(n, 8, generator=g)
+    c = torch.rand(n, 3, generator=g)
+    assert torch.equal(got, _fake_sample(x, r, c))
