@@ -438,12 +438,12 @@ static int decoder_run(const i2v_decoder* m, const float* img, const float* z, f
     // Tensor-core conv on split fp16 operands: x lives in `xbuf` as (hi | lo) halves of n_in elements each.
     auto conv_tc = [&](const std::string& wname, const float* xbuf, size_t n_in, const float* bias, const float* res, float* y,
                        int Bc, int Tc, int Hc_, int Wc_, int cin_, int cout_, int kt, int kh, int kw, int rut, int ruh, int ruw,
-                       int act, int out_mode, double* stats_out = nullptr) -> int {
+                       int act, int out_mode, double* stats_out = nullptr, int t_phase = 0) -> int {
         const int cpad = (cout_ + 15) / 16 * 16;
-        const size_t wn = (size_t)kt * kh * kw * cpad * cin_;
-        const __half* wh = m->tt.get<__half>(wname + ".wh", wn);
-        const __half* wl = m->tt.get<__half>(wname + ".wl", wn);
-        const float* ws = m->tt.get(wname + ".ws", 1);
+        const size_t wn = (size_t)(t_phase ? 4 : kt) * kh * kw * cpad * cin_;
+        const __half* wh = m->tt.get<__half>(wname + (t_phase ? ".wph" : ".wh"), wn);
+        const __half* wl = m->tt.get<__half>(wname + (t_phase ? ".wpl" : ".wl"), wn);
+        const float* ws = m->tt.get(wname + (t_phase ? ".wps" : ".ws"), 1);
         if (!wh || !wl || !ws) return -3;
         ConvTcArgs a;
         a.x_hi = reinterpret_cast<const __half*>(xbuf); a.x_lo = a.x_hi + n_in;
@@ -452,6 +452,7 @@ static int decoder_run(const i2v_decoder* m, const float* img, const float* z, f
         a.kt = kt; a.kh = kh; a.kw = kw; a.res_ut = rut; a.res_uh = ruh; a.res_uw = ruw; a.act = act; a.out_mode = out_mode;
         a.terms = eng == 1 ? 3 : 1;
         a.stats = stats_out;
+        a.t_phase = t_phase;
         if (stats_out) I2V_CHECK_CUDA(cudaMemsetAsync(stats_out, 0, sizeof(double) * 2 * (size_t)Bc * cout_, s));
         return launch_conv_tc(a, s);
     };
@@ -514,7 +515,11 @@ static int decoder_run(const i2v_decoder* m, const float* img, const float* z, f
         int groups = 16;
         while (cin % groups) --groups;
         I2V_TRY(launch_norm_coeffs(sums, coef, B, cin, vlow, groups, 1e-5f, nullptr, nullptr, nullptr, s));
-        I2V_TRY(modulate_to(x, coef, gb, bufp, (size_t)B * vhi * cin, B, T, Hc, Wc, cin, k.ut, k.uh, k.uw, ACT_LRELU02));
+        // conv_0 behind a x2 temporal upsample: keep a0 at T/2 and let the conv use its 2-tap phase form
+        const bool phase = tc && k.ut == 2 && m->tt.has(nm + ".conv_0.wph") && conv_tc_halo_eligible(Hc, Wc, 3);
+        const int Ta = phase ? T / 2 : T;                       // stored planes of a0
+        const size_t n_a0 = (size_t)B * Ta * Hc * Wc * cin;
+        I2V_TRY(modulate_to(x, coef, gb, bufp, n_a0, B, Ta, Hc, Wc, cin, phase ? 1 : k.ut, k.uh, k.uw, ACT_LRELU02));
         // shortcut at low resolution
         const float* xs = x;
         if (cin != cout) {
@@ -538,8 +543,8 @@ static int decoder_run(const i2v_decoder* m, const float* img, const float* z, f
             I2V_PTR(w0, G(nm + ".conv_0.w", (size_t)27 * cmid * cin));
             I2V_TRY(conv(0, bufp, w0, b0, nullptr, bufd, B, T, Hc, Wc, cin, cmid, 3, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, ACT_NONE, 0, s));
         } else {
-            I2V_TRY(conv_tc(nm + ".conv_0", bufp, (size_t)B * vhi * cin, b0, nullptr, bufd, B, T, Hc, Wc, cin, cmid, 3, 3, 3, 1, 1, 1,
-                            ACT_NONE, 0, fuse ? sums_mid : nullptr));
+            I2V_TRY(conv_tc(nm + ".conv_0", bufp, n_a0, b0, nullptr, bufd, B, T, Hc, Wc, cin, cmid, 3, 3, 3, 1, 1, 1,
+                            ACT_NONE, 0, fuse ? sums_mid : nullptr, phase ? 1 : 0));
         }
         // a1 = lrelu(AdaIN(dx, z))
         I2V_PTR(aw, G(nm + ".adain.w", (size_t)2 * cmid * zd));

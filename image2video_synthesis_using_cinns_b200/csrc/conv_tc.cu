@@ -1,33 +1,3 @@
-__device__ __forceinline__ void flush_stats(double* stats_b, int Cout, int n0, int col0, int ncols, int lane, const float (&ssum)[4],
-                                            const float (&ssq)[4]) {
-    const int c4n = ncols >> 2;
-    const int lanes_per_row = c4n < 32 ? c4n : 32;
-    const int rsub = lane / lanes_per_row, cl = lane - rsub * lanes_per_row;
-    float s[4], q[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { s[j] = ssum[j]; q[j] = ssq[j]; }
-    // lanes that own the same column group (different row phases) combine first: fewer same-address atomics
-    if ((lanes_per_row & (lanes_per_row - 1)) == 0) {
-        for (int off = lanes_per_row; off < 32; off <<= 1) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                s[j] += __shfl_xor_sync(0xffffffffu, s[j], off);
-                q[j] += __shfl_xor_sync(0xffffffffu, q[j], off);
-            }
-        }
-        if (rsub != 0) return;
-    } else if (rsub >= 32 / lanes_per_row) {
-        return;
-    }
-    const int n = n0 + col0 + cl * 4;
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-        if (n + j < Cout) {
-            atomicAdd(stats_b + 2 * (size_t)(n + j), (double)s[j]);
-            atomicAdd(stats_b + 2 * (size_t)(n + j) + 1, (double)q[j]);
-        }
-}
-
 // Tensor-core convolution engine for sm_100a: stride-1 "same" Conv3d/Conv2d as an implicit GEMM on
 // tcgen05.mma with TMEM accumulators, operands staged by TMA, fp32-grade accuracy from an
 // error-compensated fp16 split.
@@ -264,13 +234,28 @@ __device__ __forceinline__ void flush_stats(double* stats_b, int Cout, int n0, i
     const int c4n = ncols >> 2;
     const int lanes_per_row = c4n < 32 ? c4n : 32;
     const int rsub = lane / lanes_per_row, cl = lane - rsub * lanes_per_row;
-    if (rsub >= 32 / lanes_per_row) return;
+    float s[4], q[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { s[j] = ssum[j]; q[j] = ssq[j]; }
+    // lanes that own the same column group (different row phases) combine first: fewer same-address atomics
+    if ((lanes_per_row & (lanes_per_row - 1)) == 0) {
+        for (int off = lanes_per_row; off < 32; off <<= 1) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                s[j] += __shfl_xor_sync(0xffffffffu, s[j], off);
+                q[j] += __shfl_xor_sync(0xffffffffu, q[j], off);
+            }
+        }
+        if (rsub != 0) return;
+    } else if (rsub >= 32 / lanes_per_row) {
+        return;
+    }
     const int n = n0 + col0 + cl * 4;
 #pragma unroll
     for (int j = 0; j < 4; ++j)
         if (n + j < Cout) {
-            atomicAdd(stats_b + 2 * (size_t)(n + j), (double)ssum[j]);
-            atomicAdd(stats_b + 2 * (size_t)(n + j) + 1, (double)ssq[j]);
+            atomicAdd(stats_b + 2 * (size_t)(n + j), (double)s[j]);
+            atomicAdd(stats_b + 2 * (size_t)(n + j) + 1, (double)q[j]);
         }
 }
 
@@ -317,39 +302,64 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    // warp-uniform by construction; the shuffle tells the compiler so (TMEM addresses feed uniform registers)
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
+    // A tap whose shifted box lies entirely in the zero padding contributes nothing (head_0: T = 1, so 18 of
+    // the 27 taps): producer, issuer and epilogue all skip it.
+    auto tap_ok = [&](int it, int& tap, int& c0, int& cw, int& ch, int& ct) -> bool {
+        tap = it / cchunks;
+        c0 = (it - tap * cchunks) * a.kc;
+        const int dw = tap % a.kw, dh = (tap / a.kw) % a.kh, dt = tap / (a.kw * a.kh);
+        cw = w0 + dw - a.kw / 2; ch = h0 + dh - a.kh / 2; ct = t0 + dt - a.kt / 2;
+        return cw + a.bw > 0 && cw < a.W && ch + a.bh > 0 && ch < a.H && ct + a.bt > 0 && ct < a.T;
+    };
+
+    // Role loops run on the WHOLE warp with warp-uniform control flow; only the asynchronous instructions are
+    // predicated on one elected lane.  (Running the loop under `if (lane == 0)` makes every operand a
+    // divergent value that has to be moved into uniform registers one MMA at a time.)
     if (warp == 0) {
-        // ================================ TMA producer (one lane)
-        if (lane == 0) {
+        // ================================ TMA producer
+        {
             const uint32_t tx = (a.terms > 1 ? 2u : 1u) * (a_bytes + (uint32_t)a.n_tile * rb);
+            int n = 0;
             for (int it = 0; it < iters; ++it) {
-                const int s = it % a.stages;
-                const uint32_t ph = (uint32_t)(it / a.stages) & 1u;
+                int tap, c0, cw, ch, ct;
+                if (!tap_ok(it, tap, c0, cw, ch, ct)) continue;
+                const int s = n % a.stages;
+                const uint32_t ph = (uint32_t)(n / a.stages) & 1u;
+                ++n;
                 ptx::mbar_wait(empty + s, ph ^ 1u);
-                const int tap = it / cchunks, c0 = (it - tap * cchunks) * a.kc;
-                const int dw = tap % a.kw, dh = (tap / a.kw) % a.kh, dt = tap / (a.kw * a.kh);
-                const int cw = w0 + dw - a.kw / 2, ch = h0 + dh - a.kh / 2, ct = t0 + dt - a.kt / 2;
                 uint8_t* st = smem + (size_t)s * stage_bytes;
-                ptx::mbar_expect_tx(full + s, tx);
-                ptx::tma_load_5d(st, &mAh, full + s, c0, cw, ch, ct, b0);
-                ptx::tma_load_3d(st + 2 * a_bytes, &mBh, full + s, c0, n0, tap);
-                if (a.terms > 1) {
-                    ptx::tma_load_5d(st + a_bytes, &mAl, full + s, c0, cw, ch, ct, b0);
-                    ptx::tma_load_3d(st + 2 * a_bytes + b_bytes, &mBl, full + s, c0, n0, tap);
+                if (ptx::elect_one()) {
+                    ptx::mbar_expect_tx(full + s, tx);
+                    ptx::tma_load_5d(st, &mAh, full + s, c0, cw, ch, ct, b0);
+                    ptx::tma_load_3d(st + 2 * a_bytes, &mBh, full + s, c0, n0, tap);
+                    if (a.terms > 1) {
+                        ptx::tma_load_5d(st + a_bytes, &mAl, full + s, c0, cw, ch, ct, b0);
+                        ptx::tma_load_3d(st + 2 * a_bytes + b_bytes, &mBl, full + s, c0, n0, tap);
+                    }
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
-        // ================================ MMA issuer (one lane)
-        if (lane == 0) {
+        // ================================ MMA issuer
+        {
             const uint32_t idesc = ptx::make_idesc_f16(TILE_M, a.n_tile);
             const int ksteps = a.kc / 16;
             const uint64_t dproto = ptx::make_kmajor_desc(0, rb);
             const uint32_t dlo = (uint32_t)dproto, dhi = (uint32_t)(dproto >> 32);
+            int n = 0, n_total = 0;
             for (int it = 0; it < iters; ++it) {
-                const int s = it % a.stages;
-                const uint32_t ph = (uint32_t)(it / a.stages) & 1u;
+                int tap, c0, cw, ch, ct;
+                if (tap_ok(it, tap, c0, cw, ch, ct)) ++n_total;
+            }
+            for (int it = 0; it < iters; ++it) {
+                int tap, c0, cw, ch, ct;
+                if (!tap_ok(it, tap, c0, cw, ch, ct)) continue;
+                const int s = n % a.stages;
+                const uint32_t ph = (uint32_t)(n / a.stages) & 1u;
                 ptx::mbar_wait(full + s, ph);
                 ptx::tc_fence_after();
                 const uint32_t sa = ptx::smem_u32(smem + (size_t)s * stage_bytes);
@@ -360,27 +370,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
                 // round-robin over `nacc` TMEM accumulators: the tensor core's fp32 accumulate truncates, so
                 // the chain of dependent adds per accumulator is cut nacc-fold and the partial sums are
                 // combined with round-to-nearest fp32 adds in the epilogue
-                const uint32_t tacc = tmem_base + (uint32_t)((it % a.nacc) * a.n_tile);
-                uint32_t acc_flag = it >= a.nacc ? 1u : 0u;
+                const uint32_t tacc = tmem_base + (uint32_t)((n % a.nacc) * a.n_tile);
+                uint32_t acc_flag = n >= a.nacc ? 1u : 0u;
+                if (ptx::elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (k < ksteps) {
-                        const uint32_t o = (uint32_t)k * 2u;          // 16 fp16 = 32 B along K, in 16-byte units
-                        ptx::mma_f16_ss(tacc, ptx::desc64(lah + o, dhi), ptx::desc64(lbh + o, dhi), idesc, acc_flag);
-                        acc_flag = 1u;
-                        if (a.terms > 1) {
-                            ptx::mma_f16_ss(tacc, ptx::desc64(lah + o, dhi), ptx::desc64(lbl + o, dhi), idesc, 1u);
-                            ptx::mma_f16_ss(tacc, ptx::desc64(lal + o, dhi), ptx::desc64(lbh + o, dhi), idesc, 1u);
+                    for (int k = 0; k < 4; ++k) {
+                        if (k < ksteps) {
+                            const uint32_t o = (uint32_t)k * 2u;          // 16 fp16 = 32 B along K, in 16-byte units
+                            ptx::mma_f16_ss(tacc, ptx::desc64(lah + o, dhi), ptx::desc64(lbh + o, dhi), idesc, acc_flag);
+                            acc_flag = 1u;
+                            if (a.terms > 1) {
+                                ptx::mma_f16_ss(tacc, ptx::desc64(lah + o, dhi), ptx::desc64(lbl + o, dhi), idesc, 1u);
+                                ptx::mma_f16_ss(tacc, ptx::desc64(lal + o, dhi), ptx::desc64(lbh + o, dhi), idesc, 1u);
+                            }
                         }
                     }
+                    ptx::mma_commit(empty + s);        // frees the smem stage once these MMAs have read it
+                    if (n == n_total - 1) ptx::mma_commit(tmem_full);   // accumulator complete
                 }
-                ptx::mma_commit(empty + s);        // frees the smem stage once these MMAs have read it
+                __syncwarp();
+                ++n;
             }
-            ptx::mma_commit(tmem_full);            // accumulator complete
         }
     } else {
-        // ================================ epilogue (4 warps, one TMEM lane quarter each)
-        ptx::mbar_wait(tmem_full, 0);
+        // ================================ epilogue (8 warps, two per TMEM lane quarter)
+        ptx::mbar_wait_backoff(tmem_full, 0);
         ptx::tc_fence_after();
         const int q = warp & 3, half = (warp - 2) >> 2;       // two warps per TMEM lane quarter: column halves
         const int m = q * 32 + lane;
@@ -390,6 +404,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
         const int ti = r % a.bt;
         const int bi = r / a.bt;
         EpiArgs e{a.bias, a.res, a.y, a.T, a.H, a.W, a.Cout, a.res_ut, a.res_uh, a.res_uw, a.act, a.out_mode};
+        int n_total = 0;
+        for (int it = 0; it < iters; ++it) {
+            int tap, c0, cw, ch, ct;
+            if (tap_ok(it, tap, c0, cw, ch, ct)) ++n_total;
+        }
+        const int nacc_used = n_total < a.nacc ? n_total : a.nacc;
         // column split between the two warps of a quarter (multiples of 16)
         const int nh0 = ((a.n_tile / 16 + 1) / 2) * 16;
         const int col0 = half == 0 ? 0 : nh0, ncols = half == 0 ? nh0 : a.n_tile - nh0;
@@ -404,12 +424,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
             if (ncols > 0) {
                 float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};
                 const bool want_stats = a.stats != nullptr;     // host guarantees bb == 1 (one sample per tile) and ncols <= 128
-                epilogue_warp_coalesced(e, stile, tmem_base + ((uint32_t)(q * 32) << 16), col0, ncols, a.nacc, a.n_tile, n0,
+                epilogue_warp_coalesced(e, stile, tmem_base + ((uint32_t)(q * 32) << 16), col0, ncols, nacc_used, a.n_tile, n0,
                                         __ldg(a.scale_ptr), lane, vox_lane, roff_lane, want_stats, ssum, ssq);
                 if (want_stats) flush_stats(a.stats + (size_t)b0 * a.Cout * 2, a.Cout, n0, col0, ncols, lane, ssum, ssq);
             }
         } else if (half == 0) {
-            epilogue_row(e, tmem_base + ((uint32_t)(q * 32) << 16), a.n_tile, a.nacc, a.n_tile, n0, __ldg(a.scale_ptr), b0 + bi,
+            epilogue_row(e, tmem_base + ((uint32_t)(q * 32) << 16), a.n_tile, nacc_used, a.n_tile, n0, __ldg(a.scale_ptr), b0 + bi,
                          t0 + ti, h0 + hi, w0 + wi, b0 + bi < a.B);
         }
     }
@@ -431,6 +451,7 @@ struct ConvTcHArgs {
     const float* bias; const float* res; const float* scale_ptr; float* y; double* stats;
     int B, T, H, W, Cin, Cout;
     int kt, kw;                   // kh == 3
+    int t_phase;                  // 1: input is the temporally x2 nearest-upsampled tensor stored at T/2 (see below)
     int bw, bh2;                  // patch: bw x bh2 voxels (= 256)
     int tiles_w, tiles_h;
     int n_tile, kc, stages, terms, nacc;
@@ -487,42 +508,60 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform (see conv_tc_kernel)
     if (threadIdx.x == 0) dbg_stamp(1);                       // prologue done
 
-    // temporal taps that fall outside [0, T) contribute only zero padding: both pipeline ends skip them
-    auto tap_t = [&](int it, int& dt, int& dw, int& c0) -> bool {
+    // Temporal taps that fall outside the clip contribute only zero padding: both pipeline ends skip them.
+    // t_phase (conv_0 of a block whose input was nearest-upsampled x2 in time, decoder.py:102-111): the input
+    // frames 2j and 2j+1 are identical (SPADE's gamma/beta do not depend on t), so
+    //   out[2j]   = W0 a[j-1] + (W1+W2) a[j]        out[2j+1] = (W0+W1) a[j] + W2 a[j+1]
+    // i.e. TWO temporal taps on the T/2 tensor with per-phase pre-summed weights (loader.py) instead of three
+    // on the upsampled one: 2/3 of the MMAs and of the operand traffic, and the upsampled tensor never exists.
+    // `ct` = source plane in the stored tensor, `wt` = temporal index into the weight tensor.
+    const int Tin = a.t_phase ? a.T / 2 : a.T;
+    auto tap_t = [&](int it, int& ct, int& wt, int& dw, int& c0) -> bool {
         const int tk = it / cchunks;
         c0 = (it - tk * cchunks) * a.kc;
-        dw = tk % a.kw; dt = tk / a.kw;
-        const int ct = t + dt - a.kt / 2;
-        return ct >= 0 && ct < a.T;
+        dw = tk % a.kw;
+        const int dt = tk / a.kw;
+        if (a.t_phase) {
+            const int p = t & 1;
+            ct = (t >> 1) + dt - 1 + p;
+            wt = p * 2 + dt;
+        } else {
+            ct = t + dt - a.kt / 2;
+            wt = dt;
+        }
+        return ct >= 0 && ct < Tin;
     };
 
     if (warp == 0) {
-        if (lane == 0) {
+        {
             const uint32_t tx = (a.terms > 1 ? 2u : 1u) * (a_rows * rb + b_bytes);
             int n = 0;
             for (int it = 0; it < iters; ++it) {
-                int dt, dw, c0;
-                if (!tap_t(it, dt, dw, c0)) continue;
+                int ct, wt, dw, c0;
+                if (!tap_t(it, ct, wt, dw, c0)) continue;
                 const int s = n % a.stages;
                 const uint32_t ph = (uint32_t)(n / a.stages) & 1u;
                 ++n;
                 ptx::mbar_wait(empty + s, ph ^ 1u);
                 uint8_t* st = smem + (size_t)s * stage_bytes;
-                const int cw = w0 + dw - a.kw / 2, ch = h0 - 1, ct = t + dt - a.kt / 2;
-                ptx::mbar_expect_tx(full + s, tx);
-                ptx::tma_load_5d(st, &mAh, full + s, c0, cw, ch, ct, b);
-                ptx::tma_load_5d(st + off_bhi, &mBh, full + s, c0, n0, dw, 0, dt);
-                if (a.terms > 1) {
-                    ptx::tma_load_5d(st + off_alo, &mAl, full + s, c0, cw, ch, ct, b);
-                    ptx::tma_load_5d(st + off_blo, &mBl, full + s, c0, n0, dw, 0, dt);
+                const int cw = w0 + dw - a.kw / 2, ch = h0 - 1;
+                if (ptx::elect_one()) {
+                    ptx::mbar_expect_tx(full + s, tx);
+                    ptx::tma_load_5d(st, &mAh, full + s, c0, cw, ch, ct, b);
+                    ptx::tma_load_5d(st + off_bhi, &mBh, full + s, c0, n0, dw, 0, wt);
+                    if (a.terms > 1) {
+                        ptx::tma_load_5d(st + off_alo, &mAl, full + s, c0, cw, ch, ct, b);
+                        ptx::tma_load_5d(st + off_blo, &mBl, full + s, c0, n0, dw, 0, wt);
+                    }
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             const uint32_t idesc = ptx::make_idesc_f16(TILE_M, a.n_tile);
             const int ksteps = a.kc / 16;
             const uint64_t dproto = ptx::make_kmajor_desc(0, rb);
@@ -530,12 +569,12 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
             const uint32_t sub_step = (uint32_t)(bh_sub * a.bw) * rb >> 4, kh_step = (uint32_t)a.bw * rb >> 4;
             int n = 0;
             for (int it = 0; it < iters; ++it) {
-                int dt, dw, c0;
-                if (!tap_t(it, dt, dw, c0)) continue;
+                int ct, wt, dw, c0;
+                if (!tap_t(it, ct, wt, dw, c0)) continue;
                 const int s = n % a.stages;
                 const uint32_t ph = (uint32_t)(n / a.stages) & 1u;
                 ptx::mbar_wait(full + s, ph);
-                if (n == 0) dbg_stamp(2);                     // first stage landed
+                if (n == 0 && lane == 0) dbg_stamp(2);        // first stage landed
                 ptx::tc_fence_after();
                 const uint32_t sa = ptx::smem_u32(smem + (size_t)s * stage_bytes);
                 const uint32_t lah = dlo + (sa >> 4), lal = lah + (off_alo >> 4);
@@ -546,6 +585,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
                 // (N = 64) MMA never waits on the one before it
                 const uint32_t tacc0 = tmem_base + (uint32_t)(ai * a.n_tile), tacc1 = tacc0 + (uint32_t)(a.nacc * a.n_tile);
                 uint32_t acc_flag = fresh;
+                if (ptx::elect_one()) {
 #pragma unroll
                 for (int kh = 0; kh < 3; ++kh) {
                     const uint32_t ao = (uint32_t)kh * kh_step, bo = (uint32_t)kh * (b_tap >> 4);
@@ -569,19 +609,22 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
                     }
                 }
                 ptx::mma_commit(empty + s);
+                }
+                __syncwarp();
                 ++n;
             }
-            ptx::mma_commit(tmem_full);
-            dbg_stamp(3);                                     // last MMA issued
+            if (ptx::elect_one()) ptx::mma_commit(tmem_full);
+            __syncwarp();
+            if (lane == 0) dbg_stamp(3);                      // last MMA issued
         }
     } else {
-        ptx::mbar_wait(tmem_full, 0);
+        ptx::mbar_wait_backoff(tmem_full, 0);
         if (threadIdx.x == 64) dbg_stamp(4);                  // accumulators complete
         ptx::tc_fence_after();
         int n_valid = 0;
-        for (int dt = 0; dt < a.kt; ++dt) {
-            const int ct = t + dt - a.kt / 2;
-            if (ct >= 0 && ct < a.T) n_valid += a.kw * cchunks;
+        for (int it = 0; it < iters; it += cchunks) {      // one probe per (kt, kw) tap pair
+            int ct, wt, dw, c0;
+            if (tap_t(it, ct, wt, dw, c0)) n_valid += cchunks;
         }
         const int nacc_used = n_valid < a.nacc ? n_valid : a.nacc;
         const int q = warp & 3, half = (warp - 2) >> 2;       // two warps per TMEM lane quarter: column halves
@@ -673,6 +716,13 @@ int conv_tc_set_debug(unsigned long long* buf, int ctas) {
 // (every 128/256-row tile lies inside one sample and takes the coalesced channels-last path).
 bool conv_tc_fuses_stats(int T, int H, int W) { return (long long)T * H * W >= 128; }
 
+// Shapes the 256-row halo kernel takes (whatever the channel counts, as long as conv_tc_supported holds).
+bool conv_tc_halo_eligible(int H, int W, int kh) {
+    if (kh != 3 || W < 16 || H * W < 256) return false;
+    const int bw = W < 128 ? W : 128, bh2 = 256 / bw;
+    return bh2 >= 2 && H % bh2 == 0;
+}
+
 bool conv_tc_supported(int B, int T, int H, int W, int Cin, int Cout, int kt, int kh, int kw) {
     (void)B; (void)Cout;
     if (!(kt == 1 || kt == 3) || !(kh == 1 || kh == 3) || !(kw == 1 || kw == 3)) return false;
@@ -693,6 +743,9 @@ int launch_split_fp16(const float* x, __half* hi, __half* lo, float scale, long 
 // v2 eligibility + launch.  Returns 1 if the shape is not eligible (caller falls through to v1).
 static int launch_conv_tc_halo(const ConvTcArgs& h, cudaStream_t stream) {
     if (h.kh != 3 || h.W < 16 || h.H * h.W < 256) return 1;
+    I2V_REQUIRE(!h.t_phase || (h.kt == 3 && h.T % 2 == 0), "conv_tc: t_phase needs a 3-tap temporal kernel and even T");
+    const int kt_eff = h.t_phase ? 2 : h.kt;     // temporal taps actually iterated
+    const int Tin = h.t_phase ? h.T / 2 : h.T;   // planes of the stored activation tensor
     ConvTcHArgs a;
     a.bw = h.W < 128 ? h.W : 128;
     a.bh2 = 256 / a.bw;
@@ -716,22 +769,23 @@ static int launch_conv_tc_halo(const ConvTcArgs& h, cudaStream_t stream) {
     a.kc = kc; a.stages = stages; a.terms = h.terms;
     int nacc = 512 / (2 * a.n_tile);
     if (nacc > 4) nacc = 4;
-    const int iters = h.kt * h.kw * (h.Cin / kc);
+    const int iters = kt_eff * h.kw * (h.Cin / kc);
     if (nacc > iters) nacc = iters;
     if (nacc < 1) return 1;
     a.nacc = nacc;
+    a.t_phase = h.t_phase ? 1 : 0;
     a.bias = h.bias; a.res = h.res; a.scale_ptr = h.scale_ptr; a.y = h.y; a.stats = h.stats;
     I2V_REQUIRE(h.stats == nullptr || (h.out_mode == 0 && a.n_tile <= 256), "conv_tc: fused statistics need channels-last output");
-    a.B = h.B; a.T = h.T; a.H = h.H; a.W = h.W; a.Cin = h.Cin; a.Cout = h.Cout; a.kt = h.kt; a.kw = h.kw;
+    a.B = h.B; a.T = h.T; a.H = h.H; a.W = h.W; a.Cin = h.Cin; a.Cout = h.Cout; a.kt = kt_eff; a.kw = h.kw;
     a.tiles_w = h.W / a.bw; a.tiles_h = h.H / a.bh2;
     a.res_ut = h.res_ut; a.res_uh = h.res_uh; a.res_uw = h.res_uw; a.act = h.act; a.out_mode = h.out_mode;
     const int rb = kc * 2;
 
     CUtensorMap mAh, mAl, mBh, mBl;
     {
-        const cuuint64_t dims[5] = {(cuuint64_t)h.Cin, (cuuint64_t)h.W, (cuuint64_t)h.H, (cuuint64_t)h.T, (cuuint64_t)h.B};
+        const cuuint64_t dims[5] = {(cuuint64_t)h.Cin, (cuuint64_t)h.W, (cuuint64_t)h.H, (cuuint64_t)Tin, (cuuint64_t)h.B};
         const cuuint64_t st[4] = {(cuuint64_t)h.Cin * 2, (cuuint64_t)h.W * h.Cin * 2, (cuuint64_t)h.H * h.W * h.Cin * 2,
-                                  (cuuint64_t)h.T * h.H * h.W * h.Cin * 2};
+                                  (cuuint64_t)Tin * h.H * h.W * h.Cin * 2};
         const cuuint32_t box[5] = {(cuuint32_t)kc, (cuuint32_t)a.bw, (cuuint32_t)(a.bh2 + 2), 1, 1};
         if (int rc = encode_map(&mAh, h.x_hi, 5, dims, st, box, rb)) return rc;
         if (int rc = encode_map(&mAl, h.terms > 1 ? h.x_lo : h.x_hi, 5, dims, st, box, rb)) return rc;
@@ -740,7 +794,8 @@ static int launch_conv_tc_halo(const ConvTcArgs& h, cudaStream_t stream) {
         // weights [kt][kh][kw][cout_pad][Cin] viewed as (Cin, cout_pad, kw, kh, kt) (strides ascending): the 3 kh taps of
         // one (kt, kw) arrive as a single box -> smem [kh][n][kc]
         const cuuint64_t row = (cuuint64_t)h.cout_pad * h.Cin * 2;
-        const cuuint64_t dims[5] = {(cuuint64_t)h.Cin, (cuuint64_t)h.cout_pad, (cuuint64_t)h.kw, 3, (cuuint64_t)h.kt};
+        // temporal extent of the weight tensor: kt taps, or 2 phases x 2 taps ([phase][tap][kh][kw][cout][cin])
+        const cuuint64_t dims[5] = {(cuuint64_t)h.Cin, (cuuint64_t)h.cout_pad, (cuuint64_t)h.kw, 3, (cuuint64_t)(h.t_phase ? 4 : h.kt)};
         const cuuint64_t st[4] = {(cuuint64_t)h.Cin * 2, row, row * h.kw, row * h.kw * 3};
         const cuuint32_t box[5] = {(cuuint32_t)kc, (cuuint32_t)a.n_tile, 1, 3, 1};
         if (int rc = encode_map(&mBh, h.w_hi, 5, dims, st, box, rb)) return rc;
@@ -778,6 +833,7 @@ int launch_conv_tc(const ConvTcArgs& h, cudaStream_t stream) {
         if (rc <= 0) return rc;     // launched (0) or failed (<0); 1 = shape not eligible -> v1 below
         I2V_REQUIRE(h.variant != 2, "conv_tc: shape not eligible for the halo kernel");
     }
+    I2V_REQUIRE(!h.t_phase, "conv_tc: t_phase is only implemented by the halo kernel (ask conv_tc_halo_eligible first)");
     ConvTcKArgs a;
     a.bias = h.bias; a.res = h.res; a.scale_ptr = h.scale_ptr; a.y = h.y; a.stats = h.stats;
     a.B = h.B; a.T = h.T; a.H = h.H; a.W = h.W; a.Cin = h.Cin; a.Cout = h.Cout;

@@ -36,8 +36,12 @@ struct ConvTcArgs {
     int res_ut, res_uh, res_uw, act, out_mode;
     int terms;                                // 3: hi*hi+hi*lo+lo*hi (fp32-grade)   1: hi*hi only
     int variant = 0;                          // 0: auto (halo kernel when eligible)  1: force v1  2: force halo kernel
+    // 1: the logical input is x nearest-upsampled x2 in time; x_hi/x_lo hold it at T/2 planes and w_hi/w_lo hold the
+    //    phase-combined weights [2 phases][2 taps][kh][kw][cout_pad][Cin] (halo kernel only)
+    int t_phase = 0;
 };
 bool conv_tc_fuses_stats(int T, int H, int W);
+bool conv_tc_halo_eligible(int H, int W, int kh);
 bool conv_tc_supported(int B, int T, int H, int W, int Cin, int Cout, int kt, int kh, int kw);
 int launch_conv_tc(const ConvTcArgs& a, cudaStream_t stream);
 int conv_tc_set_debug(unsigned long long* buf, int ctas);   // phase timestamps of the halo kernel (profiling aid)

@@ -56,6 +56,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// long waits (epilogue warps parked for a whole main loop): back off so the pollers do not steal issue slots
+// from the TMA / MMA warps that share their schedulers
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(200);
+}
 
 // ----------------------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* m) {

@@ -120,7 +120,16 @@ def split_fp16(w, in_scale):
     return hi.contiguous(), lo.contiguous(), torch.tensor([1.0 / (in_scale * s)], dtype=torch.float32)
 
 
-def pack_decoder(sd, nf, engine=0):
+def phase_weights(w_taps):
+    """[27, Cout, Cin] (kt, kh, kw) -> [2 phases * 2 taps * 9, Cout, Cin] for a conv whose input was
+    nearest-upsampled x2 in time: frames 2j and 2j+1 of the input are identical, so
+        out[2j]   = W0 a[j-1] + (W1+W2) a[j]        out[2j+1] = (W0+W1) a[j] + W2 a[j+1]
+    (csrc/conv_tc.cu, t_phase).  Sums are formed in float64."""
+    w = w_taps.double().reshape(3, 9, *w_taps.shape[1:])
+    return torch.stack((w[0], w[1] + w[2], w[0] + w[1], w[2])).reshape(36, *w_taps.shape[1:])
+
+
+def pack_decoder(sd, nf, engine=0, upsample_t=(2, 1)):
     """Returns (tensors, scalars).  engine >= 1 adds the split fp16 weights of the tensor-core engine."""
     import math
     t, scalars = {}, {}
@@ -152,6 +161,11 @@ def pack_decoder(sd, nf, engine=0):
         tc = {}
         for name in DEC_BLOCKS:
             convs = ["conv_0", "conv_1"] + (["conv_s"] if f"{name}.conv_s.w" in t else [])
+            # conv_0 of the blocks that run on 16x16+ planes behind a x2 temporal upsample: phase-combined weights
+            ut = {"g_1": 2, "g_2": 2, "g_3": upsample_t[0], "g_4": upsample_t[1]}.get(name, 0)
+            if ut == 2:
+                ph, pl, ps = split_fp16(phase_weights(t[f"{name}.conv_0.w"]), ACT_SPLIT_SCALE)   # float64 sums -> split
+                tc[f"{name}.conv_0.wph"], tc[f"{name}.conv_0.wpl"], tc[f"{name}.conv_0.wps"] = ph, pl, ps
             for c in convs:
                 tc[f"{name}.{c}.wh"], tc[f"{name}.{c}.wl"], tc[f"{name}.{c}.ws"] = split_fp16(t.pop(f"{name}.{c}.w"), ACT_SPLIT_SCALE)
             # SPADE hidden map h = lrelu(conv(img) + b) with |img| <= 1 after the bilinear resize:

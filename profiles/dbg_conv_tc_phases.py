@@ -28,3 +28,4 @@ def run(name, B,C,T,H,W,Cout):
 run('g3_conv1_like', 4,128,16,64,64,128)
 run('g4_conv1_like', 4,64,16,64,64,64)
 run('g3_conv0_like', 4,256,16,64,64,128)
+run('g4_conv0_like', 4,128,16,64,64,64)
