@@ -307,13 +307,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
 
     // A tap whose shifted box lies entirely in the zero padding contributes nothing (head_0: T = 1, so 18 of
     // the 27 taps): producer, issuer and epilogue all skip it.
-    auto tap_ok = [&](int it, int& tap, int& c0, int& cw, int& ch, int& ct) -> bool {
-        tap = it / cchunks;
-        c0 = (it - tap * cchunks) * a.kc;
-        const int dw = tap % a.kw, dh = (tap / a.kw) % a.kh, dt = tap / (a.kw * a.kh);
-        cw = w0 + dw - a.kw / 2; ch = h0 + dh - a.kh / 2; ct = t0 + dt - a.kt / 2;
-        return cw + a.bw > 0 && cw < a.W && ch + a.bh > 0 && ch < a.H && ct + a.bt > 0 && ct < a.T;
+    // Valid taps form a contiguous range per dimension; computed once so that the role loops carry no
+    // divisions (they run on a single warp and are latency-bound).
+    auto tap_range = [](int k, int origin, int box, int extent, int& lo, int& hi) {
+        lo = k / 2 - origin - box + 1; if (lo < 0) lo = 0;         // first d with origin + d - k/2 + box > 0
+        hi = extent - 1 - origin + k / 2; if (hi > k - 1) hi = k - 1;   // last d with origin + d - k/2 < extent
     };
+    int dt_lo, dt_hi, dh_lo, dh_hi, dw_lo, dw_hi;
+    tap_range(a.kt, t0, a.bt, a.T, dt_lo, dt_hi);
+    tap_range(a.kh, h0, a.bh, a.H, dh_lo, dh_hi);
+    tap_range(a.kw, w0, a.bw, a.W, dw_lo, dw_hi);
+    const int n_total = (dt_hi - dt_lo + 1) * (dh_hi - dh_lo + 1) * (dw_hi - dw_lo + 1) * cchunks;   // >= 1: the centre tap
+    (void)iters;
 
     // Role loops run on the WHOLE warp with warp-uniform control flow; only the asynchronous instructions are
     // predicated on one elected lane.  (Running the loop under `if (lane == 0)` makes every operand a
@@ -322,13 +327,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
         // ================================ TMA producer
         {
             const uint32_t tx = (a.terms > 1 ? 2u : 1u) * (a_bytes + (uint32_t)a.n_tile * rb);
-            int n = 0;
-            for (int it = 0; it < iters; ++it) {
-                int tap, c0, cw, ch, ct;
-                if (!tap_ok(it, tap, c0, cw, ch, ct)) continue;
-                const int s = n % a.stages;
-                const uint32_t ph = (uint32_t)(n / a.stages) & 1u;
-                ++n;
+            int s = 0;
+            uint32_t ph = 0;
+            for (int dt = dt_lo; dt <= dt_hi; ++dt)
+            for (int dh = dh_lo; dh <= dh_hi; ++dh)
+            for (int dw = dw_lo; dw <= dw_hi; ++dw)
+            for (int cc = 0; cc < cchunks; ++cc) {
+                const int tap = (dt * a.kh + dh) * a.kw + dw, c0 = cc * a.kc;
+                const int cw = w0 + dw - a.kw / 2, ch = h0 + dh - a.kh / 2, ct = t0 + dt - a.kt / 2;
                 ptx::mbar_wait(empty + s, ph ^ 1u);
                 uint8_t* st = smem + (size_t)s * stage_bytes;
                 if (ptx::elect_one()) {
@@ -341,6 +347,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
                     }
                 }
                 __syncwarp();
+                if (++s == a.stages) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
@@ -350,16 +357,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
             const int ksteps = a.kc / 16;
             const uint64_t dproto = ptx::make_kmajor_desc(0, rb);
             const uint32_t dlo = (uint32_t)dproto, dhi = (uint32_t)(dproto >> 32);
-            int n = 0, n_total = 0;
-            for (int it = 0; it < iters; ++it) {
-                int tap, c0, cw, ch, ct;
-                if (tap_ok(it, tap, c0, cw, ch, ct)) ++n_total;
-            }
-            for (int it = 0; it < iters; ++it) {
-                int tap, c0, cw, ch, ct;
-                if (!tap_ok(it, tap, c0, cw, ch, ct)) continue;
-                const int s = n % a.stages;
-                const uint32_t ph = (uint32_t)(n / a.stages) & 1u;
+            int s = 0, ai = 0;
+            uint32_t ph = 0;
+            for (int n = 0; n < n_total; ++n) {
                 ptx::mbar_wait(full + s, ph);
                 ptx::tc_fence_after();
                 const uint32_t sa = ptx::smem_u32(smem + (size_t)s * stage_bytes);
@@ -370,7 +370,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
                 // round-robin over `nacc` TMEM accumulators: the tensor core's fp32 accumulate truncates, so
                 // the chain of dependent adds per accumulator is cut nacc-fold and the partial sums are
                 // combined with round-to-nearest fp32 adds in the epilogue
-                const uint32_t tacc = tmem_base + (uint32_t)((n % a.nacc) * a.n_tile);
+                const uint32_t tacc = tmem_base + (uint32_t)(ai * a.n_tile);
                 uint32_t acc_flag = n >= a.nacc ? 1u : 0u;
                 if (ptx::elect_one()) {
 #pragma unroll
@@ -389,7 +389,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
                     if (n == n_total - 1) ptx::mma_commit(tmem_full);   // accumulator complete
                 }
                 __syncwarp();
-                ++n;
+                if (++s == a.stages) { s = 0; ph ^= 1u; }
+                if (++ai == a.nacc) ai = 0;
             }
         }
     } else {
@@ -404,11 +405,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
         const int ti = r % a.bt;
         const int bi = r / a.bt;
         EpiArgs e{a.bias, a.res, a.y, a.T, a.H, a.W, a.Cout, a.res_ut, a.res_uh, a.res_uw, a.act, a.out_mode};
-        int n_total = 0;
-        for (int it = 0; it < iters; ++it) {
-            int tap, c0, cw, ch, ct;
-            if (tap_ok(it, tap, c0, cw, ch, ct)) ++n_total;
-        }
         const int nacc_used = n_total < a.nacc ? n_total : a.nacc;
         // column split between the two warps of a quarter (multiples of 16)
         const int nh0 = ((a.n_tile / 16 + 1) / 2) * 16;
@@ -518,33 +514,24 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
     // i.e. TWO temporal taps on the T/2 tensor with per-phase pre-summed weights (loader.py) instead of three
     // on the upsampled one: 2/3 of the MMAs and of the operand traffic, and the upsampled tensor never exists.
     // `ct` = source plane in the stored tensor, `wt` = temporal index into the weight tensor.
+    // Source plane of temporal tap dt is ct_base + dt, its weight slab wt_base + dt; the valid dt form a range.
     const int Tin = a.t_phase ? a.T / 2 : a.T;
-    auto tap_t = [&](int it, int& ct, int& wt, int& dw, int& c0) -> bool {
-        const int tk = it / cchunks;
-        c0 = (it - tk * cchunks) * a.kc;
-        dw = tk % a.kw;
-        const int dt = tk / a.kw;
-        if (a.t_phase) {
-            const int p = t & 1;
-            ct = (t >> 1) + dt - 1 + p;
-            wt = p * 2 + dt;
-        } else {
-            ct = t + dt - a.kt / 2;
-            wt = dt;
-        }
-        return ct >= 0 && ct < Tin;
-    };
+    const int ct_base = a.t_phase ? (t >> 1) - 1 + (t & 1) : t - a.kt / 2;
+    const int wt_base = a.t_phase ? (t & 1) * 2 : 0;
+    const int dt_lo = ct_base < 0 ? -ct_base : 0;
+    const int dt_hi = (Tin - 1 - ct_base) < (a.kt - 1) ? (Tin - 1 - ct_base) : (a.kt - 1);
+    const int n_total = (dt_hi - dt_lo + 1) * a.kw * cchunks;     // pipeline stages this CTA runs
+    (void)iters;
 
     if (warp == 0) {
         {
             const uint32_t tx = (a.terms > 1 ? 2u : 1u) * (a_rows * rb + b_bytes);
-            int n = 0;
-            for (int it = 0; it < iters; ++it) {
-                int ct, wt, dw, c0;
-                if (!tap_t(it, ct, wt, dw, c0)) continue;
-                const int s = n % a.stages;
-                const uint32_t ph = (uint32_t)(n / a.stages) & 1u;
-                ++n;
+            int s = 0;
+            uint32_t ph = 0;
+            for (int dt = dt_lo; dt <= dt_hi; ++dt)
+            for (int dw = 0; dw < a.kw; ++dw)
+            for (int cc = 0; cc < cchunks; ++cc) {
+                const int ct = ct_base + dt, wt = wt_base + dt, c0 = cc * a.kc;
                 ptx::mbar_wait(empty + s, ph ^ 1u);
                 uint8_t* st = smem + (size_t)s * stage_bytes;
                 const int cw = w0 + dw - a.kw / 2, ch = h0 - 1;
@@ -558,6 +545,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
                     }
                 }
                 __syncwarp();
+                if (++s == a.stages) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
@@ -567,19 +555,15 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
             const uint64_t dproto = ptx::make_kmajor_desc(0, rb);
             const uint32_t dlo = (uint32_t)dproto, dhi = (uint32_t)(dproto >> 32);
             const uint32_t sub_step = (uint32_t)(bh_sub * a.bw) * rb >> 4, kh_step = (uint32_t)a.bw * rb >> 4;
-            int n = 0;
-            for (int it = 0; it < iters; ++it) {
-                int ct, wt, dw, c0;
-                if (!tap_t(it, ct, wt, dw, c0)) continue;
-                const int s = n % a.stages;
-                const uint32_t ph = (uint32_t)(n / a.stages) & 1u;
+            int s = 0, ai = 0;
+            uint32_t ph = 0;
+            for (int n = 0; n < n_total; ++n) {
                 ptx::mbar_wait(full + s, ph);
                 if (n == 0 && lane == 0) dbg_stamp(2);        // first stage landed
                 ptx::tc_fence_after();
                 const uint32_t sa = ptx::smem_u32(smem + (size_t)s * stage_bytes);
                 const uint32_t lah = dlo + (sa >> 4), lal = lah + (off_alo >> 4);
                 const uint32_t lbh = lah + (off_bhi >> 4), lbl = lah + (off_blo >> 4);
-                const int ai = n % a.nacc;
                 const uint32_t fresh = n < a.nacc ? 0u : 1u;     // first visit of this accumulator pair -> overwrite
                 // issue order (kh, k, term, sub): back-to-back MMAs target different TMEM accumulators, so a short
                 // (N = 64) MMA never waits on the one before it
@@ -611,7 +595,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
                 ptx::mma_commit(empty + s);
                 }
                 __syncwarp();
-                ++n;
+                if (++s == a.stages) { s = 0; ph ^= 1u; }
+                if (++ai == a.nacc) ai = 0;
             }
             if (ptx::elect_one()) ptx::mma_commit(tmem_full);
             __syncwarp();
@@ -621,12 +606,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
         ptx::mbar_wait_backoff(tmem_full, 0);
         if (threadIdx.x == 64) dbg_stamp(4);                  // accumulators complete
         ptx::tc_fence_after();
-        int n_valid = 0;
-        for (int it = 0; it < iters; it += cchunks) {      // one probe per (kt, kw) tap pair
-            int ct, wt, dw, c0;
-            if (tap_t(it, ct, wt, dw, c0)) n_valid += cchunks;
-        }
-        const int nacc_used = n_valid < a.nacc ? n_valid : a.nacc;
+        const int nacc_used = n_total < a.nacc ? n_total : a.nacc;
         const int q = warp & 3, half = (warp - 2) >> 2;       // two warps per TMEM lane quarter: column halves
         const int m = q * 32 + lane;
         const int wi = m % a.bw, hi = m / a.bw;
