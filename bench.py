@@ -234,7 +234,7 @@ def run_b200(args):
         ms = e0.elapsed_time(e1)
         prof = None
         if profile:
-            arr = [(ctypes.c_double * 5)(), (ctypes.c_double * 5)(), (ctypes.c_double * 5)(), (ctypes.c_longlong * 5)()]
+            arr = [(ctypes.c_double * 7)(), (ctypes.c_double * 7)(), (ctypes.c_double * 7)(), (ctypes.c_longlong * 7)()]
             lib.check(L.i2v_prof_collect(*arr), "prof_collect")
             L.i2v_prof_enable(0)
             prof = [list(a) for a in arr]
@@ -270,15 +270,26 @@ def run_b200(args):
         peak_tf = peaks.get("bf16_tflops_sustained", 1590.0 * 1441.7 / 1690.8)
         peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback (B200_PROFILING.md)"
         cms, cfl, cby, cn = prof
-        names = ["conv", "stats", "modulate", "flow", "other"]
+        names = ["conv_tc_halo", "stats", "modulate", "flow", "other", "conv_tc_pertap", "conv_simt"]
         fam = {names[i]: {"ms": cms[i] / args.steps, "launches": cn[i] / args.steps,
                           "tflops": (cfl[i] / (cms[i] * 1e-3) / 1e12) if cms[i] > 0 else 0.0,
-                          "gbs": (cby[i] / (cms[i] * 1e-3) / 1e9) if cms[i] > 0 else 0.0} for i in range(5)}
-        achieved = fam["conv"]["tflops"]
-        roofline = {"bound": "tensor", "kernel": "conv (decoder/embedder implicit-GEMM convolutions, all launches of the timed steps)",
+                          "gbs": (cby[i] / (cms[i] * 1e-3) / 1e9) if cms[i] > 0 else 0.0} for i in range(7)}
+        dom = "conv_tc_halo" if fam["conv_tc_halo"]["ms"] >= fam["conv_simt"]["ms"] else "conv_simt"
+        achieved = fam[dom]["tflops"]
+        ncu = {}
+        try:
+            ncu = json.load(open(os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")))
+        except (OSError, ValueError):
+            pass
+        roofline = {"bound": "tensor",
+                    "kernel": f"{dom}_kernel: all its launches in the timed steps (decoder Conv3d/Conv2d stack), algorithmic FLOPs = "
+                              "2*taps*Cin*Cout per output voxel (reference's nominal count, SURVEY 8d) / summed CUDA-event time",
                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                    "peak_source": peak_src, "traffic": None,
-                    "share_of_step": fam["conv"]["ms"] / (ms / args.steps), "families": fam}
+                    "peak_source": peak_src,
+                    "note": "fp32-parity mode issues 3 fp16 MMAs per algorithmic MAC (hi*hi+hi*lo+lo*hi) and the phase form "
+                            "skips 1/3 of conv_0's taps: tensor-pipe FLOP/s = achieved x 3 x (issued/nominal taps)",
+                    "traffic": ncu.get("dram_bytes_per_launch"), "traffic_note": ncu.get("note"),
+                    "share_of_step": fam[dom]["ms"] / (ms / args.steps), "families": fam}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

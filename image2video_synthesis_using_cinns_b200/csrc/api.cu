@@ -22,7 +22,7 @@ namespace {
 struct ProfRec { cudaEvent_t a, b; int cat; double flops, bytes; };
 struct ProfState {
     bool on = false;
-    long long launches[PROF_NCAT] = {0, 0, 0, 0, 0};
+    long long launches[PROF_NCAT] = {0, 0, 0, 0, 0, 0, 0};
     std::vector<ProfRec> recs;
     std::vector<cudaEvent_t> pool;
     size_t pool_used = 0;
@@ -95,11 +95,17 @@ struct Arena {
 #define I2V_TRY(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
 #define I2V_PTR(var, expr) auto var = (expr); if (!dry && var == nullptr) return -3
 
+// split-K scratch of the SIMT engine (encoders' deep-K / small-M layers)
+struct SplitK { float* ws = nullptr; size_t bytes = 0; unsigned* counters = nullptr; int max_tiles = 0; };
+constexpr size_t kSplitKBytes = 48ull << 20;
+constexpr int kSplitKTiles = 4096;
+
 // conv helper (stride-1 'same' or general), channels-last
 int conv(int engine, const float* x, const float* w, const float* bias, const float* res, float* y, int B, int Ti, int Hi,
          int Wi, int Cin, int Cout, int kt, int kh, int kw, int st, int sh, int sw, int pt, int ph, int pw, int rut, int ruh,
-         int ruw, int act, int out_mode, cudaStream_t s) {
+         int ruw, int act, int out_mode, cudaStream_t s, const SplitK* sk = nullptr) {
     ConvArgs a;
+    if (sk) { a.splitk_ws = sk->ws; a.splitk_ws_bytes = sk->bytes; a.splitk_counters = sk->counters; a.splitk_max_tiles = sk->max_tiles; }
     a.x = x; a.w = w; a.bias = bias; a.res = res; a.y = y;
     a.B = B; a.Ti = Ti; a.Hi = Hi; a.Wi = Wi; a.Cin = Cin;
     a.To = (Ti + 2 * pt - kt) / st + 1; a.Ho = (Hi + 2 * ph - kh) / sh + 1; a.Wo = (Wi + 2 * pw - kw) / sw + 1;
@@ -240,8 +246,12 @@ static int embedder_run(const i2v_embedder* m, const float* x0, float* embed, in
     float* coef = ar.take<float>((size_t)B * 2048 * 2);
     float* coef2 = ar.take<float>((size_t)B * 2048 * 2);
     float* pooled = ar.take<float>((size_t)B * 2048);
+    SplitK sk;
+    sk.ws = ar.take<float>(kSplitKBytes / sizeof(float)); sk.bytes = kSplitKBytes;
+    sk.counters = ar.take<unsigned>(kSplitKTiles); sk.max_tiles = kSplitKTiles;
     if (!ar.ok()) { set_error("embedder: workspace too small (%zu needed, %zu given)", ar.peak, ar.cap); return -4; }
     if (dry) return 0;
+    I2V_CHECK_CUDA(cudaMemsetAsync(sk.counters, 0, sizeof(unsigned) * kSplitKTiles, s));   // counters self-reset afterwards
 
     auto W_ = [&](const std::string& n, size_t e) { return m->tt.get(n, e); };
     auto Bv = [&](const std::string& n, size_t e) -> const float* { return inorm ? nullptr : m->tt.get(n, e); };
@@ -253,7 +263,7 @@ static int embedder_run(const i2v_embedder* m, const float* x0, float* embed, in
         const int Ho = (Hi + 2 * pad - k) / stride + 1, Wo = (Wi + 2 * pad - k) / stride + 1;
         if (inorm) {
             I2V_TRY(conv(0, in, w, nullptr, nullptr, tmp, B, 1, Hi, Wi, Cin, Cout, 1, k, k, 1, stride, stride, 0, pad, pad, 1, 1,
-                         1, ACT_NONE, 0, s));
+                         1, ACT_NONE, 0, s, &sk));
             I2V_TRY(launch_channel_stats(tmp, sums, B, (long long)Ho * Wo, Cout, s));
             I2V_TRY(launch_norm_coeffs(sums, coef, B, Cout, (long long)Ho * Wo, 0, 1e-5f, nullptr, nullptr, nullptr, s));
             I2V_TRY(modulate(tmp, coef, nullptr, nullptr, nullptr, out, B, 1, Ho, Wo, Cout, 1, 1, 1, relu ? ACT_RELU : ACT_NONE, s));
@@ -261,7 +271,7 @@ static int embedder_run(const i2v_embedder* m, const float* x0, float* embed, in
             const float* b = Bv(name + ".b", Cout);
             if (!b) return -3;
             I2V_TRY(conv(0, in, w, b, nullptr, out, B, 1, Hi, Wi, Cin, Cout, 1, k, k, 1, stride, stride, 0, pad, pad, 1, 1, 1,
-                         relu ? ACT_RELU : ACT_NONE, 0, s));
+                         relu ? ACT_RELU : ACT_NONE, 0, s, &sk));
         }
         return 0;
     };
@@ -285,7 +295,7 @@ static int embedder_run(const i2v_embedder* m, const float* x0, float* embed, in
             if (!w3) return -3;
             if (inorm) {
                 // o3 raw -> t1 ; identity branch raw (downsample conv) -> t3 ; out = relu(IN(o3) + IN(ds) | h) -> t4
-                I2V_TRY(conv(0, t2, w3, nullptr, nullptr, t1, B, 1, Ho, Wo, pl, 4 * pl, 1, 1, 1, 1, 1, 1, 0, 0, 0, 1, 1, 1, ACT_NONE, 0, s));
+                I2V_TRY(conv(0, t2, w3, nullptr, nullptr, t1, B, 1, Ho, Wo, pl, 4 * pl, 1, 1, 1, 1, 1, 1, 0, 0, 0, 1, 1, 1, ACT_NONE, 0, s, &sk));
                 I2V_TRY(launch_channel_stats(t1, sums, B, (long long)Ho * Wo, 4 * pl, s));
                 I2V_TRY(launch_norm_coeffs(sums, coef, B, 4 * pl, (long long)Ho * Wo, 0, 1e-5f, nullptr, nullptr, nullptr, s));
                 const float* idt = cur; const float* c2 = nullptr;
@@ -293,7 +303,7 @@ static int embedder_run(const i2v_embedder* m, const float* x0, float* embed, in
                     const float* wd = W_(p + "ds.w", (size_t)4 * pl * Cc);
                     if (!wd) return -3;
                     I2V_TRY(conv(0, cur, wd, nullptr, nullptr, t3, B, 1, Hc, Wc, Cc, 4 * pl, 1, 1, 1, 1, stride, stride, 0, 0, 0, 1, 1, 1,
-                                 ACT_NONE, 0, s));
+                                 ACT_NONE, 0, s, &sk));
                     I2V_TRY(launch_channel_stats(t3, sums2, B, (long long)Ho * Wo, 4 * pl, s));
                     I2V_TRY(launch_norm_coeffs(sums2, coef2, B, 4 * pl, (long long)Ho * Wo, 0, 1e-5f, nullptr, nullptr, nullptr, s));
                     idt = t3; c2 = coef2;
@@ -308,10 +318,10 @@ static int embedder_run(const i2v_embedder* m, const float* x0, float* embed, in
                     const float* bd = m->tt.get(p + "ds.b", (size_t)4 * pl);
                     if (!wd || !bd) return -3;
                     I2V_TRY(conv(0, cur, wd, bd, nullptr, t3, B, 1, Hc, Wc, Cc, 4 * pl, 1, 1, 1, 1, stride, stride, 0, 0, 0, 1, 1, 1,
-                                 ACT_NONE, 0, s));
+                                 ACT_NONE, 0, s, &sk));
                     idt = t3;
                 }
-                I2V_TRY(conv(0, t2, w3, b3, idt, t4, B, 1, Ho, Wo, pl, 4 * pl, 1, 1, 1, 1, 1, 1, 0, 0, 0, 1, 1, 1, ACT_RELU, 0, s));
+                I2V_TRY(conv(0, t2, w3, b3, idt, t4, B, 1, Ho, Wo, pl, 4 * pl, 1, 1, 1, 1, 1, 1, 0, 0, 0, 1, 1, 1, ACT_RELU, 0, s, &sk));
             }
             float* old = cur; cur = t4; t4 = old;   // rotate: previous input buffer becomes scratch
             Hc = Ho; Wc = Wo; Cc = 4 * pl;
@@ -642,8 +652,12 @@ static int encoder3d_run(const i2v_encoder3d* m, const float* seq, float* mu, in
     double* sums2 = ar.take<double>((size_t)B * cmax * 2);
     float* coef = ar.take<float>((size_t)B * cmax * 2);
     float* coef2 = ar.take<float>((size_t)B * cmax * 2);
+    SplitK sk;
+    sk.ws = ar.take<float>(kSplitKBytes / sizeof(float)); sk.bytes = kSplitKBytes;
+    sk.counters = ar.take<unsigned>(kSplitKTiles); sk.max_tiles = kSplitKTiles;
     if (!ar.ok()) { set_error("encoder3d: workspace too small (%zu needed, %zu given)", ar.peak, ar.cap); return -4; }
     if (dry) return 0;
+    I2V_CHECK_CUDA(cudaMemsetAsync(sk.counters, 0, sizeof(unsigned) * kSplitKTiles, s));
     auto G = [&](const std::string& n, size_t e) { return m->tt.get(n, e); };
 
     // [B,T,3,H,W] -> [B,T,H,W,3]
@@ -651,7 +665,7 @@ static int encoder3d_run(const i2v_encoder3d* m, const float* seq, float* mu, in
     I2V_PTR(w1, G("conv1.w", (size_t)147 * m->ch[0] * 3));
     I2V_PTR(n1w, G("norm1.w", m->ch[0]));
     I2V_PTR(n1b, G("norm1.b", m->ch[0]));
-    I2V_TRY(conv(0, xin, w1, nullptr, nullptr, buf[1], B, T, H, W, 3, m->ch[0], 3, 7, 7, 2, 2, 2, 1, 3, 3, 1, 1, 1, ACT_NONE, 0, s));
+    I2V_TRY(conv(0, xin, w1, nullptr, nullptr, buf[1], B, T, H, W, 3, m->ch[0], 3, 7, 7, 2, 2, 2, 1, 3, 3, 1, 1, 1, ACT_NONE, 0, s, &sk));
     long long V = (long long)T1 * H1 * W1;
     I2V_TRY(launch_channel_stats(buf[1], sums, B, V, m->ch[0], s));
     I2V_TRY(launch_norm_coeffs(sums, coef, B, m->ch[0], V, 16, 1e-5f, n1w, n1b, nullptr, s));
@@ -671,19 +685,19 @@ static int encoder3d_run(const i2v_encoder3d* m, const float* seq, float* mu, in
             I2V_PTR(wc2, G(p + "conv2.w", (size_t)27 * pl * pl));
             I2V_PTR(g2w, G(p + "bn2.w", pl)); I2V_PTR(g2b, G(p + "bn2.b", pl));
             // o = relu(GN(conv1(h)))
-            I2V_TRY(conv(0, cur, wc1, nullptr, nullptr, ta, B, Tc, Hc, Wc, Cc, pl, 3, 3, 3, st, ss, ss, 1, 1, 1, 1, 1, 1, ACT_NONE, 0, s));
+            I2V_TRY(conv(0, cur, wc1, nullptr, nullptr, ta, B, Tc, Hc, Wc, Cc, pl, 3, 3, 3, st, ss, ss, 1, 1, 1, 1, 1, 1, ACT_NONE, 0, s, &sk));
             I2V_TRY(launch_channel_stats(ta, sums, B, Vo, pl, s));
             I2V_TRY(launch_norm_coeffs(sums, coef, B, pl, Vo, 16, 1e-5f, g1w, g1b, nullptr, s));
             I2V_TRY(modulate(ta, coef, nullptr, nullptr, nullptr, tb, B, To, Ho, Wo, pl, 1, 1, 1, ACT_RELU, s));
             // o = GN(conv2(o))
-            I2V_TRY(conv(0, tb, wc2, nullptr, nullptr, ta, B, To, Ho, Wo, pl, pl, 3, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, ACT_NONE, 0, s));
+            I2V_TRY(conv(0, tb, wc2, nullptr, nullptr, ta, B, To, Ho, Wo, pl, pl, 3, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, ACT_NONE, 0, s, &sk));
             I2V_TRY(launch_channel_stats(ta, sums, B, Vo, pl, s));
             I2V_TRY(launch_norm_coeffs(sums, coef, B, pl, Vo, 16, 1e-5f, g2w, g2b, nullptr, s));
             const float* res = cur; const float* c2 = nullptr;
             if (m->tt.has(p + "ds.w")) {
                 I2V_PTR(wd, G(p + "ds.w", (size_t)27 * pl * Cc));
                 I2V_PTR(gdw, G(p + "ds.gn.w", pl)); I2V_PTR(gdb, G(p + "ds.gn.b", pl));
-                I2V_TRY(conv(0, cur, wd, nullptr, nullptr, tb, B, Tc, Hc, Wc, Cc, pl, 3, 3, 3, st, ss, ss, 1, 1, 1, 1, 1, 1, ACT_NONE, 0, s));
+                I2V_TRY(conv(0, cur, wd, nullptr, nullptr, tb, B, Tc, Hc, Wc, Cc, pl, 3, 3, 3, st, ss, ss, 1, 1, 1, 1, 1, 1, ACT_NONE, 0, s, &sk));
                 I2V_TRY(launch_channel_stats(tb, sums2, B, Vo, pl, s));
                 I2V_TRY(launch_norm_coeffs(sums2, coef2, B, pl, Vo, 16, 1e-5f, gdw, gdb, nullptr, s));
                 res = tb; c2 = coef2;

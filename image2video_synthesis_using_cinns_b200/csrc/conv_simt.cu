@@ -126,13 +126,22 @@ __global__ void __launch_bounds__(NT, 2) conv_simt_kernel(const ConvArgs a) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-    const int nk = (K + BK - 1) / BK;
-    load_tiles(0);
-    store_tiles(0);
+    // split-K: blockIdx.z owns a contiguous range of k-steps (deep-K / small-M layers of the encoders would
+    // otherwise run on a handful of CTAs with a serial, latency-bound K loop)
+    const int nk_all = (K + BK - 1) / BK;
+    const int ksplit = gridDim.z;
+    const int per = (nk_all + ksplit - 1) / ksplit;
+    const int kb0 = blockIdx.z * per;
+    const int kb1 = min(nk_all, kb0 + per);
+    const int nk = kb1 > kb0 ? kb1 - kb0 : 0;
+    if (nk > 0) {
+        load_tiles(kb0 * BK);
+        store_tiles(0);
+    }
     __syncthreads();
     for (int kb = 0; kb < nk; ++kb) {
         const int buf = kb & 1;
-        if (kb + 1 < nk) load_tiles((kb + 1) * BK);
+        if (kb + 1 < nk) load_tiles((kb0 + kb + 1) * BK);
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
             const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8]);
@@ -148,6 +157,39 @@ __global__ void __launch_bounds__(NT, 2) conv_simt_kernel(const ConvArgs a) {
         if (kb + 1 < nk) {
             store_tiles(buf ^ 1);
             __syncthreads();
+        }
+    }
+
+    // ---- split-K reduction: every split parks its partial tile; the LAST one to arrive sums all of them in
+    // split order (a fixed order: the result does not depend on which CTA happens to be last) and runs the epilogue
+    if (ksplit > 1) {
+        const int tile_id = blockIdx.y * gridDim.x + blockIdx.x;
+        float* part = a.splitk_ws + ((size_t)tile_id * ksplit + blockIdx.z) * (BM * BN);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4*>(part + (ty * 8 + i) * BN + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        __threadfence();
+        __syncthreads();
+        __shared__ int s_last;
+        if (tid == 0) {
+            const unsigned prev = atomicAdd(a.splitk_counters + tile_id, 1u);
+            s_last = (prev == (unsigned)ksplit - 1);
+            if (s_last) a.splitk_counters[tile_id] = 0;      // self-resetting: ready for the next launch
+        }
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        const float* base = a.splitk_ws + (size_t)tile_id * ksplit * (BM * BN);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int z = 0; z < ksplit; ++z) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 v = __ldcg(reinterpret_cast<const float4*>(base + (size_t)z * (BM * BN) + (ty * 8 + i) * BN + tx * 4));
+                acc[i][0] += v.x; acc[i][1] += v.y; acc[i][2] += v.z; acc[i][3] += v.w;
+            }
         }
     }
 
@@ -214,9 +256,20 @@ int launch_conv_simt(const ConvArgs& a, cudaStream_t stream) {
     I2V_REQUIRE(a.res == nullptr || (a.To % a.res_ut == 0 && a.Ho % a.res_uh == 0 && a.Wo % a.res_uw == 0),
                 "conv_simt: residual upsample factors must divide the output size");
     const double K_ = (double)a.kt * a.kh * a.kw * a.Cin;
-    ProfScope ps(PROF_CONV, 2.0 * (double)M * a.Cout * K_,
+    ProfScope ps(PROF_CONV_SIMT, 2.0 * (double)M * a.Cout * K_,
                  4.0 * ((double)a.B * a.Ti * a.Hi * a.Wi * a.Cin + (double)M * a.Cout + K_ * a.Cout), stream);
-    dim3 grid(ceil_div(M, BM), ceil_div(a.Cout, BN));
+    dim3 grid(ceil_div(M, BM), ceil_div(a.Cout, BN), 1);
+    // split-K when the tile grid cannot fill the machine and K is deep; bounded by the caller's scratch
+    if (a.splitk_ws != nullptr && a.splitk_counters != nullptr) {
+        const int tiles = grid.x * grid.y;
+        const int nk = ((int)K_ + BK - 1) / BK;
+        int ks = (2 * kNumSMs + tiles - 1) / tiles;
+        if (ks > nk / 4) ks = nk / 4;                       // at least 4 k-steps per split
+        const size_t per_tile = (size_t)BM * BN * sizeof(float);
+        while (ks > 1 && (size_t)tiles * ks * per_tile > a.splitk_ws_bytes) --ks;
+        if (tiles > a.splitk_max_tiles) ks = 1;
+        if (ks > 1) grid.z = ks;
+    }
     if (a.Cin % 16 == 0)
         conv_simt_kernel<true><<<grid, NT, 0, stream>>>(a);
     else

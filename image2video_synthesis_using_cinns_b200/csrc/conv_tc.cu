@@ -882,7 +882,7 @@ int launch_conv_tc(const ConvTcArgs& h, cudaStream_t stream) {
     }
     const long long M = (long long)h.B * h.T * h.H * h.W;
     const double K_ = (double)h.kt * h.kh * h.kw * h.Cin;
-    ProfScope ps(PROF_CONV, 2.0 * (double)M * h.Cout * K_, 4.0 * ((double)M * h.Cin + (double)M * h.Cout + K_ * h.Cout), stream);
+    ProfScope ps(PROF_CONV_TC1, 2.0 * (double)M * h.Cout * K_, 4.0 * ((double)M * h.Cin + (double)M * h.Cout + K_ * h.Cout), stream);
     dim3 grid((unsigned)(a.tiles_w * a.tiles_h * a.tiles_t * tiles_b), (unsigned)((h.cout_pad + a.n_tile - 1) / a.n_tile));
     conv_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(mAh, mAl, mBh, mBl, a);
     I2V_CHECK_CUDA(cudaGetLastError());

@@ -102,20 +102,34 @@ __device__ void hidden_layer(const float* __restrict__ W /*[2][H][H]*/, const fl
             const int k = lane + 32 * q;
             wv[q] = k < H4 ? __ldg(wr + k) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        for (int b = 0; b < B; ++b) {
-            const float4* hr = reinterpret_cast<const float4*>(hs + (long long)b * H);
-            float acc = 0.f;
+        // four rows per trip: four independent shuffle-reduction chains in flight (the loop runs on one warp
+        // per scheduler, so a single dependent chain would expose every shuffle's latency)
+        for (int b = 0; b < B; b += 4) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int k = lane + 32 * q;
-                if (k < H4) {
-                    const float4 hv = hr[k];
-                    acc = fmaf(wv[q].x, hv.x, acc); acc = fmaf(wv[q].y, hv.y, acc);
-                    acc = fmaf(wv[q].z, hv.z, acc); acc = fmaf(wv[q].w, hv.w, acc);
+            for (int r = 0; r < 4; ++r) {
+                if (b + r < B) {
+                    const float4* hr = reinterpret_cast<const float4*>(hs + (long long)(b + r) * H);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int k = lane + 32 * q;
+                        if (k < H4) {
+                            const float4 hv = hr[k];
+                            acc[r] = fmaf(wv[q].x, hv.x, acc[r]); acc[r] = fmaf(wv[q].y, hv.y, acc[r]);
+                            acc[r] = fmaf(wv[q].z, hv.z, acc[r]); acc[r] = fmaf(wv[q].w, hv.w, acc[r]);
+                        }
+                    }
                 }
             }
-            acc = warp_sum(acc);
-            if (lane == 0) hout[(long long)b * 2 * H + net * H + o] = lrelu001(acc + bo);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], off);
+            }
+            if (lane < 4 && b + lane < B) {
+                const float v = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : (lane == 2 ? acc[2] : acc[3]));
+                hout[(long long)(b + lane) * 2 * H + net * H + o] = lrelu001(v + bo);
+            }
         }
     }
 }
@@ -230,20 +244,32 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) flow_kernel(const FlowKernelA
                         wv[q] = k < H4 ? __ldg(wr + k) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                     const float br = __ldg(bo + r);
-                    for (int b = 0; b < B; ++b) {
-                        const float4* hr = reinterpret_cast<const float4*>(hin + (long long)b * 2 * H + rnet * H);
-                        float acc = 0.f;
+                    for (int b = 0; b < B; b += 4) {
+                        float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int k = lane + 32 * q;
-                            if (k < H4) {
-                                const float4 hv = __ldcg(hr + k);
-                                acc = fmaf(wv[q].x, hv.x, acc); acc = fmaf(wv[q].y, hv.y, acc);
-                                acc = fmaf(wv[q].z, hv.z, acc); acc = fmaf(wv[q].w, hv.w, acc);
+                        for (int rr = 0; rr < 4; ++rr) {
+                            if (b + rr < B) {
+                                const float4* hr = reinterpret_cast<const float4*>(hin + (long long)(b + rr) * 2 * H + rnet * H);
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const int k = lane + 32 * q;
+                                    if (k < H4) {
+                                        const float4 hv = __ldcg(hr + k);
+                                        acc[rr] = fmaf(wv[q].x, hv.x, acc[rr]); acc[rr] = fmaf(wv[q].y, hv.y, acc[rr]);
+                                        acc[rr] = fmaf(wv[q].z, hv.z, acc[rr]); acc[rr] = fmaf(wv[q].w, hv.w, acc[rr]);
+                                    }
+                                }
                             }
                         }
-                        acc = warp_sum(acc);
-                        if (lane == 0) a.st[(long long)b * 2 * half + r] = acc + br;
+#pragma unroll
+                        for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+                            for (int rr = 0; rr < 4; ++rr) acc[rr] += __shfl_xor_sync(0xffffffffu, acc[rr], off);
+                        }
+                        if (lane < 4 && b + lane < B) {
+                            const float v = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : (lane == 2 ? acc[2] : acc[3]));
+                            a.st[(long long)(b + lane) * 2 * half + r] = v + br;
+                        }
                     }
                 }
             }

@@ -21,6 +21,8 @@ struct ConvArgs {
     int out_mode;   // 0: [B,To,Ho,Wo,Cout]   1: [B,To,Cout,Ho,Wo] (video frames)
     // optional fp16 split of the result for the tensor-core engine: hi = fp16(s*v), lo = fp16(s*v - hi)
     __half* y_hi = nullptr; __half* y_lo = nullptr; float split_scale = 1.f;
+    // optional split-K scratch (partials [tiles][ksplit][128*64] fp32 + one zero-initialised counter per tile)
+    float* splitk_ws = nullptr; size_t splitk_ws_bytes = 0; unsigned* splitk_counters = nullptr; int splitk_max_tiles = 0;
 };
 int launch_conv_simt(const ConvArgs& a, cudaStream_t stream);
 

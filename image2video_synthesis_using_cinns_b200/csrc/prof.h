@@ -4,7 +4,9 @@
 
 namespace i2v {
 
-enum ProfCat : int { PROF_CONV = 0, PROF_STATS = 1, PROF_MODULATE = 2, PROF_FLOW = 3, PROF_OTHER = 4, PROF_NCAT = 5 };
+// 0 = the halo tensor-core conv kernel (dominant), 5 = per-tap tensor-core kernel, 6 = fp32 SIMT conv kernel
+enum ProfCat : int { PROF_CONV = 0, PROF_STATS = 1, PROF_MODULATE = 2, PROF_FLOW = 3, PROF_OTHER = 4, PROF_CONV_TC1 = 5,
+                     PROF_CONV_SIMT = 6, PROF_NCAT = 7 };
 
 // Counts the launch; when profiling is enabled also brackets it with events on `stream`.
 struct ProfScope {

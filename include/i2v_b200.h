@@ -43,9 +43,9 @@ const char* i2v_last_error(void);
 
 /* Launch accounting.  i2v_launch_count(): kernels launched by this library since load.
  * i2v_prof_enable(1) brackets every subsequent launch with CUDA events on its stream;
- * i2v_prof_collect() waits for them and returns per kernel family (0 conv, 1 stats, 2 modulate,
- * 3 flow, 4 other; arrays of 5) the summed device time [ms], algorithmic FLOPs, algorithmic bytes
- * and launch counts since the last collect. */
+ * i2v_prof_collect() waits for them and returns per kernel family (0 halo tensor-core conv, 1 stats,
+ * 2 modulate, 3 flow, 4 other, 5 per-tap tensor-core conv, 6 fp32 SIMT conv; arrays of 7) the summed
+ * device time [ms], algorithmic FLOPs, algorithmic bytes and launch counts since the last collect. */
 long long i2v_launch_count(void);
 void i2v_prof_enable(int on);
 int i2v_prof_collect(double* ms, double* flops, double* bytes, long long* launches);
