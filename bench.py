@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--dataset", default="bair")
     ap.add_argument("--batch", type=int, default=64, help="start frames per GPU per step")
     ap.add_argument("--seq-length", type=int, default=16)
-    ap.add_argument("--micro-batch", type=int, default=16)
+    ap.add_argument("--micro-batch", type=int, default=64)
     ap.add_argument("--conv-engine", type=int, default=1, help="1 tcgen05 split-fp16 (parity), 0 fp32 SIMT, 2 fp16 fast")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ckpt-dir", default=None, help="reuse / create synthetic checkpoints here")

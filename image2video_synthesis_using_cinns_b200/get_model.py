@@ -33,7 +33,7 @@ class Model:
     select the device, the decoder micro-batch and the decoder's conv engine (1 = tcgen05 tensor cores with
     the error-compensated fp16 split, fp32-grade parity, default; 0 = fp32 SIMT; 2 = single fp16 product)."""
 
-    def __init__(self, model_path, vid_length, transfer=False, *, device="cuda", micro_batch=16, conv_engine=1):
+    def __init__(self, model_path, vid_length, transfer=False, *, device="cuda", micro_batch=32, conv_engine=1):
         opt = load_yaml(model_path + "config_stage2.yaml")                                   # get_model.py:15
         fs = opt.First_stage_model
         path_stage1 = fs["model_path"] + fs["model_name"] + "/"                              # get_model.py:16
