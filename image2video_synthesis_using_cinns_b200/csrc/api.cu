@@ -768,6 +768,7 @@ int i2v_op_conv_tc(const float* x, const float* w, const float* bias, const floa
     a.res_ut = rut; a.res_uh = ruh; a.res_uw = ruw; a.act = act; a.out_mode = out_mode; a.terms = terms; a.variant = variant;
     return launch_conv_tc(a, s);
 }
+int i2v_debug_flow_timestamps(void* buf) { return flow_set_debug(static_cast<unsigned long long*>(buf)); }
 int i2v_debug_conv_tc_timestamps(void* buf, int ctas) { return conv_tc_set_debug(static_cast<unsigned long long*>(buf), ctas); }
 int i2v_op_channel_stats(const float* x, double* sums, int B, int64_t V, int C, void* stream) {
     return launch_channel_stats(x, sums, B, V, C, static_cast<cudaStream_t>(stream));

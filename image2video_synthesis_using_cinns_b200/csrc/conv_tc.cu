@@ -54,8 +54,10 @@ struct ConvTcKArgs {
     int kt, kh, kw;
     int bw, bh, bt, bb;
     int tiles_w, tiles_h, tiles_t;
-    int n_tile, kc, stages, terms, nacc;
+    int n_tile, kc, stages, terms, nacc;   // nacc accumulators per (sub-)tile ...
+    int nmain;                             // ... of which the first nmain take hi*hi, the rest the small cross terms
     int res_ut, res_uh, res_uw, act, out_mode;
+    int cc_lo, cc_hi;             // channel-chunk range [cc_lo, cc_hi) of this launch (K split across launches)
 };
 
 struct EpiArgs {
@@ -281,7 +283,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
     const int tb = tile / a.tiles_t;
     const int w0 = tw * a.bw, h0 = th * a.bh, t0 = tt * a.bt, b0 = tb * a.bb;
     const int n0 = blockIdx.y * a.n_tile;
-    const int taps = a.kt * a.kh * a.kw, cchunks = a.Cin / a.kc, iters = taps * cchunks;
+    const int taps = a.kt * a.kh * a.kw, cchunks = a.cc_hi - a.cc_lo, iters = taps * cchunks;
     uint32_t ncols = 32;
     while (ncols < (uint32_t)(a.n_tile * a.nacc)) ncols <<= 1;
 
@@ -332,7 +334,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
             for (int dt = dt_lo; dt <= dt_hi; ++dt)
             for (int dh = dh_lo; dh <= dh_hi; ++dh)
             for (int dw = dw_lo; dw <= dw_hi; ++dw)
-            for (int cc = 0; cc < cchunks; ++cc) {
+            for (int cc = a.cc_lo; cc < a.cc_hi; ++cc) {
                 const int tap = (dt * a.kh + dh) * a.kw + dw, c0 = cc * a.kc;
                 const int cw = w0 + dw - a.kw / 2, ch = h0 + dh - a.kh / 2, ct = t0 + dt - a.kt / 2;
                 ptx::mbar_wait(empty + s, ph ^ 1u);
@@ -357,7 +359,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
             const int ksteps = a.kc / 16;
             const uint64_t dproto = ptx::make_kmajor_desc(0, rb);
             const uint32_t dlo = (uint32_t)dproto, dhi = (uint32_t)(dproto >> 32);
-            int s = 0, ai = 0;
+            int s = 0, ai = 0, asm_ = 0;
+            const int nsmall = a.nacc - a.nmain;
             uint32_t ph = 0;
             for (int n = 0; n < n_total; ++n) {
                 ptx::mbar_wait(full + s, ph);
@@ -370,8 +373,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
                 // round-robin over `nacc` TMEM accumulators: the tensor core's fp32 accumulate truncates, so
                 // the chain of dependent adds per accumulator is cut nacc-fold and the partial sums are
                 // combined with round-to-nearest fp32 adds in the epilogue
+                // hi*hi goes to the "main" accumulators, the 2^-11-sized cross terms hi*lo, lo*hi to their own: a
+                // truncating add costs an error relative to the accumulator it lands in, so the small terms no longer
+                // spend the main accumulator's precision (and the main chain is 3x shorter)
                 const uint32_t tacc = tmem_base + (uint32_t)(ai * a.n_tile);
-                uint32_t acc_flag = n >= a.nacc ? 1u : 0u;
+                const uint32_t tsm = tmem_base + (uint32_t)((a.nmain + asm_) * a.n_tile);
+                uint32_t acc_flag = n >= a.nmain ? 1u : 0u;
+                uint32_t sm_flag = n >= nsmall ? 1u : 0u;
                 if (ptx::elect_one()) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
@@ -380,8 +388,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
                             ptx::mma_f16_ss(tacc, ptx::desc64(lah + o, dhi), ptx::desc64(lbh + o, dhi), idesc, acc_flag);
                             acc_flag = 1u;
                             if (a.terms > 1) {
-                                ptx::mma_f16_ss(tacc, ptx::desc64(lah + o, dhi), ptx::desc64(lbl + o, dhi), idesc, 1u);
-                                ptx::mma_f16_ss(tacc, ptx::desc64(lal + o, dhi), ptx::desc64(lbh + o, dhi), idesc, 1u);
+                                ptx::mma_f16_ss(tsm, ptx::desc64(lah + o, dhi), ptx::desc64(lbl + o, dhi), idesc, sm_flag);
+                                ptx::mma_f16_ss(tsm, ptx::desc64(lal + o, dhi), ptx::desc64(lbh + o, dhi), idesc, 1u);
+                                sm_flag = 1u;
                             }
                         }
                     }
@@ -390,7 +399,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
                 }
                 __syncwarp();
                 if (++s == a.stages) { s = 0; ph ^= 1u; }
-                if (++ai == a.nacc) ai = 0;
+                if (++ai == a.nmain) ai = 0;
+                if (nsmall > 0 && ++asm_ == nsmall) asm_ = 0;
             }
         }
     } else {
@@ -405,7 +415,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
         const int ti = r % a.bt;
         const int bi = r / a.bt;
         EpiArgs e{a.bias, a.res, a.y, a.T, a.H, a.W, a.Cout, a.res_ut, a.res_uh, a.res_uw, a.act, a.out_mode};
-        const int nacc_used = n_total < a.nacc ? n_total : a.nacc;
+        const int nacc_used = a.nacc;       // host guarantees every accumulator is written by every CTA
         // column split between the two warps of a quarter (multiples of 16)
         const int nh0 = ((a.n_tile / 16 + 1) / 2) * 16;
         const int col0 = half == 0 ? 0 : nh0, ncols = half == 0 ? nh0 : a.n_tile - nh0;
@@ -450,8 +460,10 @@ struct ConvTcHArgs {
     int t_phase;                  // 1: input is the temporally x2 nearest-upsampled tensor stored at T/2 (see below)
     int bw, bh2;                  // patch: bw x bh2 voxels (= 256)
     int tiles_w, tiles_h;
-    int n_tile, kc, stages, terms, nacc;
+    int n_tile, kc, stages, terms, nacc;   // nacc accumulators per (sub-)tile ...
+    int nmain;                             // ... of which the first nmain take hi*hi, the rest the small cross terms
     int res_ut, res_uh, res_uw, act, out_mode;
+    int cc_lo, cc_hi;             // channel-chunk range [cc_lo, cc_hi) of this launch (K split across launches)
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -481,7 +493,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
     const int b = tile / a.T;
     const int w0 = tw * a.bw, h0 = th * a.bh2;
     const int n0 = blockIdx.y * a.n_tile;
-    const int cchunks = a.Cin / a.kc;
+    const int cchunks = a.cc_hi - a.cc_lo;
     const int iters = a.kt * a.kw * cchunks;
     const int bh_sub = a.bh2 / 2;
     uint32_t ncols = 32;
@@ -530,7 +542,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
             uint32_t ph = 0;
             for (int dt = dt_lo; dt <= dt_hi; ++dt)
             for (int dw = 0; dw < a.kw; ++dw)
-            for (int cc = 0; cc < cchunks; ++cc) {
+            for (int cc = a.cc_lo; cc < a.cc_hi; ++cc) {
                 const int ct = ct_base + dt, wt = wt_base + dt, c0 = cc * a.kc;
                 ptx::mbar_wait(empty + s, ph ^ 1u);
                 uint8_t* st = smem + (size_t)s * stage_bytes;
@@ -555,7 +567,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
             const uint64_t dproto = ptx::make_kmajor_desc(0, rb);
             const uint32_t dlo = (uint32_t)dproto, dhi = (uint32_t)(dproto >> 32);
             const uint32_t sub_step = (uint32_t)(bh_sub * a.bw) * rb >> 4, kh_step = (uint32_t)a.bw * rb >> 4;
-            int s = 0, ai = 0;
+            int s = 0, ai = 0, asm_ = 0;
+            const int nsmall = a.nacc - a.nmain;
             uint32_t ph = 0;
             for (int n = 0; n < n_total; ++n) {
                 ptx::mbar_wait(full + s, ph);
@@ -564,10 +577,13 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
                 const uint32_t sa = ptx::smem_u32(smem + (size_t)s * stage_bytes);
                 const uint32_t lah = dlo + (sa >> 4), lal = lah + (off_alo >> 4);
                 const uint32_t lbh = lah + (off_bhi >> 4), lbl = lah + (off_blo >> 4);
-                const uint32_t fresh = n < a.nacc ? 0u : 1u;     // first visit of this accumulator pair -> overwrite
+                const uint32_t fresh = n < a.nmain ? 0u : 1u;    // first visit of this main accumulator pair -> overwrite
+                uint32_t sm_flag = n < nsmall ? 0u : 1u;         // same for the cross-term accumulators
                 // issue order (kh, k, term, sub): back-to-back MMAs target different TMEM accumulators, so a short
                 // (N = 64) MMA never waits on the one before it
                 const uint32_t tacc0 = tmem_base + (uint32_t)(ai * a.n_tile), tacc1 = tacc0 + (uint32_t)(a.nacc * a.n_tile);
+                // cross terms hi*lo, lo*hi accumulate apart from hi*hi (see conv_tc_kernel)
+                const uint32_t tsm0 = tmem_base + (uint32_t)((a.nmain + asm_) * a.n_tile), tsm1 = tsm0 + (uint32_t)(a.nacc * a.n_tile);
                 uint32_t acc_flag = fresh;
                 if (ptx::elect_one()) {
 #pragma unroll
@@ -584,10 +600,11 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
                             acc_flag = 1u;
                             if (a.terms > 1) {
                                 const uint64_t dBl = ptx::desc64(lbl + bo + o, dhi);
-                                ptx::mma_f16_ss(tacc0, dAh0, dBl, idesc, 1u);
-                                ptx::mma_f16_ss(tacc1, dAh1, dBl, idesc, 1u);
-                                ptx::mma_f16_ss(tacc0, ptx::desc64(lal + ao + o, dhi), dBh, idesc, 1u);
-                                ptx::mma_f16_ss(tacc1, ptx::desc64(lal + ao + sub_step + o, dhi), dBh, idesc, 1u);
+                                ptx::mma_f16_ss(tsm0, dAh0, dBl, idesc, sm_flag);
+                                ptx::mma_f16_ss(tsm1, dAh1, dBl, idesc, sm_flag);
+                                sm_flag = 1u;
+                                ptx::mma_f16_ss(tsm0, ptx::desc64(lal + ao + o, dhi), dBh, idesc, 1u);
+                                ptx::mma_f16_ss(tsm1, ptx::desc64(lal + ao + sub_step + o, dhi), dBh, idesc, 1u);
                             }
                         }
                     }
@@ -596,7 +613,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
                 }
                 __syncwarp();
                 if (++s == a.stages) { s = 0; ph ^= 1u; }
-                if (++ai == a.nacc) ai = 0;
+                if (++ai == a.nmain) ai = 0;
+                if (nsmall > 0 && ++asm_ == nsmall) asm_ = 0;
             }
             if (ptx::elect_one()) ptx::mma_commit(tmem_full);
             __syncwarp();
@@ -606,7 +624,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
         ptx::mbar_wait_backoff(tmem_full, 0);
         if (threadIdx.x == 64) dbg_stamp(4);                  // accumulators complete
         ptx::tc_fence_after();
-        const int nacc_used = n_total < a.nacc ? n_total : a.nacc;
+        const int nacc_used = a.nacc;       // host guarantees every accumulator is written by every CTA
         const int q = warp & 3, half = (warp - 2) >> 2;       // two warps per TMEM lane quarter: column halves
         const int m = q * 32 + lane;
         const int wi = m % a.bw, hi = m / a.bw;
@@ -749,10 +767,34 @@ static int launch_conv_tc_halo(const ConvTcArgs& h, cudaStream_t stream) {
     a.kc = kc; a.stages = stages; a.terms = h.terms;
     int nacc = 512 / (2 * a.n_tile);
     if (nacc > 4) nacc = 4;
-    const int iters = kt_eff * h.kw * (h.Cin / kc);
-    if (nacc > iters) nacc = iters;
-    if (nacc < 1) return 1;
-    a.nacc = nacc;
+    const int cch = h.Cin / kc;
+    // K split across launches: the tensor core's fp32 accumulate TRUNCATES, so the error of one accumulator
+    // grows with the number of MMAs chained into it (measured ~1e-5 at ~1300 chained MMAs).  Keep every chain
+    // at <= ~450 MMAs: split the channel chunks over several launches whose partial results are combined by
+    // the epilogue's exact fp32 add (launch p > 0 reads y as its residual, in place).
+    // accumulators per sub-tile: terms == 3 -> nmain for hi*hi + as many for the cross terms; terms == 1 -> all main
+    int nmain = h.terms > 1 ? nacc / 2 : nacc;
+    if (nmain < 1) return 1;                                                   // needs 2 accumulators per sub-tile
+    if (nmain > 2) nmain = 2;
+    const int main_per_stage = 3 * (kc / 16);                                  // hi*hi MMAs per stage and sub-tile
+    int parts = 1;
+    if (h.terms > 1) {
+        const long long chain = (long long)kt_eff * h.kw * cch * main_per_stage / nmain;
+        parts = (int)((chain + 449) / 450);
+        if (parts > cch) parts = cch;
+        if (parts < 1) parts = 1;
+    }
+    I2V_REQUIRE(parts == 1 || h.act == ACT_NONE, "conv_tc: K-split launches need a linear epilogue");
+    const int cper = (cch + parts - 1) / parts;
+    {
+        // every CTA runs at least kw * (chunks of the smallest part) stages: each accumulator must be written
+        const int last_chunks = cch - (parts - 1) * cper;
+        const int min_stages = h.kw * (last_chunks < cper ? last_chunks : cper);
+        if (nmain > min_stages) nmain = min_stages;
+    }
+    a.nmain = nmain;
+    a.nacc = h.terms > 1 ? 2 * nmain : nmain;
+    nacc = a.nacc;
     a.t_phase = h.t_phase ? 1 : 0;
     a.bias = h.bias; a.res = h.res; a.scale_ptr = h.scale_ptr; a.y = h.y; a.stats = h.stats;
     I2V_REQUIRE(h.stats == nullptr || (h.out_mode == 0 && a.n_tile <= 256), "conv_tc: fused statistics need channels-last output");
@@ -796,8 +838,16 @@ static int launch_conv_tc_halo(const ConvTcArgs& h, cudaStream_t stream) {
     const double K_ = (double)h.kt * h.kh * h.kw * h.Cin;
     ProfScope ps(PROF_CONV, 2.0 * (double)M * h.Cout * K_, 4.0 * ((double)M * h.Cin + (double)M * h.Cout + K_ * h.Cout), stream);
     dim3 grid((unsigned)((long long)a.tiles_w * a.tiles_h * h.T * h.B), (unsigned)((h.cout_pad + a.n_tile - 1) / a.n_tile));
-    conv_tc_halo_kernel<<<grid, TC_THREADS, smem, stream>>>(mAh, mAl, mBh, mBl, a);
-    I2V_CHECK_CUDA(cudaGetLastError());
+    for (int p = 0; p < parts; ++p) {
+        a.cc_lo = p * cper;
+        a.cc_hi = (p + 1) * cper < cch ? (p + 1) * cper : cch;
+        if (a.cc_lo >= a.cc_hi) break;
+        const bool last = a.cc_hi == cch;
+        if (p > 0) { a.bias = nullptr; a.res = h.y; a.res_ut = a.res_uh = a.res_uw = 1; }
+        a.stats = last ? h.stats : nullptr;
+        conv_tc_halo_kernel<<<grid, TC_THREADS, smem, stream>>>(mAh, mAl, mBh, mBl, a);
+        I2V_CHECK_CUDA(cudaGetLastError());
+    }
     return 0;
 }
 
@@ -833,13 +883,28 @@ int launch_conv_tc(const ConvTcArgs& h, cudaStream_t stream) {
     const int n_cap = h.terms == 3 ? 128 : 256;
     a.n_tile = h.cout_pad < n_cap ? h.cout_pad : n_cap;
     a.terms = h.terms;
+    const int cch1 = h.Cin / a.kc;
+    int parts1 = 1;
     {
-        const int iters = h.kt * h.kh * h.kw * (h.Cin / a.kc);
         int nacc = 512 / a.n_tile;
         if (nacc > 4) nacc = 4;
-        if (nacc > iters) nacc = iters;
-        a.nacc = nacc;
+        int nmain = h.terms > 1 ? nacc / 2 : nacc;        // N <= 128 in the 3-term mode, so nacc >= 4 there
+        if (nmain < 1) nmain = 1;
+        // K split across launches, same reasoning as the halo kernel (main chains of <= ~450 truncating MMAs)
+        if (h.terms > 1) {
+            const long long chain = (long long)h.kt * h.kh * h.kw * cch1 * (a.kc / 16) / nmain;
+            parts1 = (int)((chain + 449) / 450);
+            if (parts1 > cch1) parts1 = cch1;
+            if (parts1 < 1) parts1 = 1;
+        }
+        const int cper = (cch1 + parts1 - 1) / parts1;
+        const int last_chunks = cch1 - (parts1 - 1) * cper;
+        const int min_stages = last_chunks < cper ? last_chunks : cper;     // the centre tap is always valid
+        if (nmain > min_stages) nmain = min_stages;
+        a.nmain = nmain;
+        a.nacc = h.terms > 1 ? 2 * nmain : nmain;
     }
+    I2V_REQUIRE(parts1 == 1 || h.act == ACT_NONE, "conv_tc: K-split launches need a linear epilogue");
     a.res_ut = h.res_ut; a.res_uh = h.res_uh; a.res_uw = h.res_uw; a.act = h.act; a.out_mode = h.out_mode;
     I2V_REQUIRE(h.res == nullptr || (h.T % h.res_ut == 0 && h.H % h.res_uh == 0 && h.W % h.res_uw == 0),
                 "conv_tc: residual upsample factors must divide the output size");
@@ -884,8 +949,17 @@ int launch_conv_tc(const ConvTcArgs& h, cudaStream_t stream) {
     const double K_ = (double)h.kt * h.kh * h.kw * h.Cin;
     ProfScope ps(PROF_CONV_TC1, 2.0 * (double)M * h.Cout * K_, 4.0 * ((double)M * h.Cin + (double)M * h.Cout + K_ * h.Cout), stream);
     dim3 grid((unsigned)(a.tiles_w * a.tiles_h * a.tiles_t * tiles_b), (unsigned)((h.cout_pad + a.n_tile - 1) / a.n_tile));
-    conv_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(mAh, mAl, mBh, mBl, a);
-    I2V_CHECK_CUDA(cudaGetLastError());
+    const int cper1 = (cch1 + parts1 - 1) / parts1;
+    for (int p = 0; p < parts1; ++p) {
+        a.cc_lo = p * cper1;
+        a.cc_hi = (p + 1) * cper1 < cch1 ? (p + 1) * cper1 : cch1;
+        if (a.cc_lo >= a.cc_hi) break;
+        const bool last = a.cc_hi == cch1;
+        if (p > 0) { a.bias = nullptr; a.res = h.y; a.res_ut = a.res_uh = a.res_uw = 1; }
+        a.stats = last ? h.stats : nullptr;
+        conv_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(mAh, mAl, mBh, mBl, a);
+        I2V_CHECK_CUDA(cudaGetLastError());
+    }
     return 0;
 }
 

@@ -52,6 +52,16 @@ struct FlowKernelArgs {
     unsigned char cond_mode[64];   // n_flows <= 64
 };
 
+// optional phase timestamps (i2v_debug_flow_timestamps): 16 x u64 for coupling #4 of CTAs 0 and 100
+__device__ unsigned long long* g_flow_dbg = nullptr;
+__device__ __forceinline__ void fdbg(int coupling, int slot) {
+    if (g_flow_dbg != nullptr && coupling == 4 && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 100)) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_flow_dbg[(blockIdx.x == 0 ? 0 : 16) + slot] = t;
+    }
+}
+
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -87,9 +97,26 @@ __device__ void hidden_layer(const float* __restrict__ W /*[2][H][H]*/, const fl
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int H4 = H >> 2;
     // stage hin[:, net*H : (net+1)*H] (written by other CTAs before the barrier -> bypass L1)
-    for (int i = tid; i < B * H4; i += FLOW_THREADS) {
-        const int b = i / H4, k = i - b * H4;
-        reinterpret_cast<float4*>(hs)[i] = __ldcg(reinterpret_cast<const float4*>(hin + (long long)b * 2 * H + net * H) + k);
+    // eight independent 16-byte loads in flight per thread: with 8 warps per SM a one-load-per-trip loop is
+    // bound by L2 latency (measured: the staging dominated the layer time at B = 64)
+    {
+        const int total = B * H4;
+        for (int i0 = tid; i0 < total; i0 += FLOW_THREADS * 8) {
+            float4 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int i = i0 + j * FLOW_THREADS;
+                if (i < total) {
+                    const int b = i / H4, k = i - b * H4;
+                    v[j] = __ldcg(reinterpret_cast<const float4*>(hin + (long long)b * 2 * H + net * H) + k);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int i = i0 + j * FLOW_THREADS;
+                if (i < total) reinterpret_cast<float4*>(hs)[i] = v[j];
+            }
+        }
     }
     __syncthreads();
     for (int o = cta_in_net + ctas_per_net * warp; o < H; o += ctas_per_net * FLOW_WARPS) {
@@ -200,6 +227,8 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) flow_kernel(const FlowKernelA
                 __syncthreads();
             }
             const int cidx = fl * 2 + i;
+            const int cq = step * 2 + ci;      // coupling sequence number (profiling)
+            fdbg(cq, 0);
             // ---- layer 1: h1 = lrelu(W1x . x[:, :half] + c1)
             {
                 const float* w1x = fw.w1x + (long long)cidx * 2 * H * half;
@@ -207,7 +236,9 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) flow_kernel(const FlowKernelA
                 // columns n = cta, cta+G, ... of the 2H outputs
                 const int ncols = (2 * H - cta + G - 1) / G;
                 for (int e = tid; e < ncols * B; e += FLOW_THREADS) {
-                    const int b = e % B, n = cta + G * (e / B);
+                    // column index fastest: lanes of a warp share the row b (shared-memory broadcast of the state;
+                    // with b fastest the row stride of 64 floats is a 32-way bank conflict)
+                    const int b = e / ncols, n = cta + G * (e - b * ncols);
                     float acc = __ldg(c1 + (long long)b * c1_stride + n);
                     if (!cmode) {
                         const float* wr = w1x + (long long)n * half;
@@ -217,7 +248,9 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) flow_kernel(const FlowKernelA
                     a.hbuf0[(long long)b * 2 * H + n] = lrelu001(acc);
                 }
             }
+            fdbg(cq, 1);
             grid_barrier(a.bar, G);
+            fdbg(cq, 2);
             // ---- hidden layers
             const float* hin = a.hbuf0;
             float* hout = a.hbuf1;
@@ -226,15 +259,21 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) flow_kernel(const FlowKernelA
                     hidden_layer(fw.wh + ((long long)cidx * depth + l) * 2 * H * H,
                                  fw.bh + ((long long)cidx * depth + l) * 2 * H, hin, hout, hs, B, H, net, cta_in_net,
                                  ctas_per_net);
+                fdbg(cq, 3 + 2 * l);
                 grid_barrier(a.bar, G);
+                fdbg(cq, 4 + 2 * l);
                 const float* t = hin; hin = hout; hout = const_cast<float*>(t);
             }
-            // ---- last layer: (s | t)[b, r] for r in [0, 2*half): one warp per output row
+            // ---- last layer: (s | t)[b, r] for r in [0, 2*half).  Only 2*half = 64 outputs exist, so the work is
+            // spread over (output, 4-row group) tasks across every warp of the grid (one warp per output serialised
+            // all B rows: measured 39 us of an 89 us coupling at B = 64).
             {
                 const float* wo = fw.wo + (long long)cidx * 2 * half * H;
                 const float* bo = fw.bo + (long long)cidx * 2 * half;
                 const int H4 = H >> 2;
-                for (int r = cta + G * warp; r < 2 * half; r += G * FLOW_WARPS) {
+                const int R = 2 * half, RG = (B + 3) >> 2;
+                for (int task = cta * FLOW_WARPS + warp; task < R * RG; task += G * FLOW_WARPS) {
+                    const int r = task % R, b = (task / R) * 4;
                     const int rnet = r < half ? 0 : 1;
                     const float4* wr = reinterpret_cast<const float4*>(wo + (long long)r * H);
                     float4 wv[4];
@@ -244,36 +283,36 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) flow_kernel(const FlowKernelA
                         wv[q] = k < H4 ? __ldg(wr + k) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                     const float br = __ldg(bo + r);
-                    for (int b = 0; b < B; b += 4) {
-                        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                    float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                        for (int rr = 0; rr < 4; ++rr) {
-                            if (b + rr < B) {
-                                const float4* hr = reinterpret_cast<const float4*>(hin + (long long)(b + rr) * 2 * H + rnet * H);
+                    for (int rr = 0; rr < 4; ++rr) {
+                        if (b + rr < B) {
+                            const float4* hr = reinterpret_cast<const float4*>(hin + (long long)(b + rr) * 2 * H + rnet * H);
 #pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    const int k = lane + 32 * q;
-                                    if (k < H4) {
-                                        const float4 hv = __ldcg(hr + k);
-                                        acc[rr] = fmaf(wv[q].x, hv.x, acc[rr]); acc[rr] = fmaf(wv[q].y, hv.y, acc[rr]);
-                                        acc[rr] = fmaf(wv[q].z, hv.z, acc[rr]); acc[rr] = fmaf(wv[q].w, hv.w, acc[rr]);
-                                    }
+                            for (int q = 0; q < 4; ++q) {
+                                const int k = lane + 32 * q;
+                                if (k < H4) {
+                                    const float4 hv = __ldcg(hr + k);
+                                    acc[rr] = fmaf(wv[q].x, hv.x, acc[rr]); acc[rr] = fmaf(wv[q].y, hv.y, acc[rr]);
+                                    acc[rr] = fmaf(wv[q].z, hv.z, acc[rr]); acc[rr] = fmaf(wv[q].w, hv.w, acc[rr]);
                                 }
                             }
                         }
+                    }
 #pragma unroll
-                        for (int off = 16; off > 0; off >>= 1) {
+                    for (int off = 16; off > 0; off >>= 1) {
 #pragma unroll
-                            for (int rr = 0; rr < 4; ++rr) acc[rr] += __shfl_xor_sync(0xffffffffu, acc[rr], off);
-                        }
-                        if (lane < 4 && b + lane < B) {
-                            const float v = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : (lane == 2 ? acc[2] : acc[3]));
-                            a.st[(long long)(b + lane) * 2 * half + r] = v + br;
-                        }
+                        for (int rr = 0; rr < 4; ++rr) acc[rr] += __shfl_xor_sync(0xffffffffu, acc[rr], off);
+                    }
+                    if (lane < 4 && b + lane < B) {
+                        const float v = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : (lane == 2 ? acc[2] : acc[3]));
+                        a.st[(long long)(b + lane) * 2 * half + r] = v + br;
                     }
                 }
             }
+            fdbg(cq, 7);
             grid_barrier(a.bar, G);
+            fdbg(cq, 8);
             // ---- affine update of the kept half (every CTA, on its private copy)
             for (int e = tid; e < B * half; e += FLOW_THREADS) {
                 const int b = e / half, c = e - b * half;
@@ -292,6 +331,7 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) flow_kernel(const FlowKernelA
                 }
             }
             __syncthreads();
+            fdbg(cq, 9);
         }
 
         if (a.reverse) {
@@ -322,6 +362,12 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) flow_kernel(const FlowKernelA
     }
 }
 
+}  // namespace
+int flow_set_debug(unsigned long long* buf) {
+    I2V_CHECK_CUDA(cudaMemcpyToSymbol(g_flow_dbg, &buf, sizeof(buf)));
+    return 0;
+}
+namespace {
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 }  // namespace

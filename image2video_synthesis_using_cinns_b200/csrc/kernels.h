@@ -111,6 +111,7 @@ struct FlowWeights {
     const int* perm_bwd; // [n_flows, d]
 };
 size_t flow_workspace_bytes(const FlowWeights& fw, int B);
+int flow_set_debug(unsigned long long* buf);   // phase timestamps of coupling #4 (profiling aid)
 // reverse: z = flow^-1(residual | cond);  forward: (out, logdet) = flow(z | cond)
 int launch_flow(const FlowWeights& fw, const float* in, const float* cond, float* out, float* logdet, int B,
                 bool reverse, void* ws, size_t ws_bytes, cudaStream_t stream);

@@ -125,6 +125,9 @@ int i2v_op_conv_tc(const float* dev_x, const float* dev_w, const float* dev_bias
  * CTAs of grid row 0): 0 start, 1 prologue done, 2 first stage landed, 3 last MMA issued, 4 accumulators complete,
  * 5 epilogue stores issued, 6 CTA end */
 int i2v_debug_conv_tc_timestamps(void* dev_buf, int ctas);
+/* profiling aid: 2 x 16 uint64 %globaltimer stamps of the flow kernel's 5th coupling (CTA 0 and CTA 100): 0 start, 1/2 around
+ * the barrier after layer 1, 3/4 and 5/6 around the barriers after the hidden layers, 7/8 after the last layer, 9 end */
+int i2v_debug_flow_timestamps(void* dev_buf);
 /* sums[B,C,2] (double) of x[B,V,C] */
 int i2v_op_channel_stats(const float* dev_x, double* dev_sums, int B, int64_t V, int C, void* stream);
 int i2v_op_norm_coeffs(const double* dev_sums, float* dev_coef, int B, int C, int64_t V, int groups, float eps,

@@ -33,8 +33,19 @@ def test_full_size_bair_matches_oracle(full_ckpt):
     gf, gz = m.sample(x0, residual=residual, return_latent=True)
     e_z, e_f = rel_inf(gz.cpu(), wz), rel_inf(gf.cpu(), wf)
     tol_f = conditioned_tolerance(lambda a: om.forward(a, residual, batch_slice=False), (x0,))
-    report("full_size:bair", decoder=e_dec, z=e_z, frames=e_f, frames_tol=tol_f)
-    assert e_dec < 1e-4 and e_z < 1e-4 and e_f < tol_f
+    # decoder at the flow's own latent (|z| is an order of magnitude larger than randn), both engines
+    e_dec_z = rel_inf(m.decoder(x0.cuda(), wz.cuda()).cpu(), wf)
+    m0 = Model(full_ckpt, 16, conv_engine=0, micro_batch=2)
+    e_simt_z = rel_inf(m0.decoder(x0.cuda(), wz.cuda()).cpu(), wf)
+    e_simt = rel_inf(m0.decoder(x0.cuda(), z.cuda()).cpu(), om.decode(x0, z))
+    report("full_size:bair", decoder=e_dec, decoder_at_flow_z=e_dec_z, simt_decoder=e_simt, simt_decoder_at_flow_z=e_simt_z,
+           z=e_z, frames=e_f, frames_tol=tol_f, zmax=float(wz.abs().max()),
+           decoder_tol_at_flow_z=conditioned_tolerance(lambda a, b: om.decode(a, b), (x0, wz)))
+    # at the flow's own latents (|z| ~ 75) the decoder itself is ill-conditioned: the fp32 SIMT engine, which only
+    # differs from the oracle in summation order, already sits at ~8e-5.  Bar: the reference's own noise floor.
+    tol_d = conditioned_tolerance(lambda a, b: om.decode(a, b), (x0, wz))
+    assert e_dec < 1e-4 and e_simt < 1e-4 and e_z < 1e-4 and e_f < tol_f
+    assert e_dec_z < tol_d and e_simt_z < tol_d
 
 
 def test_full_size_properties_at_benchmark_batch(full_ckpt):
@@ -64,4 +75,4 @@ def test_full_size_properties_at_benchmark_batch(full_ckpt):
     m0 = Model(full_ckpt, 16, conv_engine=0, micro_batch=8)
     e = rel_inf(m.decoder(x0[:8], z[:8]).cpu(), m0.decoder(x0[:8], z[:8]).cpu())
     report("full_size:tc_vs_simt", decoder=e)
-    assert e < 5e-5
+    assert e < 2e-4        # both engines are within ~1e-4 of the oracle at these latents (see the oracle test)
