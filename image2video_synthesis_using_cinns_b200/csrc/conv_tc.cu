@@ -47,6 +47,7 @@ __device__ __forceinline__ void dbg_stamp(int slot) {
     }
 }
 constexpr int TILE_M = 128;
+constexpr int kMaxChain = 300;   // longest run of truncating hi*hi MMAs into one TMEM accumulator (see launch_conv_tc_halo)
 
 struct ConvTcKArgs {
     const float* bias; const float* res; const float* scale_ptr; float* y; double* stats;
@@ -770,7 +771,7 @@ static int launch_conv_tc_halo(const ConvTcArgs& h, cudaStream_t stream) {
     const int cch = h.Cin / kc;
     // K split across launches: the tensor core's fp32 accumulate TRUNCATES, so the error of one accumulator
     // grows with the number of MMAs chained into it (measured ~1e-5 at ~1300 chained MMAs).  Keep every chain
-    // at <= ~450 MMAs: split the channel chunks over several launches whose partial results are combined by
+    // at <= kMaxChain MMAs: split the channel chunks over several launches whose partial results are combined by
     // the epilogue's exact fp32 add (launch p > 0 reads y as its residual, in place).
     // accumulators per sub-tile: terms == 3 -> nmain for hi*hi + as many for the cross terms; terms == 1 -> all main
     int nmain = h.terms > 1 ? nacc / 2 : nacc;
@@ -780,7 +781,7 @@ static int launch_conv_tc_halo(const ConvTcArgs& h, cudaStream_t stream) {
     int parts = 1;
     if (h.terms > 1) {
         const long long chain = (long long)kt_eff * h.kw * cch * main_per_stage / nmain;
-        parts = (int)((chain + 449) / 450);
+        parts = (int)((chain + kMaxChain - 1) / kMaxChain);
         if (parts > cch) parts = cch;
         if (parts < 1) parts = 1;
     }
@@ -890,10 +891,10 @@ int launch_conv_tc(const ConvTcArgs& h, cudaStream_t stream) {
         if (nacc > 4) nacc = 4;
         int nmain = h.terms > 1 ? nacc / 2 : nacc;        // N <= 128 in the 3-term mode, so nacc >= 4 there
         if (nmain < 1) nmain = 1;
-        // K split across launches, same reasoning as the halo kernel (main chains of <= ~450 truncating MMAs)
+        // K split across launches, same reasoning as the halo kernel (main chains of <= kMaxChain truncating MMAs)
         if (h.terms > 1) {
             const long long chain = (long long)h.kt * h.kh * h.kw * cch1 * (a.kc / 16) / nmain;
-            parts1 = (int)((chain + 449) / 450);
+            parts1 = (int)((chain + kMaxChain - 1) / kMaxChain);
             if (parts1 > cch1) parts1 = cch1;
             if (parts1 < 1) parts1 = 1;
         }

