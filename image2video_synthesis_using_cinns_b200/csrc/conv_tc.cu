@@ -66,6 +66,39 @@ struct EpiArgs {
     int T, H, W, Cout, res_ut, res_uh, res_uw, act, out_mode;
 };
 
+// Finish 16 consecutive output columns [nb, nb+16) of ONE output row held in registers: scale, bias, residual,
+// activation, store (channels-last, or the (B,T,C,H,W) frame layout of conv_img when out_mode == 1).
+__device__ __forceinline__ void row_finish(const EpiArgs& e, const float (&accv)[16], int nb, float scale, long long vox, long long roff,
+                                           int b, int t, int h, int w) {
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int n = nb + j;
+        float x = accv[j] * scale;
+        if (n < e.Cout) {
+            if (e.bias != nullptr) x += __ldg(e.bias + n);
+            if (e.res != nullptr) x += __ldg(e.res + roff + n);
+        }
+        v[j] = apply_act(x, e.act);
+    }
+    if (e.out_mode == 0) {
+        float* dst = e.y + vox * e.Cout + nb;
+        if ((e.Cout & 3) == 0 && nb + 15 < e.Cout) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (nb + j < e.Cout) dst[j] = v[j];
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (nb + j < e.Cout) e.y[((((long long)b * e.T + t) * e.Cout + nb + j) * e.H + h) * e.W + w] = v[j];
+    }
+}
+
 // One output row (voxel) per thread: sum `nacc` TMEM accumulators (column stride `acc_stride`), then
 // scale, bias, residual through the nearest-upsample map, activation, store.  tcgen05.ld is warp-collective,
 // so every lane walks all column chunks and only the stores are predicated.
@@ -92,34 +125,69 @@ __device__ __forceinline__ void epilogue_row(const EpiArgs& e, uint32_t tmem_lan
         }
         const int nb = n0 + c0;
         if (!valid || nb >= e.Cout) continue;
-        float v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int n = nb + j;
-            float x = accv[j] * scale;
-            if (n < e.Cout) {
-                if (e.bias != nullptr) x += __ldg(e.bias + n);
-                if (e.res != nullptr) x += __ldg(e.res + roff + n);
+        row_finish(e, accv, nb, scale, vox, roff, b, t, h, w);
+    }
+}
+
+// Write-out half of the coalesced epilogue: `stile` holds this warp's 32 rows x ncols scaled sums (row stride
+// ncols+4); lanes own fixed column groups, rows are walked with shuffled voxel / residual offsets.
+__device__ __forceinline__ void epilogue_writeout(const EpiArgs& e, const float* stile, int col0, int ncols, int n0, int lane,
+                                                  long long vox_lane, long long roff_lane, bool want_stats, float (&ssum)[4],
+                                                  float (&ssq)[4]) {
+    const int ld = ncols + 4;
+    // lane -> (row sub-index, column group); c4n float4 per row
+    const int c4n = ncols >> 2;
+    const int lanes_per_row = c4n < 32 ? c4n : 32;
+    const int rows_per_iter = 32 / lanes_per_row;
+    const int rsub = lane / lanes_per_row, cl = lane - rsub * lanes_per_row;
+    const bool vec_ok = (e.Cout & 3) == 0;
+    for (int cg = cl; cg < c4n; cg += 32) {          // more than one pass only when the slice is wider than 128
+        const int c = cg * 4, n = n0 + col0 + c;
+        const bool full4 = vec_ok && n + 3 < e.Cout;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e.bias != nullptr && n < e.Cout) {
+            if (full4) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+            else {
+                b4.x = __ldg(e.bias + n);
+                if (n + 1 < e.Cout) b4.y = __ldg(e.bias + n + 1);
+                if (n + 2 < e.Cout) b4.z = __ldg(e.bias + n + 2);
+                if (n + 3 < e.Cout) b4.w = __ldg(e.bias + n + 3);
             }
-            v[j] = apply_act(x, e.act);
         }
-        if (e.out_mode == 0) {
-            float* dst = e.y + vox * e.Cout + nb;
-            if ((e.Cout & 3) == 0 && nb + 15 < e.Cout) {
-#pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                    *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+#pragma unroll 4
+        for (int i = 0; i < 32; i += rows_per_iter) {
+            const int r = (i + rsub) & 31;
+            const long long vox = __shfl_sync(0xffffffffu, vox_lane, r);
+            const long long roff = __shfl_sync(0xffffffffu, roff_lane, r);
+            if (n >= e.Cout || rsub >= rows_per_iter) continue;     // spare lanes when c4n does not divide 32
+            const float4 a4 = *reinterpret_cast<const float4*>(stile + r * ld + c);
+            float v[4] = {a4.x + b4.x, a4.y + b4.y, a4.z + b4.z, a4.w + b4.w};
+            if (full4) {
+                if (e.res != nullptr) {
+                    const float4 r4 = __ldg(reinterpret_cast<const float4*>(e.res + roff + n));
+                    v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
+                }
+                const float4 o4 = make_float4(apply_act(v[0], e.act), apply_act(v[1], e.act), apply_act(v[2], e.act), apply_act(v[3], e.act));
+                *reinterpret_cast<float4*>(e.y + vox * e.Cout + n) = o4;
+                if (want_stats) {   // per-(sample, channel) sum / sum of squares of the stored values (feeds the next norm)
+                    ssum[0] += o4.x; ssum[1] += o4.y; ssum[2] += o4.z; ssum[3] += o4.w;
+                    ssq[0] = fmaf(o4.x, o4.x, ssq[0]); ssq[1] = fmaf(o4.y, o4.y, ssq[1]);
+                    ssq[2] = fmaf(o4.z, o4.z, ssq[2]); ssq[3] = fmaf(o4.w, o4.w, ssq[3]);
+                }
             } else {
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (nb + j < e.Cout) dst[j] = v[j];
+                for (int j = 0; j < 4; ++j)
+                    if (n + j < e.Cout) {
+                        float x = v[j];
+                        if (e.res != nullptr) x += __ldg(e.res + roff + n + j);
+                        x = apply_act(x, e.act);
+                        e.y[vox * e.Cout + n + j] = x;
+                        if (want_stats) { ssum[j] += x; ssq[j] = fmaf(x, x, ssq[j]); }
+                    }
             }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-                if (nb + j < e.Cout) e.y[((((long long)b * e.T + t) * e.Cout + nb + j) * e.H + h) * e.W + w] = v[j];
         }
     }
+    __syncwarp();
 }
 
 // Coalesced variant for channels-last output: the 32 rows a warp pulls out of TMEM are transposed through a
@@ -176,59 +244,7 @@ __device__ __forceinline__ void epilogue_warp_coalesced(const EpiArgs& e, float*
             dst[j] = make_float4(accv[4 * j] * scale, accv[4 * j + 1] * scale, accv[4 * j + 2] * scale, accv[4 * j + 3] * scale);
     }
     __syncwarp();
-    // lane -> (row sub-index, column group); c4n float4 per row
-    const int c4n = ncols >> 2;
-    const int lanes_per_row = c4n < 32 ? c4n : 32;
-    const int rows_per_iter = 32 / lanes_per_row;
-    const int rsub = lane / lanes_per_row, cl = lane - rsub * lanes_per_row;
-    const bool vec_ok = (e.Cout & 3) == 0;
-    for (int cg = cl; cg < c4n; cg += 32) {          // more than one pass only when the slice is wider than 128
-        const int c = cg * 4, n = n0 + col0 + c;
-        const bool full4 = vec_ok && n + 3 < e.Cout;
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (e.bias != nullptr && n < e.Cout) {
-            if (full4) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + n));
-            else {
-                b4.x = __ldg(e.bias + n);
-                if (n + 1 < e.Cout) b4.y = __ldg(e.bias + n + 1);
-                if (n + 2 < e.Cout) b4.z = __ldg(e.bias + n + 2);
-                if (n + 3 < e.Cout) b4.w = __ldg(e.bias + n + 3);
-            }
-        }
-#pragma unroll 4
-        for (int i = 0; i < 32; i += rows_per_iter) {
-            const int r = (i + rsub) & 31;
-            const long long vox = __shfl_sync(0xffffffffu, vox_lane, r);
-            const long long roff = __shfl_sync(0xffffffffu, roff_lane, r);
-            if (n >= e.Cout || rsub >= rows_per_iter) continue;     // spare lanes when c4n does not divide 32
-            const float4 a4 = *reinterpret_cast<const float4*>(stile + r * ld + c);
-            float v[4] = {a4.x + b4.x, a4.y + b4.y, a4.z + b4.z, a4.w + b4.w};
-            if (full4) {
-                if (e.res != nullptr) {
-                    const float4 r4 = __ldg(reinterpret_cast<const float4*>(e.res + roff + n));
-                    v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
-                }
-                const float4 o4 = make_float4(apply_act(v[0], e.act), apply_act(v[1], e.act), apply_act(v[2], e.act), apply_act(v[3], e.act));
-                *reinterpret_cast<float4*>(e.y + vox * e.Cout + n) = o4;
-                if (want_stats) {   // per-(sample, channel) sum / sum of squares of the stored values (feeds the next norm)
-                    ssum[0] += o4.x; ssum[1] += o4.y; ssum[2] += o4.z; ssum[3] += o4.w;
-                    ssq[0] = fmaf(o4.x, o4.x, ssq[0]); ssq[1] = fmaf(o4.y, o4.y, ssq[1]);
-                    ssq[2] = fmaf(o4.z, o4.z, ssq[2]); ssq[3] = fmaf(o4.w, o4.w, ssq[3]);
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (n + j < e.Cout) {
-                        float x = v[j];
-                        if (e.res != nullptr) x += __ldg(e.res + roff + n + j);
-                        x = apply_act(x, e.act);
-                        e.y[vox * e.Cout + n + j] = x;
-                        if (want_stats) { ssum[j] += x; ssq[j] = fmaf(x, x, ssq[j]); }
-                    }
-            }
-        }
-    }
-    __syncwarp();
+    epilogue_writeout(e, stile, col0, ncols, n0, lane, vox_lane, roff_lane, want_stats, ssum, ssq);
 }
 
 // flush a lane's column-group partial sums into stats[b, c, {sum, sumsq}] (double, device-wide atomics)
@@ -260,6 +276,73 @@ __device__ __forceinline__ void flush_stats(double* stats_b, int Cout, int n0, i
             atomicAdd(stats_b + 2 * (size_t)(n + j), (double)s[j]);
             atomicAdd(stats_b + 2 * (size_t)(n + j) + 1, (double)q[j]);
         }
+}
+
+
+// ---- kw-stacked ("wstack") epilogue pieces (halo kernel, narrow layers) ------------------------------------
+// The three kw taps of a narrow layer (Cout <= 64) are stacked along the MMA's N: one UNSHIFTED activation box
+// is multiplied by [W(kw=0) | W(kw=1) | W(kw=2)], so column group kw of accumulator row m' holds the contribution
+// of INPUT voxel m' through tap kw.  Output voxel m = m' - (kw-1):
+//     out[m] = D1[m] + D0[m-1] * [w > 0] + D2[m+1] * [w < W-1]
+// (the predicates are the conv's zero padding; tiles hold whole w-rows, so no halo is needed along w).
+// Rows m-1 / m+1 live in the neighbouring lanes: warp shuffles, plus a small shared-memory exchange for the
+// first / last lane of each 32-row warp slice (published in `xd0` / `xd2`, consumed after a named barrier).
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps
+
+// 16 columns [c, c+16) of the three kw groups of this lane's row, summed over the `nacc` accumulators
+__device__ __forceinline__ void wstack_chunk16(uint32_t tbase, int n_tile, int nacc, int accw, int c, float (&d0)[16], float (&d1)[16],
+                                               float (&d2)[16]) {
+    uint32_t r0[16], r1[16], r2[16];
+    ptx::tmem_ld_32x32b_x16(tbase + (uint32_t)c, r0);
+    ptx::tmem_ld_32x32b_x16(tbase + (uint32_t)(n_tile + c), r1);
+    ptx::tmem_ld_32x32b_x16(tbase + (uint32_t)(2 * n_tile + c), r2);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { d0[j] = __uint_as_float(r0[j]); d1[j] = __uint_as_float(r1[j]); d2[j] = __uint_as_float(r2[j]); }
+    for (int ai = 1; ai < nacc; ++ai) {
+        const uint32_t tb = tbase + (uint32_t)(ai * accw);
+        ptx::tmem_ld_32x32b_x16(tb + (uint32_t)c, r0);
+        ptx::tmem_ld_32x32b_x16(tb + (uint32_t)(n_tile + c), r1);
+        ptx::tmem_ld_32x32b_x16(tb + (uint32_t)(2 * n_tile + c), r2);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { d0[j] += __uint_as_float(r0[j]); d1[j] += __uint_as_float(r1[j]); d2[j] += __uint_as_float(r2[j]); }
+    }
+}
+
+// in-warp part of the shifted sum; lanes 0 / 31 still miss their cross-warp neighbour (added after the barrier)
+__device__ __forceinline__ void wstack_combine(const float (&d0)[16], const float (&d1)[16], const float (&d2)[16], int lane, bool left_ok,
+                                               bool right_ok, float (&v)[16]) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float up = __shfl_up_sync(0xffffffffu, d0[j], 1);
+        const float dn = __shfl_down_sync(0xffffffffu, d2[j], 1);
+        v[j] = d1[j] + ((left_ok && lane > 0) ? up : 0.f) + ((right_ok && lane < 31) ? dn : 0.f);
+    }
+}
+
+// Gather half of the coalesced epilogue for the stacked layout: fills `stile` like epilogue_warp_coalesced does and
+// publishes this warp's edge rows.  xd0 / xd2: [n_tile] floats of this warp's lane quarter (tile-column indexed).
+__device__ __forceinline__ void wstack_gather(float* stile, uint32_t tbase, int col0, int ncols, int n_tile, int nacc, int accw, float scale,
+                                              int lane, bool left_ok, bool right_ok, float* xd0, float* xd2) {
+    const int ld = ncols + 4;
+    for (int c0 = 0; c0 < ncols; c0 += 16) {
+        float d0[16], d1[16], d2[16], v[16];
+        wstack_chunk16(tbase, n_tile, nacc, accw, col0 + c0, d0, d1, d2);
+        wstack_combine(d0, d1, d2, lane, left_ok, right_ok, v);
+        if (lane == 31) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) xd0[col0 + c0 + j] = d0[j];
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) xd2[col0 + c0 + j] = d2[j];
+        }
+        float4* dst = reinterpret_cast<float4*>(stile + lane * ld + c0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            dst[j] = make_float4(v[4 * j] * scale, v[4 * j + 1] * scale, v[4 * j + 2] * scale, v[4 * j + 3] * scale);
+    }
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -459,6 +542,7 @@ struct ConvTcHArgs {
     int B, T, H, W, Cin, Cout;
     int kt, kw;                   // kh == 3
     int t_phase;                  // 1: input is the temporally x2 nearest-upsampled tensor stored at T/2 (see below)
+    int wstack;                   // 1: the 3 kw taps are stacked along N (narrow layers; see wstack_gather)
     int bw, bh2;                  // patch: bw x bh2 voxels (= 256)
     int tiles_w, tiles_h;
     int n_tile, kc, stages, terms, nacc;   // nacc accumulators per (sub-)tile ...
@@ -475,7 +559,9 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
     const uint32_t rb = (uint32_t)a.kc * 2;
     const uint32_t a_rows = (uint32_t)(a.bw * (a.bh2 + 2));
     const uint32_t a_bytes = (a_rows * rb + 1023u) & ~1023u;
-    const uint32_t b_tap = (uint32_t)a.n_tile * rb;                 // multiple of 1024 (host-checked)
+    const int nw = a.wstack ? 3 : 1;                                // kw taps per weight row block
+    const int accw = nw * a.n_tile;                                 // TMEM columns of one accumulator = the MMA's N
+    const uint32_t b_tap = (uint32_t)(nw * a.n_tile) * rb;          // one kh tap; multiple of 1024 (host-checked)
     const uint32_t b_bytes = 3 * b_tap;
     const uint32_t mult = a.terms > 1 ? 2u : 1u;                    // lo words only exist in the 3-term mode
     const uint32_t off_alo = a_bytes, off_bhi = mult * a_bytes, off_blo = mult * a_bytes + b_bytes;
@@ -498,7 +584,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
     const int iters = a.kt * a.kw * cchunks;
     const int bh_sub = a.bh2 / 2;
     uint32_t ncols = 32;
-    while (ncols < (uint32_t)(2 * a.n_tile * a.nacc)) ncols <<= 1;
+    while (ncols < (uint32_t)(2 * accw * a.nacc)) ncols <<= 1;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&mAh); ptx::prefetch_tensormap(&mBh);
@@ -533,7 +619,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
     const int wt_base = a.t_phase ? (t & 1) * 2 : 0;
     const int dt_lo = ct_base < 0 ? -ct_base : 0;
     const int dt_hi = (Tin - 1 - ct_base) < (a.kt - 1) ? (Tin - 1 - ct_base) : (a.kt - 1);
-    const int n_total = (dt_hi - dt_lo + 1) * a.kw * cchunks;     // pipeline stages this CTA runs
+    const int kw_iter = a.wstack ? 1 : a.kw;                      // stacked: one unshifted load covers all kw taps
+    const int n_total = (dt_hi - dt_lo + 1) * kw_iter * cchunks;  // pipeline stages this CTA runs
     (void)iters;
 
     if (warp == 0) {
@@ -542,12 +629,12 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
             int s = 0;
             uint32_t ph = 0;
             for (int dt = dt_lo; dt <= dt_hi; ++dt)
-            for (int dw = 0; dw < a.kw; ++dw)
+            for (int dw = 0; dw < kw_iter; ++dw)
             for (int cc = a.cc_lo; cc < a.cc_hi; ++cc) {
                 const int ct = ct_base + dt, wt = wt_base + dt, c0 = cc * a.kc;
                 ptx::mbar_wait(empty + s, ph ^ 1u);
                 uint8_t* st = smem + (size_t)s * stage_bytes;
-                const int cw = w0 + dw - a.kw / 2, ch = h0 - 1;
+                const int cw = a.wstack ? w0 : w0 + dw - a.kw / 2, ch = h0 - 1;
                 if (ptx::elect_one()) {
                     ptx::mbar_expect_tx(full + s, tx);
                     ptx::tma_load_5d(st, &mAh, full + s, c0, cw, ch, ct, b);
@@ -563,7 +650,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
         }
     } else if (warp == 1) {
         {
-            const uint32_t idesc = ptx::make_idesc_f16(TILE_M, a.n_tile);
+            const uint32_t idesc = ptx::make_idesc_f16(TILE_M, accw);
             const int ksteps = a.kc / 16;
             const uint64_t dproto = ptx::make_kmajor_desc(0, rb);
             const uint32_t dlo = (uint32_t)dproto, dhi = (uint32_t)(dproto >> 32);
@@ -582,9 +669,11 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
                 uint32_t sm_flag = n < nsmall ? 0u : 1u;         // same for the cross-term accumulators
                 // issue order (kh, k, term, sub): back-to-back MMAs target different TMEM accumulators, so a short
                 // (N = 64) MMA never waits on the one before it
-                const uint32_t tacc0 = tmem_base + (uint32_t)(ai * a.n_tile), tacc1 = tacc0 + (uint32_t)(a.nacc * a.n_tile);
-                // cross terms hi*lo, lo*hi accumulate apart from hi*hi (see conv_tc_kernel)
-                const uint32_t tsm0 = tmem_base + (uint32_t)((a.nmain + asm_) * a.n_tile), tsm1 = tsm0 + (uint32_t)(a.nacc * a.n_tile);
+                const uint32_t tacc0 = tmem_base + (uint32_t)(ai * accw), tacc1 = tacc0 + (uint32_t)(a.nacc * accw);
+                // cross terms hi*lo, lo*hi accumulate apart from hi*hi (see conv_tc_kernel); with a single accumulator
+                // per sub-tile (stacked N = 192 fills TMEM) they follow hi*hi into the same one (short chains only)
+                const uint32_t tsm0 = nsmall > 0 ? tmem_base + (uint32_t)((a.nmain + asm_) * accw) : tacc0;
+                const uint32_t tsm1 = tsm0 + (uint32_t)(a.nacc * accw);
                 uint32_t acc_flag = fresh;
                 if (ptx::elect_one()) {
 #pragma unroll
@@ -634,10 +723,77 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
         const int nh0 = ((a.n_tile / 16 + 1) / 2) * 16;
         const int col0 = half == 0 ? 0 : nh0, ncols = half == 0 ? nh0 : a.n_tile - nh0;
         const size_t stile_bytes = (size_t)32 * (nh0 + 4) * sizeof(float);
-        if (a.out_mode == 0 && 8 * stile_bytes <= (size_t)a.stages * stage_bytes) {
+        const int Tr = a.T / a.res_ut, Hr = a.H / a.res_uh, Wr = a.W / a.res_uw;
+        if (a.wstack) {
+            // stacked kw taps: shifted sum of the three column groups (see wstack_gather).  Host guarantees that the
+            // transpose tiles + exchange rows fit the drained pipeline buffers.
+            const bool coal = a.out_mode == 0;
+            float* stile = reinterpret_cast<float*>(smem + (size_t)(warp - 2) * stile_bytes);
+            float* xbuf = reinterpret_cast<float*>(smem + (coal ? 8 * stile_bytes : 0));      // [slot][quarter][d0|d2][n_tile]
+            const bool left_ok = wi > 0, right_ok = wi < a.bw - 1;
+            const bool fix0 = q > 0 && ((q * 32) % a.bw) > 0, fix31 = q < 3 && ((q * 32 + 31) % a.bw) < a.bw - 1;
+            float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};
+            const bool want_stats = a.stats != nullptr;
+            int slot = 0;
+            for (int sub = 0; sub < 2; ++sub) {
+                const int ww = w0 + wi, hh = h0 + sub * bh_sub + hi;
+                const long long vox_lane = (((long long)b * a.T + t) * a.H + hh) * a.W + ww;
+                const long long roff_lane = ((((long long)b * Tr + t / a.res_ut) * Hr + hh / a.res_uh) * Wr + ww / a.res_uw) * a.Cout;
+                const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * a.nacc * accw);
+                if (coal) {
+                    float* xs = xbuf + (size_t)slot * 8 * a.n_tile;
+                    if (ncols > 0)
+                        wstack_gather(stile, tbase, col0, ncols, a.n_tile, nacc_used, accw, scale, lane, left_ok, right_ok,
+                                      xs + (size_t)(q * 2) * a.n_tile, xs + (size_t)(q * 2 + 1) * a.n_tile);
+                    epi_bar();
+                    if (ncols > 0) {
+                        const int ld = ncols + 4;
+                        for (int c = lane; c < ncols; c += 32) {
+                            if (fix0) stile[c] += scale * xs[(size_t)((q - 1) * 2) * a.n_tile + col0 + c];
+                            if (fix31) stile[31 * ld + c] += scale * xs[(size_t)((q + 1) * 2 + 1) * a.n_tile + col0 + c];
+                        }
+                        __syncwarp();
+                        epilogue_writeout(e, stile, col0, ncols, n0, lane, vox_lane, roff_lane, want_stats, ssum, ssq);
+                    }
+                    slot ^= 1;
+                } else {
+                    // one output row per thread (frame layout of conv_img): half-0 warps work, all 8 keep the barrier count
+                    for (int c0 = 0; c0 < a.n_tile; c0 += 16) {
+                        float* xs = xbuf + (size_t)slot * 8 * a.n_tile;
+                        float v[16];
+                        if (half == 0) {
+                            float d0[16], d1[16], d2[16];
+                            wstack_chunk16(tbase, a.n_tile, nacc_used, accw, c0, d0, d1, d2);
+                            wstack_combine(d0, d1, d2, lane, left_ok, right_ok, v);
+                            if (lane == 31) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) xs[(size_t)(q * 2) * a.n_tile + c0 + j] = d0[j];
+                            }
+                            if (lane == 0) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) xs[(size_t)(q * 2 + 1) * a.n_tile + c0 + j] = d2[j];
+                            }
+                        }
+                        epi_bar();
+                        if (half == 0) {
+                            if (lane == 0 && fix0) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) v[j] += xs[(size_t)((q - 1) * 2) * a.n_tile + c0 + j];
+                            }
+                            if (lane == 31 && fix31) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) v[j] += xs[(size_t)((q + 1) * 2 + 1) * a.n_tile + c0 + j];
+                            }
+                            if (n0 + c0 < a.Cout) row_finish(e, v, n0 + c0, scale, vox_lane, roff_lane, b, t, hh, ww);
+                        }
+                        slot ^= 1;
+                    }
+                }
+            }
+            if (coal && want_stats && ncols > 0) flush_stats(a.stats + (size_t)b * a.Cout * 2, a.Cout, n0, col0, ncols, lane, ssum, ssq);
+        } else if (a.out_mode == 0 && 8 * stile_bytes <= (size_t)a.stages * stage_bytes) {
             // pipeline buffers are drained (every TMA landed, every MMA retired): reuse them as transpose tiles
             float* stile = reinterpret_cast<float*>(smem + (size_t)(warp - 2) * stile_bytes);
-            const int Tr = a.T / a.res_ut, Hr = a.H / a.res_uh, Wr = a.W / a.res_uw;
             float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};
             const bool want_stats = a.stats != nullptr;
             for (int sub = 0; sub < 2; ++sub) {
@@ -751,36 +907,54 @@ static int launch_conv_tc_halo(const ConvTcArgs& h, cudaStream_t stream) {
     if (a.bh2 < 2 || h.H % a.bh2 != 0) return 1;
     const int n_cap = h.terms == 3 ? 128 : 256;
     a.n_tile = h.cout_pad < n_cap ? h.cout_pad : n_cap;
+    // kw-stacked form (variant 0 = automatic, 3 = required, 2 = never): narrow layers (Cout <= 64) stack the three kw
+    // taps along the MMA's N (N = 3 Cout <= 192).  One unshifted activation load then feeds 9 taps instead of 3, the
+    // MMA count drops 3x, and N >= 48 keeps the tensor pipe off the shared-memory A-read floor that N = 64 MMAs
+    // sit on.  Needs whole w-rows per tile (W <= 128) so the +-1 voxel shift never leaves the tile.
+    bool wstack = h.variant != 2 && h.kw == 3 && h.cout_pad <= 64 && h.W == a.bw;
     // channel chunk: the largest of 64/32/16 that divides Cin, keeps tap slabs 1024B-aligned and fits >= 2 stages
     const int mult = h.terms > 1 ? 2 : 1;
-    int kc = 0, stages = 0;
+    int kc = 0, stages = 0, nw = 1;
     size_t stage_bytes = 0;
-    for (int cand : {64, 32, 16}) {
-        if (h.Cin % cand) continue;
-        const size_t rb = (size_t)cand * 2;
-        if ((a.n_tile * rb) % 1024 != 0) continue;
-        const size_t a_bytes = ((size_t)a.bw * (a.bh2 + 2) * rb + 1023) & ~(size_t)1023;
-        const size_t sb = mult * (a_bytes + 3 * a.n_tile * rb);
-        const int st = (int)((220 * 1024 - 2048) / sb);
-        if (st >= 2) { kc = cand; stages = st > 6 ? 6 : st; stage_bytes = sb; break; }
+    for (int attempt = 0; attempt < 2 && kc == 0; ++attempt) {
+        if (attempt == 1) {
+            if (!wstack) break;
+            wstack = false;                                          // stacked form does not fit: plain halo form
+        }
+        nw = wstack ? 3 : 1;
+        for (int cand : {64, 32, 16}) {
+            if (h.Cin % cand) continue;
+            const size_t rb = (size_t)cand * 2;
+            if ((nw * a.n_tile * rb) % 1024 != 0) continue;
+            const size_t a_bytes = ((size_t)a.bw * (a.bh2 + 2) * rb + 1023) & ~(size_t)1023;
+            const size_t sb = mult * (a_bytes + 3 * nw * a.n_tile * rb);
+            const int st = (int)((220 * 1024 - 2048) / sb);
+            if (st >= 2) { kc = cand; stages = st > 6 ? 6 : st; stage_bytes = sb; break; }
+        }
     }
+    I2V_REQUIRE(h.variant != 3 || (wstack && kc != 0), "conv_tc: shape not eligible for the kw-stacked halo kernel");
+    a.wstack = wstack ? 1 : 0;
     if (kc == 0) return 1;
     a.kc = kc; a.stages = stages; a.terms = h.terms;
-    int nacc = 512 / (2 * a.n_tile);
+    int nacc = 512 / (2 * nw * a.n_tile);
     if (nacc > 4) nacc = 4;
     const int cch = h.Cin / kc;
+    const int kw_iter = wstack ? 1 : h.kw;
     // K split across launches: the tensor core's fp32 accumulate TRUNCATES, so the error of one accumulator
     // grows with the number of MMAs chained into it (measured ~1e-5 at ~1300 chained MMAs).  Keep every chain
     // at <= kMaxChain MMAs: split the channel chunks over several launches whose partial results are combined by
     // the epilogue's exact fp32 add (launch p > 0 reads y as its residual, in place).
     // accumulators per sub-tile: terms == 3 -> nmain for hi*hi + as many for the cross terms; terms == 1 -> all main
     int nmain = h.terms > 1 ? nacc / 2 : nacc;
+    // stacked N = 192 leaves room for ONE accumulator per sub-tile: the cross terms then share it (3x the chain)
+    const bool shared_acc = h.terms > 1 && nacc == 1;
+    if (shared_acc) nmain = 1;
     if (nmain < 1) return 1;                                                   // needs 2 accumulators per sub-tile
     if (nmain > 2) nmain = 2;
-    const int main_per_stage = 3 * (kc / 16);                                  // hi*hi MMAs per stage and sub-tile
+    const int main_per_stage = 3 * (kc / 16) * (shared_acc ? 3 : 1);           // chained MMAs per stage and sub-tile
     int parts = 1;
     if (h.terms > 1) {
-        const long long chain = (long long)kt_eff * h.kw * cch * main_per_stage / nmain;
+        const long long chain = (long long)kt_eff * kw_iter * cch * main_per_stage / nmain;
         parts = (int)((chain + kMaxChain - 1) / kMaxChain);
         if (parts > cch) parts = cch;
         if (parts < 1) parts = 1;
@@ -790,11 +964,11 @@ static int launch_conv_tc_halo(const ConvTcArgs& h, cudaStream_t stream) {
     {
         // every CTA runs at least kw * (chunks of the smallest part) stages: each accumulator must be written
         const int last_chunks = cch - (parts - 1) * cper;
-        const int min_stages = h.kw * (last_chunks < cper ? last_chunks : cper);
+        const int min_stages = kw_iter * (last_chunks < cper ? last_chunks : cper);
         if (nmain > min_stages) nmain = min_stages;
     }
     a.nmain = nmain;
-    a.nacc = h.terms > 1 ? 2 * nmain : nmain;
+    a.nacc = (h.terms > 1 && !shared_acc) ? 2 * nmain : nmain;
     nacc = a.nacc;
     a.t_phase = h.t_phase ? 1 : 0;
     a.bias = h.bias; a.res = h.res; a.scale_ptr = h.scale_ptr; a.y = h.y; a.stats = h.stats;
@@ -820,7 +994,8 @@ static int launch_conv_tc_halo(const ConvTcArgs& h, cudaStream_t stream) {
         // temporal extent of the weight tensor: kt taps, or 2 phases x 2 taps ([phase][tap][kh][kw][cout][cin])
         const cuuint64_t dims[5] = {(cuuint64_t)h.Cin, (cuuint64_t)h.cout_pad, (cuuint64_t)h.kw, 3, (cuuint64_t)(h.t_phase ? 4 : h.kt)};
         const cuuint64_t st[4] = {(cuuint64_t)h.Cin * 2, row, row * h.kw, row * h.kw * 3};
-        const cuuint32_t box[5] = {(cuuint32_t)kc, (cuuint32_t)a.n_tile, 1, 3, 1};
+        // stacked form: all 9 (kh, kw) taps of one kt in a single box -> smem [kh][kw][n][kc]
+        const cuuint32_t box[5] = {(cuuint32_t)kc, (cuuint32_t)a.n_tile, (cuuint32_t)nw, 3, 1};
         if (int rc = encode_map(&mBh, h.w_hi, 5, dims, st, box, rb)) return rc;
         if (int rc = encode_map(&mBl, h.terms > 1 ? h.w_lo : h.w_hi, 5, dims, st, box, rb)) return rc;
     }
@@ -834,6 +1009,10 @@ static int launch_conv_tc_halo(const ConvTcArgs& h, cudaStream_t stream) {
         const size_t nh0 = (size_t)((a.n_tile / 16 + 1) / 2) * 16;
         I2V_REQUIRE(h.stats == nullptr || 8 * 32 * (nh0 + 4) * sizeof(float) <= (size_t)stages * stage_bytes,
                     "conv_tc: transpose tiles do not fit the pipeline buffers, fused statistics unavailable");
+        // stacked form: transpose tiles + 2 slots x 4 quarters x 2 edge rows of n_tile floats
+        I2V_REQUIRE(!wstack || 8 * 32 * (nh0 + 4) * sizeof(float) + 16 * (size_t)a.n_tile * sizeof(float) <= (size_t)stages * stage_bytes,
+                    "conv_tc: stacked epilogue buffers do not fit the pipeline buffers");
+        I2V_REQUIRE(!wstack || (long long)a.tiles_w == 1, "conv_tc: stacked form needs whole rows per tile");
     }
     const long long M = (long long)h.B * h.T * h.H * h.W;
     const double K_ = (double)h.kt * h.kh * h.kw * h.Cin;

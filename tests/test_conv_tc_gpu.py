@@ -26,9 +26,16 @@ CASES = [
     ("long_k_halo", (1, 256, 2, 16, 16), 128, (3, 3, 3)),     # halo kernel, 2 accumulators x 2 sub-tiles
     ("halo_n64_t4", (2, 64, 4, 8, 64), 64, (3, 3, 3)),        # halo kernel, interior t (all 3 temporal taps) + edges
     ("halo_cout3", (1, 64, 2, 4, 64), 3, (3, 3, 3)),          # conv_img shape: N padded to 16
+    ("g4_conv0_like", (1, 128, 4, 8, 64), 64, (3, 3, 3)),     # kw-stacked N=192, kc=16, one shared accumulator
+    ("wstack_w32_n32", (2, 32, 2, 32, 32), 32, (3, 3, 3)),    # stacked N=96, 2 accumulators, rows of 32 (no cross-warp edge)
+    ("wstack_w16_n48", (1, 64, 2, 16, 16), 48, (3, 3, 3)),    # stacked N=144, rows of 16
+    ("wstack_2d", (2, 64, 1, 16, 64), 64, (1, 3, 3)),         # 2-D conv (kt=1), stacked
 ]
 HALO_OK = {"g3_like_w64", "w32_kc64_n128", "w16_n256", "kc32", "spade_gb_2d", "w128_row", "long_k_halo",
-           "halo_n64_t4", "halo_cout3"}
+           "halo_n64_t4", "halo_cout3", "g4_conv0_like", "wstack_w32_n32", "wstack_w16_n48", "wstack_2d"}
+# narrow layers (Cout <= 64, whole w-rows per tile): the halo kernel's kw-stacked form, forced with variant=3
+WSTACK_OK = {"g3_like_w64", "kc32", "w128_row", "halo_n64_t4", "halo_cout3", "g4_conv0_like", "wstack_w32_n32",
+             "wstack_w16_n48", "wstack_2d"}
 
 
 @pytest.mark.parametrize("name,xs,cout,k", CASES, ids=[c[0] for c in CASES])
@@ -46,8 +53,10 @@ def test_conv_tc_matches_fp32(name, xs, cout, k):
     # both kernels explicitly: v1 (per-tap boxes) everywhere, v2 (256-row H-halo) where the shape allows
     ev1 = rel_inf(ou.from_cl(ou.conv_tc(ou.to_cl(x), ou.taps(w), b.cuda(), None, k, variant=1)), want)
     ev2 = rel_inf(ou.from_cl(ou.conv_tc(ou.to_cl(x), ou.taps(w), b.cuda(), None, k, variant=2)), want) if name in HALO_OK else None
-    report("conv_tc:" + name, split3=e3, fp16_single=e1, simt_fp32=simt, v1=ev1, v2_halo=ev2)
+    ev3 = rel_inf(ou.from_cl(ou.conv_tc(ou.to_cl(x), ou.taps(w), b.cuda(), None, k, variant=3)), want) if name in WSTACK_OK else None
+    report("conv_tc:" + name, split3=e3, fp16_single=e1, simt_fp32=simt, v1=ev1, v2_halo=ev2, v3_wstack=ev3)
     assert ev1 < 6e-6 and (ev2 is None or ev2 < 1e-5)   # halo kernel: 2 accumulators at N=128 instead of 4
+    assert ev3 is None or ev3 < 1e-5
     assert got.shape == want.shape
     # fp32-grade: within a small factor of the fp32 SIMT engine's own rounding.  The residual gap is the
     # tensor core's truncating fp32 accumulate (measured ~1e-5 at K=6912 with ONE accumulator), which the
@@ -70,6 +79,28 @@ def test_conv_tc_epilogue_residual_act_and_frames_layout():
     want = torch.tanh(F.conv3d(x, w3, b3, 1, 1)).transpose(1, 2)
     got = ou.conv_tc(ou.to_cl(x), ou.taps(w3), b3.cuda(), None, (3, 3, 3), act=3, out_mode=1)
     assert rel_inf(got.cpu(), want) < 1e-5
+
+
+@pytest.mark.parametrize("hw", [(16, 16), (8, 64), (2, 128)])
+def test_conv_tc_wstack_epilogue_residual_act_and_frames_layout(hw):
+    """kw-stacked halo kernel: shifted-sum epilogue with bias, upsampled residual, activation; frame layout + tanh."""
+    g = G(11)
+    H, W = hw
+    x = torch.randn(2, 64, 2, H, W, generator=g)
+    w = torch.randn(32, 64, 3, 3, 3, generator=g) * 0.03
+    b = torch.randn(32, generator=g)
+    res = torch.randn(2, 32, 1, H // 2, W // 2, generator=g)
+    want = F.leaky_relu(F.conv3d(x, w, b, 1, 1) + F.interpolate(res, scale_factor=2.0), 0.2)
+    got = ou.conv_tc(ou.to_cl(x), ou.taps(w), b.cuda(), ou.to_cl(res), (3, 3, 3), res_up=(2, 2, 2), act=2, variant=3)
+    assert rel_inf(ou.from_cl(got), want) < 1e-5
+    w3 = torch.randn(3, 64, 3, 3, 3, generator=g) * 0.03
+    b3 = torch.randn(3, generator=g)
+    want = torch.tanh(F.conv3d(x, w3, b3, 1, 1)).transpose(1, 2)
+    got = ou.conv_tc(ou.to_cl(x), ou.taps(w3), b3.cuda(), None, (3, 3, 3), act=3, out_mode=1, variant=3)
+    assert rel_inf(got.cpu(), want) < 1e-5
+    # single fp16 product mode takes the same path with one accumulator
+    got = ou.conv_tc(ou.to_cl(x), ou.taps(w), b.cuda(), None, (3, 3, 3), terms=1, variant=3)
+    assert rel_inf(ou.from_cl(got), F.conv3d(x, w, b, 1, 1)) < 1e-3
 
 
 @pytest.mark.parametrize("engine", [1])
