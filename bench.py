@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--conv-engine", type=int, default=1, help="1 tcgen05 split-fp16 (parity), 0 fp32 SIMT, 2 fp16 fast")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ckpt-dir", default=None, help="reuse / create synthetic checkpoints here")
+    ap.add_argument("--streams", type=int, default=1, help="decoder micro-batches alternate over this many CUDA streams")
     ap.add_argument("--dump-launches", default=None, help="CSV of per-launch device times of the timed steps")
     return ap.parse_args()
 
@@ -190,7 +191,8 @@ def run_b200(args):
 
     L = lib.load()
     mp = synthetic_ckpt(args, rank, barrier)
-    model = Model(mp, args.seq_length, device=dev, micro_batch=args.micro_batch, conv_engine=args.conv_engine)
+    model = Model(mp, args.seq_length, device=dev, micro_batch=args.micro_batch, conv_engine=args.conv_engine,
+                  streams=args.streams)
     img = model.config.Data["img_size"]
     B = args.batch
     x0_all, res_all = make_inputs(B * world, img, model.z_dim)        # one global draw, sliced per rank
@@ -296,7 +298,7 @@ def run_b200(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic start frames U[-1,1], random-init weights in the reference checkpoint format",
             "config": {"workload": f"{args.dataset.upper()} {img}x{img} seq_length={args.seq_length}, batch={B} per GPU "
-                                   f"(global {B * world}), fp32 parity arithmetic, conv_engine={args.conv_engine}, micro_batch={args.micro_batch}",
+                                   f"(global {B * world}), fp32 parity arithmetic, conv_engine={args.conv_engine}, micro_batch={args.micro_batch}, streams={args.streams}",
                        "l2": "per-step working set (activations+weights, GBs) exceeds the 126 MB L2; no explicit flush",
                        "parallelism": f"batch-sharded x{world}, one all-gather of frames" if world > 1 else "single GPU"},
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,

@@ -37,7 +37,7 @@ struct ConvTcArgs {
     int kt, kh, kw;
     int res_ut, res_uh, res_uw, act, out_mode;
     int terms;                                // 3: hi*hi+hi*lo+lo*hi (fp32-grade)   1: hi*hi only
-    int variant = 0;                          // 0: auto (halo kernel when eligible)  1: force v1  2: force halo kernel
+    int variant = 0;                          // 0: auto  1: per-tap kernel  2: halo kernel, never kw-stacked  3: halo kernel, kw-stacked
     // 1: the logical input is x nearest-upsampled x2 in time; x_hi/x_lo hold it at T/2 planes and w_hi/w_lo hold the
     //    phase-combined weights [2 phases][2 taps][kh][kw][cout_pad][Cin] (halo kernel only)
     int t_phase = 0;

@@ -33,7 +33,7 @@ class Model:
     select the device, the decoder micro-batch and the decoder's conv engine (1 = tcgen05 tensor cores with
     the error-compensated fp16 split, fp32-grade parity, default; 0 = fp32 SIMT; 2 = single fp16 product)."""
 
-    def __init__(self, model_path, vid_length, transfer=False, *, device="cuda", micro_batch=32, conv_engine=1):
+    def __init__(self, model_path, vid_length, transfer=False, *, device="cuda", micro_batch=32, conv_engine=1, streams=1):
         opt = load_yaml(model_path + "config_stage2.yaml")                                   # get_model.py:15
         fs = opt.First_stage_model
         path_stage1 = fs["model_path"] + fs["model_name"] + "/"                              # get_model.py:16
@@ -42,7 +42,7 @@ class Model:
 
         self.decoder = modules.Generator(_load_state(path_stage1 + fs["checkpoint_decoder"] + ".pth"),
                                          config.Decoder, device=device, conv_engine=conv_engine,
-                                         micro_batch=micro_batch)                             # get_model.py:22-24
+                                         micro_batch=micro_batch, streams=streams)                             # get_model.py:22-24
         if transfer:
             self.encoder = modules.Encoder(_load_state(path_stage1 + fs["checkpoint_encoder"] + ".pth.tar"),
                                            config.Encoder, device=device)                     # get_model.py:27-31

@@ -184,11 +184,15 @@ class Generator(_Native):
 
     _destroy = "i2v_decoder_destroy"
 
-    def __init__(self, state_dict, dic, device="cuda", conv_engine=1, micro_batch=16):
+    def __init__(self, state_dict, dic, device="cuda", conv_engine=1, micro_batch=16, streams=1):
         super().__init__(device)
         self.nf, self.z_dim = dic["channel_factor"], dic["z_dim"]
         self.upsample_s, self.upsample_t = list(dic["upsample_s"]), list(dic["upsample_t"])
         self.micro_batch = micro_batch
+        # micro-batches are independent: with streams > 1 they alternate over side streams (own workspace each), so one
+        # micro-batch's HBM-bound passes and kernel tails overlap the other's tensor-bound convs
+        self.n_streams = max(1, int(streams))
+        self._side = None
         if conv_engine >= 1 and self.nf % 16 != 0:
             conv_engine = 0      # tensor-core tiles need channel counts that are multiples of 16
         us = (ctypes.c_int * 2)(*self.upsample_s)
@@ -215,11 +219,31 @@ class Generator(_Native):
         mb = max(1, min(self.micro_batch, B))
         if B == 0:
             return out
-        ws = self._workspace(self.L.i2v_decoder_workspace_bytes(self.h, mb, H, W))
-        for b0 in range(0, B, mb):
+        nbytes = self.L.i2v_decoder_workspace_bytes(self.h, mb, H, W)
+        ns = min(self.n_streams, (B + mb - 1) // mb)
+        if ns <= 1:
+            ws = self._workspace(nbytes)
+            for b0 in range(0, B, mb):
+                n = min(mb, B - b0)
+                _lib.check(self.L.i2v_decoder_forward(self.h, _ptr(img[b0:b0 + n]), _ptr(z[b0:b0 + n]), _ptr(out[b0:b0 + n]),
+                                                      n, H, W, _ptr(ws), ws.numel(), _stream()), "decoder_forward")
+            return out
+        if nbytes == 0:
+            raise RuntimeError(f"workspace query failed: {self.L.i2v_last_error().decode()}")
+        if self._side is None or len(self._side) < ns or self._side[0][1].numel() < nbytes:
+            self._side = [(torch.cuda.Stream(device=self.device),
+                           torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)) for _ in range(ns)]
+        cur = torch.cuda.current_stream(self.device)
+        for st, _ in self._side[:ns]:
+            st.wait_stream(cur)                       # inputs were produced on the caller's stream
+        for i, b0 in enumerate(range(0, B, mb)):
             n = min(mb, B - b0)
+            st, ws = self._side[i % ns]
             _lib.check(self.L.i2v_decoder_forward(self.h, _ptr(img[b0:b0 + n]), _ptr(z[b0:b0 + n]), _ptr(out[b0:b0 + n]),
-                                                  n, H, W, _ptr(ws), ws.numel(), _stream()), "decoder_forward")
+                                                  n, H, W, _ptr(ws), ws.numel(), ctypes.c_void_p(st.cuda_stream)),
+                       "decoder_forward")
+        for st, _ in self._side[:ns]:
+            cur.wait_stream(st)                       # the caller's stream owns the frames again
         return out
 
     __call__ = forward
