@@ -3,6 +3,7 @@
 // it never allocates device memory and never synchronises.
 #include <algorithm>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -45,6 +46,15 @@ ProfScope::ProfScope(int cat, double flops, double bytes, cudaStream_t stream) :
 }
 ProfScope::~ProfScope() {
     if (idx_ >= 0) cudaEventRecord(g_prof.recs[idx_].b, stream_);
+}
+
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("I2V_PDL");
+        v = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
 }
 
 void set_error(const char* fmt, ...) {

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <utility>
 
 namespace i2v {
 
@@ -24,6 +25,29 @@ __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+// Programmatic dependent launch.  Every kernel of the path (except the cooperative flow kernel) is launched with the
+// programmatic-stream-serialization attribute, lets its successor be scheduled right away (launch_dependents) and
+// only then waits for its predecessor to complete and flush (wait): the successor's launch latency, block scheduling
+// and prologue (barrier init, TMEM allocation, tensor-map prefetch) overlap the predecessor's tail.  Correctness
+// rests on one rule: no global-memory access before pdl_wait().  Completion is transitive because every kernel
+// finishes after its own wait returns.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();   // api.cu; I2V_PDL=0 turns the launch attribute off (the device-side instructions become no-ops)
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 // thread-local error slot surfaced through i2v_last_error()

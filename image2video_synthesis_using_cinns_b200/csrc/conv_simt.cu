@@ -30,6 +30,8 @@ template <bool VEC>
 __global__ void __launch_bounds__(NT, 2) conv_simt_kernel(const ConvArgs a) {
     __shared__ __align__(16) float As[2][BK][BM];
     __shared__ __align__(16) float Bs[2][BK][BN];
+    pdl_launch_dependents();
+    pdl_wait();
 
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
@@ -271,10 +273,9 @@ int launch_conv_simt(const ConvArgs& a, cudaStream_t stream) {
         if (ks > 1) grid.z = ks;
     }
     if (a.Cin % 16 == 0)
-        conv_simt_kernel<true><<<grid, NT, 0, stream>>>(a);
+        I2V_CHECK_CUDA(launch_k(conv_simt_kernel<true>, grid, dim3(NT), 0, stream, a));
     else
-        conv_simt_kernel<false><<<grid, NT, 0, stream>>>(a);
-    I2V_CHECK_CUDA(cudaGetLastError());
+        I2V_CHECK_CUDA(launch_k(conv_simt_kernel<false>, grid, dim3(NT), 0, stream, a));
     return 0;
 }
 

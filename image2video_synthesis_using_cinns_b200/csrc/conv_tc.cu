@@ -25,6 +25,8 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "prof.h"
@@ -36,14 +38,14 @@ namespace {
 
 constexpr int TC_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 
-// optional phase timestamps (i2v_debug_set_buffer): 8 x u64 per CTA, %globaltimer in ns
+// optional phase timestamps (i2v_debug_conv_tc_timestamps): 16 x u64 per CTA, %globaltimer in ns
 __device__ unsigned long long* g_dbg = nullptr;
 __device__ int g_dbg_ctas = 0;
 __device__ __forceinline__ void dbg_stamp(int slot) {
     if (g_dbg != nullptr && (int)blockIdx.x < g_dbg_ctas && blockIdx.y == 0) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        g_dbg[(size_t)blockIdx.x * 8 + slot] = t;
+        g_dbg[(size_t)blockIdx.x * 16 + slot] = t;
     }
 }
 constexpr int TILE_M = 128;
@@ -200,7 +202,7 @@ __device__ __forceinline__ void epilogue_writeout(const EpiArgs& e, const float*
 __device__ __forceinline__ void epilogue_warp_coalesced(const EpiArgs& e, float* stile /* [32][ncols+4] */, uint32_t tmem_lane_base,
                                                         int col0, int ncols, int nacc, int acc_stride, int n0, float scale, int lane,
                                                         long long vox_lane, long long roff_lane, bool want_stats, float (&ssum)[4],
-                                                        float (&ssq)[4]) {
+                                                        float (&ssq)[4], int dbg_slot = -1) {
     // this warp owns tile columns [col0, col0+ncols) of its 32 rows
     const int ld = ncols + 4;
     int c0 = 0;
@@ -244,7 +246,9 @@ __device__ __forceinline__ void epilogue_warp_coalesced(const EpiArgs& e, float*
             dst[j] = make_float4(accv[4 * j] * scale, accv[4 * j + 1] * scale, accv[4 * j + 2] * scale, accv[4 * j + 3] * scale);
     }
     __syncwarp();
+    if (dbg_slot >= 0 && threadIdx.x == 64) dbg_stamp(dbg_slot);          // this sub-tile is out of TMEM
     epilogue_writeout(e, stile, col0, ncols, n0, lane, vox_lane, roff_lane, want_stats, ssum, ssq);
+    if (dbg_slot >= 0 && threadIdx.x == 64) dbg_stamp(dbg_slot + 1);      // ... and its stores are issued
 }
 
 // flush a lane's column-group partial sums into stats[b, c, {sum, sumsq}] (double, device-wide atomics)
@@ -390,6 +394,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
     ptx::tc_fence_after();
     // warp-uniform by construction; the shuffle tells the compiler so (TMEM addresses feed uniform registers)
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    // Only now may the successor be scheduled: this CTA already owns its TMEM columns, so a co-resident CTA of the
+    // next kernel can never take them first and then sit in its own pdl_wait() while this one starves.
+    pdl_launch_dependents();
+    pdl_wait();      // prologue above touched no global memory: it overlapped the previous kernel's tail
 
     // A tap whose shifted box lies entirely in the zero padding contributes nothing (head_0: T = 1, so 18 of
     // the 27 taps): producer, issuer and epilogue all skip it.
@@ -549,6 +557,7 @@ struct ConvTcHArgs {
     int nmain;                             // ... of which the first nmain take hi*hi, the rest the small cross terms
     int res_ut, res_uh, res_uw, act, out_mode;
     int cc_lo, cc_hi;             // channel-chunk range [cc_lo, cc_hi) of this launch (K split across launches)
+    int flags;                    // bit 0: epilogue warps prefetch their residual rows into L2 while the main loop runs
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -604,6 +613,10 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform (see conv_tc_kernel)
+    // Only now may the successor be scheduled: this CTA already owns its TMEM columns, so a co-resident CTA of the
+    // next kernel can never take them first and then sit in its own pdl_wait() while this one starves.
+    pdl_launch_dependents();
+    pdl_wait();      // prologue above touched no global memory: it overlapped the previous kernel's tail
     if (threadIdx.x == 0) dbg_stamp(1);                       // prologue done
 
     // Temporal taps that fall outside the clip contribute only zero padding: both pipeline ends skip them.
@@ -711,6 +724,25 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
             if (lane == 0) dbg_stamp(3);                      // last MMA issued
         }
     } else {
+        if (a.res != nullptr && (a.flags & 1)) {
+            // The epilogue warps idle through the main loop: pull the residual rows they will add (the shortcut through
+            // its upsample map, or the previous K-split partial sum) from HBM into L2 now, so that the latency-bound
+            // residual reads of the epilogue hit L2.
+            const int q = warp & 3, half = (warp - 2) >> 2, m = q * 32 + lane;
+            const int wi = m % a.bw, hi = m / a.bw;
+            const int nh0 = ((a.n_tile / 16 + 1) / 2) * 16;
+            const int col0 = half == 0 ? 0 : nh0, ncols = half == 0 ? nh0 : a.n_tile - nh0;
+            const int Tr = a.T / a.res_ut, Hr = a.H / a.res_uh, Wr = a.W / a.res_uw;
+            for (int sub = 0; sub < 2; ++sub) {
+                const int ww = w0 + wi, hh = h0 + sub * bh_sub + hi;
+                const long long roff = ((((long long)b * Tr + t / a.res_ut) * Hr + hh / a.res_uh) * Wr + ww / a.res_uw) * a.Cout;
+                int c_lo = n0 + col0, c_hi = n0 + col0 + ncols;
+                if (c_hi > a.Cout) c_hi = a.Cout;
+                const char* p = reinterpret_cast<const char*>(a.res + roff + c_lo);
+                for (int off = 0; off < (c_hi - c_lo) * 4; off += 128)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
+            }
+        }
         ptx::mbar_wait_backoff(tmem_full, 0);
         if (threadIdx.x == 64) dbg_stamp(4);                  // accumulators complete
         ptx::tc_fence_after();
@@ -753,7 +785,9 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
                             if (fix31) stile[31 * ld + c] += scale * xs[(size_t)((q + 1) * 2 + 1) * a.n_tile + col0 + c];
                         }
                         __syncwarp();
+                        if (threadIdx.x == 64) dbg_stamp(8 + 2 * sub);
                         epilogue_writeout(e, stile, col0, ncols, n0, lane, vox_lane, roff_lane, want_stats, ssum, ssq);
+                        if (threadIdx.x == 64) dbg_stamp(9 + 2 * sub);
                     }
                     slot ^= 1;
                 } else {
@@ -802,9 +836,11 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
                 const long long roff_lane = ((((long long)b * Tr + t / a.res_ut) * Hr + hh / a.res_uh) * Wr + ww / a.res_uw) * a.Cout;
                 if (ncols > 0)
                     epilogue_warp_coalesced(e, stile, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * a.nacc * a.n_tile), col0,
-                                            ncols, nacc_used, a.n_tile, n0, scale, lane, vox_lane, roff_lane, want_stats, ssum, ssq);
+                                            ncols, nacc_used, a.n_tile, n0, scale, lane, vox_lane, roff_lane, want_stats, ssum, ssq,
+                                            8 + 2 * sub);
             }
             if (want_stats && ncols > 0) flush_stats(a.stats + (size_t)b * a.Cout * 2, a.Cout, n0, col0, ncols, lane, ssum, ssq);
+            if (threadIdx.x == 64) dbg_stamp(12);
         } else if (half == 0) {
             for (int sub = 0; sub < 2; ++sub)
                 epilogue_row(e, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * a.nacc * a.n_tile), a.n_tile, nacc_used,
@@ -820,6 +856,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
 
 __global__ void split_fp16_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, float scale,
                                   long long n) {
+    pdl_launch_dependents();
+    pdl_wait();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float v = x[i] * scale;
         const __half h = __float2half_rn(v);
@@ -859,6 +897,28 @@ int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dim
 
 bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
+// tuning switches of the halo kernel (I2V_TC_FLAGS overrides; bit 0 = residual L2 prefetch)
+int tc_flags() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("I2V_TC_FLAGS");
+        v = e ? atoi(e) : 1;
+    }
+    return v;
+}
+
+// pipeline depth the halo kernel aims for when it picks its channel chunk (I2V_TC_MIN_STAGES overrides: tuning aid)
+int tc_min_stages() {
+    static int v = 0;
+    if (v == 0) {
+        const char* e = getenv("I2V_TC_MIN_STAGES");
+        v = e ? atoi(e) : 2;
+        if (v < 2) v = 2;
+        if (v > 6) v = 6;
+    }
+    return v;
+}
+
 }  // namespace
 
 int conv_tc_set_debug(unsigned long long* buf, int ctas) {
@@ -890,8 +950,7 @@ int launch_split_fp16(const float* x, __half* hi, __half* lo, float scale, long 
     long long blocks = (n + 255) / 256;
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
     ProfScope ps(PROF_OTHER, 0, 0, stream);
-    split_fp16_kernel<<<(int)blocks, 256, 0, stream>>>(x, hi, lo, scale, n);
-    I2V_CHECK_CUDA(cudaGetLastError());
+    I2V_CHECK_CUDA(launch_k(split_fp16_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, x, hi, lo, scale, n));
     return 0;
 }
 
@@ -922,14 +981,19 @@ static int launch_conv_tc_halo(const ConvTcArgs& h, cudaStream_t stream) {
             wstack = false;                                          // stacked form does not fit: plain halo form
         }
         nw = wstack ? 3 : 1;
-        for (int cand : {64, 32, 16}) {
-            if (h.Cin % cand) continue;
-            const size_t rb = (size_t)cand * 2;
-            if ((nw * a.n_tile * rb) % 1024 != 0) continue;
-            const size_t a_bytes = ((size_t)a.bw * (a.bh2 + 2) * rb + 1023) & ~(size_t)1023;
-            const size_t sb = mult * (a_bytes + 3 * nw * a.n_tile * rb);
-            const int st = (int)((220 * 1024 - 2048) / sb);
-            if (st >= 2) { kc = cand; stages = st > 6 ? 6 : st; stage_bytes = sb; break; }
+        // the widest chunk that still leaves `want` stages in flight (the main loop is bound by L2 latency +
+        // transfer per stage against the MMAs of the stages behind it); two stages as the last resort
+        for (int want : {tc_min_stages(), 2}) {
+            for (int cand : {64, 32, 16}) {
+                if (h.Cin % cand) continue;
+                const size_t rb = (size_t)cand * 2;
+                if ((nw * a.n_tile * rb) % 1024 != 0) continue;
+                const size_t a_bytes = ((size_t)a.bw * (a.bh2 + 2) * rb + 1023) & ~(size_t)1023;
+                const size_t sb = mult * (a_bytes + 3 * nw * a.n_tile * rb);
+                const int st = (int)((220 * 1024 - 2048) / sb);
+                if (st >= want) { kc = cand; stages = st > 6 ? 6 : st; stage_bytes = sb; break; }
+            }
+            if (kc != 0) break;
         }
     }
     I2V_REQUIRE(h.variant != 3 || (wstack && kc != 0), "conv_tc: shape not eligible for the kw-stacked halo kernel");
@@ -971,6 +1035,7 @@ static int launch_conv_tc_halo(const ConvTcArgs& h, cudaStream_t stream) {
     a.nacc = (h.terms > 1 && !shared_acc) ? 2 * nmain : nmain;
     nacc = a.nacc;
     a.t_phase = h.t_phase ? 1 : 0;
+    a.flags = tc_flags();
     a.bias = h.bias; a.res = h.res; a.scale_ptr = h.scale_ptr; a.y = h.y; a.stats = h.stats;
     I2V_REQUIRE(h.stats == nullptr || (h.out_mode == 0 && a.n_tile <= 256), "conv_tc: fused statistics need channels-last output");
     a.B = h.B; a.T = h.T; a.H = h.H; a.W = h.W; a.Cin = h.Cin; a.Cout = h.Cout; a.kt = kt_eff; a.kw = h.kw;
@@ -1025,8 +1090,7 @@ static int launch_conv_tc_halo(const ConvTcArgs& h, cudaStream_t stream) {
         const bool last = a.cc_hi == cch;
         if (p > 0) { a.bias = nullptr; a.res = h.y; a.res_ut = a.res_uh = a.res_uw = 1; }
         a.stats = last ? h.stats : nullptr;
-        conv_tc_halo_kernel<<<grid, TC_THREADS, smem, stream>>>(mAh, mAl, mBh, mBl, a);
-        I2V_CHECK_CUDA(cudaGetLastError());
+        I2V_CHECK_CUDA(launch_k(conv_tc_halo_kernel, grid, dim3(TC_THREADS), smem, stream, mAh, mAl, mBh, mBl, a));
     }
     return 0;
 }
@@ -1137,8 +1201,7 @@ int launch_conv_tc(const ConvTcArgs& h, cudaStream_t stream) {
         const bool last = a.cc_hi == cch1;
         if (p > 0) { a.bias = nullptr; a.res = h.y; a.res_ut = a.res_uh = a.res_uw = 1; }
         a.stats = last ? h.stats : nullptr;
-        conv_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(mAh, mAl, mBh, mBl, a);
-        I2V_CHECK_CUDA(cudaGetLastError());
+        I2V_CHECK_CUDA(launch_k(conv_tc_kernel, grid, dim3(TC_THREADS), smem, stream, mAh, mAl, mBh, mBl, a));
     }
     return 0;
 }

@@ -13,6 +13,8 @@ namespace {
 __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                      const float* __restrict__ bias, float* __restrict__ y, int B,
                                                      int K, int N, int act) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= N) return;
     const int K4 = K >> 2;
@@ -43,6 +45,8 @@ __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x
 
 __global__ void resize_bilinear_kernel(const float* __restrict__ img, float* __restrict__ out, int B, int C, int H0,
                                        int W0, int H, int W, float sh, float sw) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long n = (long long)B * H * W * C;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(i % C);
@@ -65,6 +69,8 @@ __global__ void resize_bilinear_kernel(const float* __restrict__ img, float* __r
 
 __global__ void maxpool3x3s2_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C,
                                     int Ho, int Wo) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int C4 = C >> 2;
     const long long n = (long long)B * Ho * Wo * C4;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -94,8 +100,7 @@ int launch_linear(const float* x, const float* w, const float* bias, float* y, i
                   cudaStream_t stream) {
     I2V_REQUIRE(K % 4 == 0, "linear: K=%d must be a multiple of 4", K);
     ProfScope ps(PROF_OTHER, 2.0 * (double)B * K * N, 4.0 * ((double)K * N + (double)B * (K + N)), stream);
-    linear_kernel<<<ceil_div((long long)N * 32, 256), 256, 0, stream>>>(x, w, bias, y, B, K, N, act);
-    I2V_CHECK_CUDA(cudaGetLastError());
+    I2V_CHECK_CUDA(launch_k(linear_kernel, dim3(ceil_div((long long)N * 32, 256)), dim3(256), 0, stream, x, w, bias, y, B, K, N, act));
     return 0;
 }
 
@@ -107,8 +112,7 @@ int launch_resize_bilinear_nchw_to_nhwc(const float* img, float* out, int B, int
     long long blocks = (n + 255) / 256;
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
     ProfScope ps(PROF_OTHER, 0, 0, stream);
-    resize_bilinear_kernel<<<(int)blocks, 256, 0, stream>>>(img, out, B, C, H0, W0, H, W, sh, sw);
-    I2V_CHECK_CUDA(cudaGetLastError());
+    I2V_CHECK_CUDA(launch_k(resize_bilinear_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, img, out, B, C, H0, W0, H, W, sh, sw));
     return 0;
 }
 
@@ -119,8 +123,7 @@ int launch_maxpool3x3s2(const float* x, float* y, int B, int H, int W, int C, cu
     long long blocks = (n + 255) / 256;
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
     ProfScope ps(PROF_OTHER, 0, 0, stream);
-    maxpool3x3s2_kernel<<<(int)blocks, 256, 0, stream>>>(x, y, B, H, W, C, Ho, Wo);
-    I2V_CHECK_CUDA(cudaGetLastError());
+    I2V_CHECK_CUDA(launch_k(maxpool3x3s2_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, x, y, B, H, W, C, Ho, Wo));
     return 0;
 }
 

@@ -24,6 +24,8 @@ __global__ void __launch_bounds__(STATS_THREADS) channel_stats_kernel(const floa
                                                                       double* __restrict__ sums, long long V,
                                                                       int C, int lanes_c, int rows) {
     extern __shared__ double sh[];   // [C][2]
+    pdl_launch_dependents();
+    pdl_wait();
     const int b = blockIdx.y;
     const int C4 = C >> 2;
     for (int i = threadIdx.x; i < 2 * C; i += STATS_THREADS) sh[i] = 0.0;
@@ -65,6 +67,8 @@ __global__ void norm_coeffs_kernel(const double* __restrict__ sums, float* __res
                                    double count_per_channel, int groups, float eps,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    const float* __restrict__ mod) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= B * C) return;
     const int b = idx / C, c = idx - b * C;
@@ -93,6 +97,8 @@ __global__ void norm_coeffs_kernel(const double* __restrict__ sums, float* __res
 }
 
 __global__ void __launch_bounds__(256) modulate_kernel(const ModArgs a, long long total4) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int C4 = a.C >> 2;
     const int Ts = a.T / a.ut, Hs = a.H / a.uh, Ws = a.W / a.uw;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4;
@@ -151,6 +157,8 @@ __global__ void __launch_bounds__(256) modulate_kernel(const ModArgs a, long lon
 // words), one (b, t) plane per blockIdx.y, shift/mask index decode (W and C/8 are powers of two in the decoder).
 // No second branch, output always the fp16 split.
 __global__ void __launch_bounds__(256) modulate8_split_kernel(const ModArgs a, int c8_shift, int w_shift) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int C8 = a.C >> 3;
     const int plane = blockIdx.y;                 // b * T + t
     const int b = plane / a.T, t = plane - b * a.T;
@@ -196,6 +204,8 @@ __global__ void __launch_bounds__(256) modulate8_split_kernel(const ModArgs a, i
 }
 
 __global__ void mean_from_sums_kernel(const double* __restrict__ sums, float* __restrict__ y, int n, double inv) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] = (float)(sums[2 * (long long)i] * inv);
 }
@@ -211,8 +221,7 @@ int launch_channel_stats(const float* x, double* sums, int B, long long V, int C
     const long long chunk = (long long)rows * STATS_ELEMS_PER_THREAD;
     ProfScope ps(PROF_STATS, 3.0 * (double)B * V * C, 4.0 * (double)B * V * C, stream);
     dim3 grid(ceil_div(V, chunk), B);
-    channel_stats_kernel<<<grid, STATS_THREADS, sizeof(double) * 2 * C, stream>>>(x, sums, V, C, lanes_c, rows);
-    I2V_CHECK_CUDA(cudaGetLastError());
+    I2V_CHECK_CUDA(launch_k(channel_stats_kernel, grid, dim3(STATS_THREADS), sizeof(double) * 2 * C, stream, x, sums, V, C, lanes_c, rows));
     return 0;
 }
 
@@ -222,8 +231,7 @@ int launch_norm_coeffs(const double* sums, float* coef, int B, int C, long long 
     I2V_REQUIRE((gamma == nullptr) == (beta == nullptr), "norm_coeffs: gamma and beta go together");
     const int n = B * C;
     ProfScope ps(PROF_OTHER, 0, 0, stream);
-    norm_coeffs_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(sums, coef, B, C, (double)V, groups, eps, gamma, beta, mod);
-    I2V_CHECK_CUDA(cudaGetLastError());
+    I2V_CHECK_CUDA(launch_k(norm_coeffs_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, stream, sums, coef, B, C, (double)V, groups, eps, gamma, beta, mod));
     return 0;
 }
 
@@ -241,8 +249,7 @@ int launch_modulate(const ModArgs& a, cudaStream_t stream) {
         if (bx > cap) bx = cap < 1 ? 1 : cap;
         const double tot = (double)planes * per_plane * 8;
         ProfScope ps(PROF_MODULATE, 4.0 * tot, 4.0 * (tot + tot / ((double)a.ut * a.uh * a.uw)) + (a.gb ? 8.0 * tot / a.T : 0.0), stream);
-        modulate8_split_kernel<<<dim3(bx, planes), 256, 0, stream>>>(a, ilog2(a.C / 8), ilog2(a.W));
-        I2V_CHECK_CUDA(cudaGetLastError());
+        I2V_CHECK_CUDA(launch_k(modulate8_split_kernel, dim3(bx, planes), dim3(256), 0, stream, a, ilog2(a.C / 8), ilog2(a.W)));
         return 0;
     }
     const long long total4 = (long long)a.B * a.T * a.H * a.W * (a.C / 4);
@@ -251,16 +258,14 @@ int launch_modulate(const ModArgs& a, cudaStream_t stream) {
     if (blocks > cap) blocks = cap;
     ProfScope ps(PROF_MODULATE, 4.0 * (double)total4 * 4,
                  4.0 * 4 * ((double)total4 * (1.0 + (a.r ? 1.0 : 0.0)) + (double)total4 / ((double)a.ut * a.uh * a.uw)), stream);
-    modulate_kernel<<<(int)blocks, 256, 0, stream>>>(a, total4);
-    I2V_CHECK_CUDA(cudaGetLastError());
+    I2V_CHECK_CUDA(launch_k(modulate_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, a, total4));
     return 0;
 }
 
 int launch_mean_from_sums(const double* sums, float* y, int B, int C, long long V, cudaStream_t stream) {
     const int n = B * C;
     ProfScope ps(PROF_OTHER, 0, 0, stream);
-    mean_from_sums_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(sums, y, n, 1.0 / (double)V);
-    I2V_CHECK_CUDA(cudaGetLastError());
+    I2V_CHECK_CUDA(launch_k(mean_from_sums_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, stream, sums, y, n, 1.0 / (double)V));
     return 0;
 }
 

@@ -201,9 +201,8 @@ def decoder_forward(sd, img, z, upsample_s, upsample_t, trace=None):
 
 
 # ---------------------------------------------------------------------------------- 3-D encoder
-def encoder3d_mu(sd, x, stride_s, stride_t, layers=(2, 2, 2, 2)):
-    """Encoder.forward (resnet3D.py:208-219) on (B, 3, T, H, W); returns mu only -- the sample and
-    logvar are not consumed by the transfer path (get_model.py:87)."""
+def _encoder3d_trunk(sd, x, stride_s, stride_t, layers=(2, 2, 2, 2)):
+    """conv1 -> GN -> ReLU -> 4 stages x 2 BasicBlocks -> squeeze(T)  (resnet3D.py:208-219, :101-135)."""
     if x.shape[1] > x.shape[2]:
         x = x.transpose(1, 2)
     h = F.conv3d(x, sd["conv1.weight"], None, (2, 2, 2), (1, 3, 3))
@@ -221,8 +220,30 @@ def encoder3d_mu(sd, x, stride_s, stride_t, layers=(2, 2, 2, 2)):
                 res = F.conv3d(h, sd[p + "downsample.0.weight"], None, st, 1)
                 res = F.group_norm(res, 16, sd[p + "downsample.1.weight"], sd[p + "downsample.1.bias"], 1e-5)
             h = F.relu(o + res)
-    h = h.squeeze(2)
+    return h.squeeze(2)
+
+
+def encoder3d_mu(sd, x, stride_s, stride_t, layers=(2, 2, 2, 2)):
+    """Encoder.forward (resnet3D.py:208-219) on (B, 3, T, H, W); returns mu only -- the sample and
+    logvar are not consumed by the transfer path (get_model.py:87)."""
+    h = _encoder3d_trunk(sd, x, stride_s, stride_t, layers)
     return F.conv2d(h, sd["conv_mu.weight"], sd["conv_mu.bias"]).reshape(h.shape[0], -1)
+
+
+def encoder3d_posterior(sd, x, stride_s, stride_t, layers=(2, 2, 2, 2)):
+    """Encoder.forward with its reparameterisation (resnet3D.py:202-206): (mu + exp(logvar/2) * eps, mu, logvar),
+    eps drawn from the CPU generator exactly like ``torch.FloatTensor(size).normal_()`` does."""
+    h = _encoder3d_trunk(sd, x, stride_s, stride_t, layers)
+    mu = F.conv2d(h, sd["conv_mu.weight"], sd["conv_mu.bias"]).reshape(h.shape[0], -1)
+    logvar = F.conv2d(h, sd["conv_var.weight"], sd["conv_var.bias"]).reshape(h.shape[0], -1)
+    eps = torch.FloatTensor(logvar.size()).normal_()
+    return eps.mul(logvar.mul(0.5).exp()).add(mu), mu, logvar
+
+
+def flow_nll(gauss, logdet):
+    """FlowLoss.forward (stage2_cINN/modules/loss.py:9-28) without logging: mean(0.5*|gauss|^2) - mean(logdet)."""
+    g = gauss.reshape(gauss.shape[0], -1)
+    return torch.mean(0.5 * torch.sum(g * g, dim=1)) - torch.mean(logdet)
 
 
 # -------------------------------------------------------------------------------------- facade
@@ -291,3 +312,20 @@ class OracleModel:
         z = flow_reverse(self.flow, res, self.embed(x_0), self.n_flows, self.control, self.depth)
         seq = self._extend(x_0, z)
         return (seq, z, mu, res, logdet) if return_latent else seq
+
+    @torch.no_grad()
+    def validation_step(self, seq, cond=None):
+        """stage2_cINN/main.py:55-63: posterior sample -> forward flow on the first frame -> NLL.
+        Returns (loss, gauss, logdet, post)."""
+        e = self.c1["Encoder"]
+        post, mu, logvar = encoder3d_posterior(self.enc, seq[:, 1:].transpose(1, 2), e["stride_s"], e["stride_t"])
+        gauss, logdet = flow_forward(self.flow, post.reshape(post.shape[0], -1), self.embed(seq[:, 0], cond), self.n_flows,
+                                     self.control, self.depth)
+        return flow_nll(gauss, logdet), gauss, logdet, post
+
+    @torch.no_grad()
+    def reconstruct(self, seq):
+        """utils/auxiliaries.py:73-75: decoder(seq[:, 0], Encoder(seq[:, 1:]).sample)."""
+        e = self.c1["Encoder"]
+        post, _, _ = encoder3d_posterior(self.enc, seq[:, 1:].transpose(1, 2), e["stride_s"], e["stride_t"])
+        return self.decode(seq[:, 0], post)

@@ -131,3 +131,24 @@ def run_reference_forward(model, x_0, seed: int, cond=None):
 def run_reference_transfer(model, seq_query, x_0):
     with cpu_cuda_identity(), torch.no_grad():
         return model.transfer(seq_query, x_0)
+
+
+def run_reference_validation_step(model, seq, seed: int):
+    """The stage-2 validator's loop body (stage2_cINN/main.py:55-63) on the reference's own modules, with the
+    reference's FlowLoss arithmetic (stage2_cINN/modules/loss.py:9-28; the wandb logging is not part of the value).
+    Returns (loss, gauss, logdet, post)."""
+    with cpu_cuda_identity(), torch.no_grad():
+        torch.manual_seed(seed)
+        post, mean, *_ = model.encoder(seq[:, 1:].transpose(1, 2))
+        gauss, logdet = model.flow(post.reshape(post.size(0), -1).detach(), [seq[:, 0]])
+        nll = 0.5 * torch.sum(torch.pow(gauss, 2), dim=[1, 2, 3])
+        loss = torch.mean(nll) - torch.mean(logdet)
+        return loss, gauss, logdet, post
+
+
+def run_reference_reconstruction(model, seq, seed: int):
+    """evaluate_FVD_posterior's loop body (utils/auxiliaries.py:73-75) on the reference's own modules."""
+    with cpu_cuda_identity(), torch.no_grad():
+        torch.manual_seed(seed)
+        motion, *_ = model.encoder(seq[:, 1:].transpose(1, 2))
+        return model.decoder(seq[:, 0], motion)

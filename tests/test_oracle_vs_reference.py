@@ -29,6 +29,23 @@ def test_full_model_matches_reference(dataset, kw, ckpt_cache):
     assert rel_inf(om.transfer(q, x0), rh.run_reference_transfer(ref, q, x0)) < 1e-6
 
 
+def test_validation_step_and_reconstruction_match_reference(ckpt_cache):
+    """posterior sample (CPU-RNG eps) -> forward flow -> NLL, and the stage-1 reconstruction."""
+    mp = ckpt_cache(dataset="bair", seed=3, nf=16, n_flows=3, enc_channels=[64, 32, 32, 64, 64], spade_gain=1.0)
+    ref = rh.build_reference_model(mp, 16, transfer=True)
+    om = ot.OracleModel(mp, 16, transfer=True)
+    img = om.opt["Data"]["img_size"]
+    seq = torch.rand(2, 16, 3, img, img, generator=torch.Generator().manual_seed(11)) * 2 - 1
+    w_loss, w_gauss, w_logdet, w_post = rh.run_reference_validation_step(ref, seq, seed=21)
+    torch.manual_seed(21)
+    loss, gauss, logdet, post = om.validation_step(seq)
+    assert rel_inf(post, w_post) < 1e-6 and rel_inf(gauss.reshape(2, -1), w_gauss.reshape(2, -1)) < 1e-6
+    assert rel_inf(logdet, w_logdet) < 1e-6 and abs(loss.item() - w_loss.item()) < 1e-5 * abs(w_loss.item())
+    want = rh.run_reference_reconstruction(ref, seq, seed=22)
+    torch.manual_seed(22)
+    assert rel_inf(om.reconstruct(seq), want) < 1e-6
+
+
 def test_synthetic_layout_matches_reference_constructors(ckpt_cache):
     """Key set, shapes and dtypes of every synthetic state-dict equal the reference constructors'
     (full-size BAIR geometry, flow with control to cover the 'cond' blocks)."""
