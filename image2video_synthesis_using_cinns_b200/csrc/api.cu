@@ -458,7 +458,8 @@ static int decoder_run(const i2v_decoder* m, const float* img, const float* z, f
     // Tensor-core conv on split fp16 operands: x lives in `xbuf` as (hi | lo) halves of n_in elements each.
     auto conv_tc = [&](const std::string& wname, const float* xbuf, size_t n_in, const float* bias, const float* res, float* y,
                        int Bc, int Tc, int Hc_, int Wc_, int cin_, int cout_, int kt, int kh, int kw, int rut, int ruh, int ruw,
-                       int act, int out_mode, double* stats_out = nullptr, int t_phase = 0) -> int {
+                       int act, int out_mode, double* stats_out = nullptr, int t_phase = 0, const float* x2buf = nullptr,
+                       size_t n_in2 = 0, int cin2 = 0) -> int {
         const int cpad = (cout_ + 15) / 16 * 16;
         const size_t wn = (size_t)(t_phase ? 4 : kt) * kh * kw * cpad * cin_;
         const __half* wh = m->tt.get<__half>(wname + (t_phase ? ".wph" : ".wh"), wn);
@@ -473,6 +474,14 @@ static int decoder_run(const i2v_decoder* m, const float* img, const float* z, f
         a.terms = eng == 1 ? 3 : 1;
         a.stats = stats_out;
         a.t_phase = t_phase;
+        if (x2buf != nullptr) {      // fused learned shortcut: <conv>x holds conv_s as a kw-stacked centre-tap slab
+            const size_t w2n = (size_t)3 * cpad * cin2;
+            const __half* w2h = m->tt.get<__half>(wname + "x.wh", w2n);
+            const __half* w2l = m->tt.get<__half>(wname + "x.wl", w2n);
+            if (!w2h || !w2l) return -3;
+            a.x2_hi = reinterpret_cast<const __half*>(x2buf); a.x2_lo = a.x2_hi + n_in2;
+            a.w2_hi = w2h; a.w2_lo = w2l; a.Cin2 = cin2;
+        }
         if (stats_out) I2V_CHECK_CUDA(cudaMemsetAsync(stats_out, 0, sizeof(double) * 2 * (size_t)Bc * cout_, s));
         return launch_conv_tc(a, s);
     };
@@ -542,12 +551,18 @@ static int decoder_run(const i2v_decoder* m, const float* img, const float* z, f
         I2V_TRY(modulate_to(x, coef, gb, bufp, n_a0, B, Ta, Hc, Wc, cin, phase ? 1 : k.ut, k.uh, k.uw, ACT_LRELU02));
         // shortcut at low resolution
         const float* xs = x;
+        // a block that keeps the resolution runs its learned shortcut inside conv_1 (side input through the centre tap)
+        static const bool no_fuse_s = getenv("I2V_NO_FUSE_S") != nullptr;      // A/B switch (tuning aid)
+        const bool fuse_s = !no_fuse_s && tc && cin != cout && k.ut == 1 && k.uh == 1 && k.uw == 1 && m->tt.has(nm + ".conv_1x.wh") &&
+                            conv_tc_side_eligible(Hc, Wc, cmid, cin, (cout + 15) / 16 * 16, eng == 1 ? 3 : 1);
         if (cin != cout) {
             I2V_PTR(nsw, G(nm + ".norm_s.w", cin));
             I2V_PTR(nsb, G(nm + ".norm_s.b", cin));
             I2V_TRY(launch_norm_coeffs(sums, coefs, B, cin, vlow, 16, 1e-5f, nsw, nsb, nullptr, s));
             I2V_TRY(modulate_to(x, coefs, nullptr, lowin, (size_t)B * vlow * cin, B, Tl, Hl, Wl, cin, 1, 1, 1, ACT_NONE));
-            if (!tc) {
+            if (fuse_s) {
+                xs = nullptr;                                     // conv_1 below takes lowin as its side input
+            } else if (!tc) {
                 I2V_PTR(csw, G(nm + ".conv_s.w", (size_t)cout * cin));
                 I2V_TRY(conv(0, lowin, csw, nullptr, nullptr, lowout, B, Tl, Hl, Wl, cin, cout, 1, 1, 1, 1, 1, 1, 0, 0, 0, 1, 1, 1,
                              ACT_NONE, 0, s));
@@ -555,7 +570,7 @@ static int decoder_run(const i2v_decoder* m, const float* img, const float* z, f
                 I2V_TRY(conv_tc(nm + ".conv_s", lowin, (size_t)B * vlow * cin, nullptr, nullptr, lowout, B, Tl, Hl, Wl, cin, cout, 1, 1, 1,
                                 1, 1, 1, ACT_NONE, 0));
             }
-            xs = lowout;
+            if (!fuse_s) xs = lowout;
         }
         // dx = conv_0(a0)
         I2V_PTR(b0, G(nm + ".conv_0.b", cmid));
@@ -582,7 +597,8 @@ static int decoder_run(const i2v_decoder* m, const float* img, const float* z, f
             // the next block normalises this output: its statistics ride in the epilogue (not needed after g_4)
             const bool fuse_out = fuse && i < 5;
             I2V_TRY(conv_tc(nm + ".conv_1", bufp, (size_t)B * vhi * cmid, b1, xs, xn, B, T, Hc, Wc, cmid, cout, 3, 3, 3, k.ut, k.uh, k.uw,
-                            ACT_NONE, 0, fuse_out ? sums_next : nullptr));
+                            ACT_NONE, 0, fuse_out ? sums_next : nullptr, 0, fuse_s ? lowin : nullptr, (size_t)B * vlow * cin,
+                            fuse_s ? cin : 0));
             have_in_stats = fuse_out;
         }
         if (have_in_stats) { double* tsw = sums; sums = sums_next; sums_next = tsw; }
@@ -778,6 +794,33 @@ int i2v_op_conv_tc(const float* x, const float* w, const float* bias, const floa
     a.res_ut = rut; a.res_uh = ruh; a.res_uw = ruw; a.act = act; a.out_mode = out_mode; a.terms = terms; a.variant = variant;
     return launch_conv_tc(a, s);
 }
+int i2v_op_conv_tc_side(const float* x, const float* w, const float* x2, const float* w2, const float* bias, float* y, int B, int T,
+                        int H, int W, int Cin, int Cin2, int Cout, int cout_pad, int act, int out_mode, int terms, int variant,
+                        float scale_a, float scale_w, void* ws, size_t ws_bytes, void* stream) {
+    I2V_REQUIRE(x && w && x2 && w2 && y && ws, "op_conv_tc_side: null argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t nx = (size_t)B * T * H * W * Cin, nw = (size_t)27 * cout_pad * Cin;
+    const size_t nx2 = (size_t)B * T * H * W * Cin2, nw2 = (size_t)3 * cout_pad * Cin2;
+    Arena ar(ws, ws_bytes, false);
+    __half* xh = ar.take<__half>(nx); __half* xl = ar.take<__half>(nx);
+    __half* wh = ar.take<__half>(nw); __half* wl = ar.take<__half>(nw);
+    __half* x2h = ar.take<__half>(2 * nx2);                       // (hi | lo) halves back to back, like the decoder's buffers
+    __half* w2h = ar.take<__half>(nw2); __half* w2l = ar.take<__half>(nw2);
+    float* sc = ar.take<float>(1);
+    I2V_REQUIRE(ar.ok(), "op_conv_tc_side: workspace too small (%zu needed)", ar.peak);
+    I2V_TRY(launch_split_fp16(x, xh, xl, scale_a, (long long)nx, s));
+    I2V_TRY(launch_split_fp16(w, wh, wl, scale_w, (long long)nw, s));
+    I2V_TRY(launch_split_fp16(x2, x2h, x2h + nx2, scale_a, (long long)nx2, s));
+    I2V_TRY(launch_split_fp16(w2, w2h, w2l, scale_w, (long long)nw2, s));
+    const float inv = 1.f / (scale_a * scale_w);
+    I2V_CHECK_CUDA(cudaMemcpyAsync(sc, &inv, sizeof(float), cudaMemcpyHostToDevice, s));
+    ConvTcArgs a;
+    a.x_hi = xh; a.x_lo = xl; a.w_hi = wh; a.w_lo = wl; a.scale_ptr = sc; a.bias = bias; a.res = nullptr; a.y = y;
+    a.B = B; a.T = T; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.cout_pad = cout_pad; a.kt = 3; a.kh = 3; a.kw = 3;
+    a.res_ut = a.res_uh = a.res_uw = 1; a.act = act; a.out_mode = out_mode; a.terms = terms; a.variant = variant;
+    a.x2_hi = x2h; a.x2_lo = x2h + nx2; a.w2_hi = w2h; a.w2_lo = w2l; a.Cin2 = Cin2;
+    return launch_conv_tc(a, s);
+}
 int i2v_debug_flow_timestamps(void* buf) { return flow_set_debug(static_cast<unsigned long long*>(buf)); }
 int i2v_debug_conv_tc_timestamps(void* buf, int ctas) { return conv_tc_set_debug(static_cast<unsigned long long*>(buf), ctas); }
 int i2v_op_channel_stats(const float* x, double* sums, int B, int64_t V, int C, void* stream) {
@@ -790,6 +833,15 @@ int i2v_op_norm_coeffs(const double* sums, float* coef, int B, int C, int64_t V,
 int i2v_op_modulate(const float* x, const float* coef, const float* gb, const float* r, const float* coef2, float* out, int B,
                     int T, int H, int W, int C, int ut, int uh, int uw, int act, void* stream) {
     return modulate(x, coef, gb, r, coef2, out, B, T, H, W, C, ut, uh, uw, act, static_cast<cudaStream_t>(stream));
+}
+int i2v_op_modulate_split(const float* x, const float* coef, const float* gb, void* out_hi, void* out_lo, int B, int T, int H, int W,
+                          int C, int ut, int uh, int uw, int act, float split_scale, void* stream) {
+    I2V_REQUIRE(x && out_hi && out_lo, "op_modulate_split: null argument");
+    ModArgs m;
+    m.x = x; m.coef = coef; m.gb = gb; m.r = nullptr; m.coef2 = nullptr; m.out = nullptr;
+    m.B = B; m.T = T; m.H = H; m.W = W; m.C = C; m.ut = ut; m.uh = uh; m.uw = uw; m.act = act;
+    m.out_hi = static_cast<__half*>(out_hi); m.out_lo = static_cast<__half*>(out_lo); m.split_scale = split_scale;
+    return launch_modulate(m, static_cast<cudaStream_t>(stream));
 }
 int i2v_op_linear(const float* x, const float* w, const float* bias, float* y, int B, int K, int N, int act, void* stream) {
     return launch_linear(x, w, bias, y, B, K, N, act, static_cast<cudaStream_t>(stream));

@@ -558,11 +558,19 @@ struct ConvTcHArgs {
     int res_ut, res_uh, res_uw, act, out_mode;
     int cc_lo, cc_hi;             // channel-chunk range [cc_lo, cc_hi) of this launch (K split across launches)
     int flags;                    // bit 0: epilogue warps prefetch their residual rows into L2 while the main loop runs
+    // Side input (K extension): `cc2` extra channel chunks of a SECOND activation tensor (same voxel grid) enter through
+    // the centre tap only -- a fused 1x1x1 convolution.  This is the GeneratorBlock's learned shortcut
+    // conv_s(Norm3D(x)) (decoder.py:44-50) in the blocks that do not upsample: out = conv_1(a1) + conv_s(x_n) is ONE
+    // implicit GEMM over K = 27 C_mid + C_in, so the separate shortcut launch, its output tensor and the residual read
+    // of this epilogue disappear.  Maps mA2*/mB2* ; weights [kw=3][cout_pad][Cin2] with only the kw = 1 slab non-zero.
+    int cc2;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
-                    const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl, const ConvTcHArgs a) {
+                    const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl,
+                    const __grid_constant__ CUtensorMap mA2h, const __grid_constant__ CUtensorMap mA2l,
+                    const __grid_constant__ CUtensorMap mB2h, const __grid_constant__ CUtensorMap mB2l, const ConvTcHArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t rb = (uint32_t)a.kc * 2;
@@ -598,6 +606,10 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&mAh); ptx::prefetch_tensormap(&mBh);
         if (a.terms > 1) { ptx::prefetch_tensormap(&mAl); ptx::prefetch_tensormap(&mBl); }
+        if (a.cc2 > 0) {
+            ptx::prefetch_tensormap(&mA2h); ptx::prefetch_tensormap(&mB2h);
+            if (a.terms > 1) { ptx::prefetch_tensormap(&mA2l); ptx::prefetch_tensormap(&mB2l); }
+        }
     }
     if (warp == 1) {
         if (lane == 0) {
@@ -633,7 +645,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
     const int dt_lo = ct_base < 0 ? -ct_base : 0;
     const int dt_hi = (Tin - 1 - ct_base) < (a.kt - 1) ? (Tin - 1 - ct_base) : (a.kt - 1);
     const int kw_iter = a.wstack ? 1 : a.kw;                      // stacked: one unshifted load covers all kw taps
-    const int n_total = (dt_hi - dt_lo + 1) * kw_iter * cchunks;  // pipeline stages this CTA runs
+    const int n_main = (dt_hi - dt_lo + 1) * kw_iter * cchunks;   // pipeline stages of the 3x3(x3) taps
+    const int n_total = n_main + a.cc2;                           // ... plus the side-input chunks (centre tap only)
     (void)iters;
 
     if (warp == 0) {
@@ -655,6 +668,24 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
                     if (a.terms > 1) {
                         ptx::tma_load_5d(st + off_alo, &mAl, full + s, c0, cw, ch, ct, b);
                         ptx::tma_load_5d(st + off_blo, &mBl, full + s, c0, n0, dw, 0, wt);
+                    }
+                }
+                __syncwarp();
+                if (++s == a.stages) { s = 0; ph ^= 1u; }
+            }
+            // side input: same box (the halo rows ride along unused), one weight slab [nw][n_tile][kc] per chunk
+            const uint32_t tx2 = (a.terms > 1 ? 2u : 1u) * (a_rows * rb + b_tap);
+            for (int cc = 0; cc < a.cc2; ++cc) {
+                const int c0 = cc * a.kc;
+                ptx::mbar_wait(empty + s, ph ^ 1u);
+                uint8_t* st = smem + (size_t)s * stage_bytes;
+                if (ptx::elect_one()) {
+                    ptx::mbar_expect_tx(full + s, tx2);
+                    ptx::tma_load_5d(st, &mA2h, full + s, c0, w0, h0 - 1, t, b);
+                    ptx::tma_load_5d(st + off_bhi, &mB2h, full + s, c0, n0, a.wstack ? 0 : 1, 0, 0);
+                    if (a.terms > 1) {
+                        ptx::tma_load_5d(st + off_alo, &mA2l, full + s, c0, w0, h0 - 1, t, b);
+                        ptx::tma_load_5d(st + off_blo, &mB2l, full + s, c0, n0, a.wstack ? 0 : 1, 0, 0);
                     }
                 }
                 __syncwarp();
@@ -688,10 +719,12 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
                 const uint32_t tsm0 = nsmall > 0 ? tmem_base + (uint32_t)((a.nmain + asm_) * accw) : tacc0;
                 const uint32_t tsm1 = tsm0 + (uint32_t)(a.nacc * accw);
                 uint32_t acc_flag = fresh;
+                const bool ext = n >= n_main;                    // side-input stage: centre row only, weight slab 0
                 if (ptx::elect_one()) {
 #pragma unroll
                 for (int kh = 0; kh < 3; ++kh) {
-                    const uint32_t ao = (uint32_t)kh * kh_step, bo = (uint32_t)kh * (b_tap >> 4);
+                    if (ext && kh != 1) continue;
+                    const uint32_t ao = (uint32_t)kh * kh_step, bo = ext ? 0u : (uint32_t)kh * (b_tap >> 4);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         if (k < ksteps) {
@@ -954,25 +987,22 @@ int launch_split_fp16(const float* x, __half* hi, __half* lo, float scale, long 
     return 0;
 }
 
-// v2 eligibility + launch.  Returns 1 if the shape is not eligible (caller falls through to v1).
-static int launch_conv_tc_halo(const ConvTcArgs& h, cudaStream_t stream) {
-    if (h.kh != 3 || h.W < 16 || h.H * h.W < 256) return 1;
-    I2V_REQUIRE(!h.t_phase || (h.kt == 3 && h.T % 2 == 0), "conv_tc: t_phase needs a 3-tap temporal kernel and even T");
-    const int kt_eff = h.t_phase ? 2 : h.kt;     // temporal taps actually iterated
-    const int Tin = h.t_phase ? h.T / 2 : h.T;   // planes of the stored activation tensor
-    ConvTcHArgs a;
-    a.bw = h.W < 128 ? h.W : 128;
-    a.bh2 = 256 / a.bw;
-    if (a.bh2 < 2 || h.H % a.bh2 != 0) return 1;
-    const int n_cap = h.terms == 3 ? 128 : 256;
-    a.n_tile = h.cout_pad < n_cap ? h.cout_pad : n_cap;
+// Tile / pipeline configuration of the halo kernel for a layer; false when the shape is not eligible.
+struct HaloCfg { int bw, bh2, n_tile, kc, stages, nw; size_t stage_bytes; bool wstack; };
+static bool halo_config(int H, int W, int Cin, int cout_pad, int kh, int kw, int terms, int variant, HaloCfg& c) {
+    if (kh != 3 || W < 16 || H * W < 256) return false;
+    c.bw = W < 128 ? W : 128;
+    c.bh2 = 256 / c.bw;
+    if (c.bh2 < 2 || H % c.bh2 != 0) return false;
+    const int n_cap = terms == 3 ? 128 : 256;
+    c.n_tile = cout_pad < n_cap ? cout_pad : n_cap;
     // kw-stacked form (variant 0 = automatic, 3 = required, 2 = never): narrow layers (Cout <= 64) stack the three kw
     // taps along the MMA's N (N = 3 Cout <= 192).  One unshifted activation load then feeds 9 taps instead of 3, the
     // MMA count drops 3x, and N >= 48 keeps the tensor pipe off the shared-memory A-read floor that N = 64 MMAs
     // sit on.  Needs whole w-rows per tile (W <= 128) so the +-1 voxel shift never leaves the tile.
-    bool wstack = h.variant != 2 && h.kw == 3 && h.cout_pad <= 64 && h.W == a.bw;
+    bool wstack = variant != 2 && kw == 3 && cout_pad <= 64 && W == c.bw;
     // channel chunk: the largest of 64/32/16 that divides Cin, keeps tap slabs 1024B-aligned and fits >= 2 stages
-    const int mult = h.terms > 1 ? 2 : 1;
+    const int mult = terms > 1 ? 2 : 1;
     int kc = 0, stages = 0, nw = 1;
     size_t stage_bytes = 0;
     for (int attempt = 0; attempt < 2 && kc == 0; ++attempt) {
@@ -981,24 +1011,49 @@ static int launch_conv_tc_halo(const ConvTcArgs& h, cudaStream_t stream) {
             wstack = false;                                          // stacked form does not fit: plain halo form
         }
         nw = wstack ? 3 : 1;
-        // the widest chunk that still leaves `want` stages in flight (the main loop is bound by L2 latency +
-        // transfer per stage against the MMAs of the stages behind it); two stages as the last resort
+        // the widest chunk that still leaves `want` stages in flight; two stages as the last resort (measured: 32-byte
+        // rows just to deepen the pipeline cost 7 % on the g_3 layers, profiles/r01_conv_tc_stage_depth.txt)
         for (int want : {tc_min_stages(), 2}) {
             for (int cand : {64, 32, 16}) {
-                if (h.Cin % cand) continue;
+                if (Cin % cand) continue;
                 const size_t rb = (size_t)cand * 2;
-                if ((nw * a.n_tile * rb) % 1024 != 0) continue;
-                const size_t a_bytes = ((size_t)a.bw * (a.bh2 + 2) * rb + 1023) & ~(size_t)1023;
-                const size_t sb = mult * (a_bytes + 3 * nw * a.n_tile * rb);
+                if ((nw * c.n_tile * rb) % 1024 != 0) continue;
+                const size_t a_bytes = ((size_t)c.bw * (c.bh2 + 2) * rb + 1023) & ~(size_t)1023;
+                const size_t sb = mult * (a_bytes + 3 * nw * c.n_tile * rb);
                 const int st = (int)((220 * 1024 - 2048) / sb);
                 if (st >= want) { kc = cand; stages = st > 6 ? 6 : st; stage_bytes = sb; break; }
             }
             if (kc != 0) break;
         }
     }
-    I2V_REQUIRE(h.variant != 3 || (wstack && kc != 0), "conv_tc: shape not eligible for the kw-stacked halo kernel");
+    c.kc = kc; c.stages = stages; c.nw = nw; c.stage_bytes = stage_bytes; c.wstack = wstack;
+    return kc != 0;
+}
+
+// A 3x3x3 layer can take a fused 1x1x1 side input of Cin2 channels (ConvTcHArgs::cc2) when it runs on the halo kernel
+// and its channel chunk divides Cin2.
+bool conv_tc_side_eligible(int H, int W, int Cin, int Cin2, int cout_pad, int terms) {
+    HaloCfg c;
+    return halo_config(H, W, Cin, cout_pad, 3, 3, terms, 0, c) && Cin2 > 0 && Cin2 % c.kc == 0;
+}
+
+// v2 eligibility + launch.  Returns 1 if the shape is not eligible (caller falls through to v1).
+static int launch_conv_tc_halo(const ConvTcArgs& h, cudaStream_t stream) {
+    HaloCfg cfg{};
+    if (!halo_config(h.H, h.W, h.Cin, h.cout_pad, h.kh, h.kw, h.terms, h.variant, cfg)) {
+        I2V_REQUIRE(h.variant != 3, "conv_tc: shape not eligible for the kw-stacked halo kernel");
+        return 1;
+    }
+    I2V_REQUIRE(h.variant != 3 || cfg.wstack, "conv_tc: shape not eligible for the kw-stacked halo kernel");
+    I2V_REQUIRE(!h.t_phase || (h.kt == 3 && h.T % 2 == 0), "conv_tc: t_phase needs a 3-tap temporal kernel and even T");
+    const int kt_eff = h.t_phase ? 2 : h.kt;     // temporal taps actually iterated
+    const int Tin = h.t_phase ? h.T / 2 : h.T;   // planes of the stored activation tensor
+    ConvTcHArgs a;
+    a.bw = cfg.bw; a.bh2 = cfg.bh2; a.n_tile = cfg.n_tile;
+    const bool wstack = cfg.wstack;
+    const int kc = cfg.kc, stages = cfg.stages, nw = cfg.nw;
+    const size_t stage_bytes = cfg.stage_bytes;
     a.wstack = wstack ? 1 : 0;
-    if (kc == 0) return 1;
     a.kc = kc; a.stages = stages; a.terms = h.terms;
     int nacc = 512 / (2 * nw * a.n_tile);
     if (nacc > 4) nacc = 4;
@@ -1016,14 +1071,19 @@ static int launch_conv_tc_halo(const ConvTcArgs& h, cudaStream_t stream) {
     if (nmain < 1) return 1;                                                   // needs 2 accumulators per sub-tile
     if (nmain > 2) nmain = 2;
     const int main_per_stage = 3 * (kc / 16) * (shared_acc ? 3 : 1);           // chained MMAs per stage and sub-tile
+    // side input: Cin2 / kc extra stages through the centre tap (one kh row each)
+    I2V_REQUIRE(h.Cin2 == 0 || (h.x2_hi && h.w2_hi && h.Cin2 % kc == 0 && !h.t_phase && h.kt == 3 && h.kw == 3),
+                "conv_tc: side input needs a 3x3x3 non-phase conv and Cin2 (%d) divisible by the channel chunk %d", h.Cin2, kc);
+    const int cc2 = h.Cin2 / kc;
     int parts = 1;
     if (h.terms > 1) {
-        const long long chain = (long long)kt_eff * kw_iter * cch * main_per_stage / nmain;
+        const long long chain = ((long long)kt_eff * kw_iter * cch * main_per_stage + (long long)cc2 * (main_per_stage / 3)) / nmain;
         parts = (int)((chain + kMaxChain - 1) / kMaxChain);
         if (parts > cch) parts = cch;
         if (parts < 1) parts = 1;
     }
     I2V_REQUIRE(parts == 1 || h.act == ACT_NONE, "conv_tc: K-split launches need a linear epilogue");
+    I2V_REQUIRE(parts == 1 || cc2 == 0, "conv_tc: a side input cannot be combined with K-split launches");
     const int cper = (cch + parts - 1) / parts;
     {
         // every CTA runs at least kw * (chunks of the smallest part) stages: each accumulator must be written
@@ -1036,6 +1096,7 @@ static int launch_conv_tc_halo(const ConvTcArgs& h, cudaStream_t stream) {
     nacc = a.nacc;
     a.t_phase = h.t_phase ? 1 : 0;
     a.flags = tc_flags();
+    a.cc2 = cc2;
     a.bias = h.bias; a.res = h.res; a.scale_ptr = h.scale_ptr; a.y = h.y; a.stats = h.stats;
     I2V_REQUIRE(h.stats == nullptr || (h.out_mode == 0 && a.n_tile <= 256), "conv_tc: fused statistics need channels-last output");
     a.B = h.B; a.T = h.T; a.H = h.H; a.W = h.W; a.Cin = h.Cin; a.Cout = h.Cout; a.kt = kt_eff; a.kw = h.kw;
@@ -1064,6 +1125,21 @@ static int launch_conv_tc_halo(const ConvTcArgs& h, cudaStream_t stream) {
         if (int rc = encode_map(&mBh, h.w_hi, 5, dims, st, box, rb)) return rc;
         if (int rc = encode_map(&mBl, h.terms > 1 ? h.w_lo : h.w_hi, 5, dims, st, box, rb)) return rc;
     }
+    CUtensorMap mA2h = mAh, mA2l = mAl, mB2h = mBh, mB2l = mBl;     // placeholders when there is no side input
+    if (cc2 > 0) {
+        const cuuint64_t dims[5] = {(cuuint64_t)h.Cin2, (cuuint64_t)h.W, (cuuint64_t)h.H, (cuuint64_t)h.T, (cuuint64_t)h.B};
+        const cuuint64_t st[4] = {(cuuint64_t)h.Cin2 * 2, (cuuint64_t)h.W * h.Cin2 * 2, (cuuint64_t)h.H * h.W * h.Cin2 * 2,
+                                  (cuuint64_t)h.T * h.H * h.W * h.Cin2 * 2};
+        const cuuint32_t box[5] = {(cuuint32_t)kc, (cuuint32_t)a.bw, (cuuint32_t)(a.bh2 + 2), 1, 1};
+        if (int rc = encode_map(&mA2h, h.x2_hi, 5, dims, st, box, rb)) return rc;
+        if (int rc = encode_map(&mA2l, h.terms > 1 ? h.x2_lo : h.x2_hi, 5, dims, st, box, rb)) return rc;
+        const cuuint64_t row = (cuuint64_t)h.cout_pad * h.Cin2 * 2;
+        const cuuint64_t wd[5] = {(cuuint64_t)h.Cin2, (cuuint64_t)h.cout_pad, 3, 1, 1};
+        const cuuint64_t ws_[4] = {(cuuint64_t)h.Cin2 * 2, row, row * 3, row * 3};
+        const cuuint32_t wbox[5] = {(cuuint32_t)kc, (cuuint32_t)a.n_tile, (cuuint32_t)nw, 1, 1};
+        if (int rc = encode_map(&mB2h, h.w2_hi, 5, wd, ws_, wbox, rb)) return rc;
+        if (int rc = encode_map(&mB2l, h.terms > 1 ? h.w2_lo : h.w2_hi, 5, wd, ws_, wbox, rb)) return rc;
+    }
     static bool attr_set = false;
     if (!attr_set) {
         I2V_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1080,8 +1156,9 @@ static int launch_conv_tc_halo(const ConvTcArgs& h, cudaStream_t stream) {
         I2V_REQUIRE(!wstack || (long long)a.tiles_w == 1, "conv_tc: stacked form needs whole rows per tile");
     }
     const long long M = (long long)h.B * h.T * h.H * h.W;
-    const double K_ = (double)h.kt * h.kh * h.kw * h.Cin;
-    ProfScope ps(PROF_CONV, 2.0 * (double)M * h.Cout * K_, 4.0 * ((double)M * h.Cin + (double)M * h.Cout + K_ * h.Cout), stream);
+    const double K_ = (double)h.kt * h.kh * h.kw * h.Cin + (double)h.Cin2;
+    ProfScope ps(PROF_CONV, 2.0 * (double)M * h.Cout * K_,
+                 4.0 * ((double)M * (h.Cin + h.Cin2) + (double)M * h.Cout + K_ * h.Cout), stream);
     dim3 grid((unsigned)((long long)a.tiles_w * a.tiles_h * h.T * h.B), (unsigned)((h.cout_pad + a.n_tile - 1) / a.n_tile));
     for (int p = 0; p < parts; ++p) {
         a.cc_lo = p * cper;
@@ -1090,7 +1167,7 @@ static int launch_conv_tc_halo(const ConvTcArgs& h, cudaStream_t stream) {
         const bool last = a.cc_hi == cch;
         if (p > 0) { a.bias = nullptr; a.res = h.y; a.res_ut = a.res_uh = a.res_uw = 1; }
         a.stats = last ? h.stats : nullptr;
-        I2V_CHECK_CUDA(launch_k(conv_tc_halo_kernel, grid, dim3(TC_THREADS), smem, stream, mAh, mAl, mBh, mBl, a));
+        I2V_CHECK_CUDA(launch_k(conv_tc_halo_kernel, grid, dim3(TC_THREADS), smem, stream, mAh, mAl, mBh, mBl, mA2h, mA2l, mB2h, mB2l, a));
     }
     return 0;
 }
@@ -1108,6 +1185,7 @@ int launch_conv_tc(const ConvTcArgs& h, cudaStream_t stream) {
         I2V_REQUIRE(h.variant != 2, "conv_tc: shape not eligible for the halo kernel");
     }
     I2V_REQUIRE(!h.t_phase, "conv_tc: t_phase is only implemented by the halo kernel (ask conv_tc_halo_eligible first)");
+    I2V_REQUIRE(h.Cin2 == 0, "conv_tc: a side input is only implemented by the halo kernel (ask conv_tc_halo_eligible first)");
     ConvTcKArgs a;
     a.bias = h.bias; a.res = h.res; a.scale_ptr = h.scale_ptr; a.y = h.y; a.stats = h.stats;
     a.B = h.B; a.T = h.T; a.H = h.H; a.W = h.W; a.Cin = h.Cin; a.Cout = h.Cout;

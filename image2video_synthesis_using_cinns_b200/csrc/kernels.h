@@ -41,9 +41,15 @@ struct ConvTcArgs {
     // 1: the logical input is x nearest-upsampled x2 in time; x_hi/x_lo hold it at T/2 planes and w_hi/w_lo hold the
     //    phase-combined weights [2 phases][2 taps][kh][kw][cout_pad][Cin] (halo kernel only)
     int t_phase = 0;
+    // optional side input (fused 1x1x1 conv through the centre tap, halo kernel only; see ConvTcHArgs::cc2):
+    // x2 [B,T,H,W,Cin2] split like x, w2 [3 (kw)][cout_pad][Cin2] split with the SAME scales (only the kw = 1 slab non-zero)
+    const __half* x2_hi = nullptr; const __half* x2_lo = nullptr;
+    const __half* w2_hi = nullptr; const __half* w2_lo = nullptr;
+    int Cin2 = 0;
 };
 bool conv_tc_fuses_stats(int T, int H, int W);
 bool conv_tc_halo_eligible(int H, int W, int kh);
+bool conv_tc_side_eligible(int H, int W, int Cin, int Cin2, int cout_pad, int terms);   // fused 1x1x1 side input possible?
 bool conv_tc_supported(int B, int T, int H, int W, int Cin, int Cout, int kt, int kh, int kw);
 int launch_conv_tc(const ConvTcArgs& a, cudaStream_t stream);
 int conv_tc_set_debug(unsigned long long* buf, int ctas);   // phase timestamps of the halo kernel (profiling aid)

@@ -107,11 +107,13 @@ SIGNATURES = {
     "i2v_encoder3d_destroy": (None, [_P]),
     "i2v_op_conv": (_I, [_P] * 5 + [_I] * 21 + [_P]),
     "i2v_op_conv_tc": (_I, [_P] * 5 + [_I] * 17 + [_F, _F, _P, _SZ, _P]),
+    "i2v_op_conv_tc_side": (_I, [_P] * 6 + [_I] * 12 + [_F, _F, _P, _SZ, _P]),
     "i2v_debug_conv_tc_timestamps": (_I, [_P, _I]),
     "i2v_debug_flow_timestamps": (_I, [_P]),
     "i2v_op_channel_stats": (_I, [_P, _P, _I, _I64, _I, _P]),
     "i2v_op_norm_coeffs": (_I, [_P, _P, _I, _I, _I64, _I, _F, _P, _P, _P, _P]),
     "i2v_op_modulate": (_I, [_P] * 6 + [_I] * 9 + [_P]),
+    "i2v_op_modulate_split": (_I, [_P] * 5 + [_I] * 9 + [_F, _P]),
     "i2v_op_linear": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "i2v_op_resize_bilinear": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "i2v_op_maxpool3x3s2": (_I, [_P, _P, _I, _I, _I, _I, _P]),

@@ -99,15 +99,16 @@ DEC_BLOCKS = ("head_0", "g_0", "g_1", "g_2", "g_3", "g_4")
 ACT_SPLIT_SCALE = 16.0      # must equal ACT_SPLIT_SCALE in csrc/api.cu
 
 
-def split_fp16(w, in_scale):
+def split_fp16(w, in_scale, wmax=None):
     """fp32 weights [taps, Cout, Cin] -> (hi, lo, ws) for the tensor-core engine (csrc/conv_tc.cu).
+    ``wmax`` overrides max|w| when several tensors must share one scale (fused shortcut, see pack_decoder).
 
     hi = fp16(s*w), lo = fp16(s*w - hi) with s the power of two that puts max|w| in [2^13, 2^14): both
     words stay in fp16's normal range for everything that matters and hi+lo carries ~22 significand
     bits.  Rows are zero-padded to a multiple of 16 (UMMA N granularity).  ws = 1/(in_scale*s) is the
     exact power-of-two factor the epilogue applies to the fp32 accumulator."""
     import math
-    m = float(w.abs().max())
+    m = float(w.abs().max()) if wmax is None else float(wmax)
     s = 2.0 ** math.floor(math.log2(2.0 ** 14 / m)) if m > 0 else 1.0
     ws = w.double() * s
     hi = ws.to(torch.float16)
@@ -129,8 +130,12 @@ def phase_weights(w_taps):
     return torch.stack((w[0], w[1] + w[2], w[0] + w[1], w[2])).reshape(36, *w_taps.shape[1:])
 
 
-def pack_decoder(sd, nf, engine=0, upsample_t=(2, 1)):
-    """Returns (tensors, scalars).  engine >= 1 adds the split fp16 weights of the tensor-core engine."""
+def pack_decoder(sd, nf, engine=0, upsample_t=(2, 1), upsample_s=(2, 2)):
+    """Returns (tensors, scalars).  engine >= 1 adds the split fp16 weights of the tensor-core engine.
+
+    Blocks that do not upsample but change the channel count (BAIR / iPER g_4) get their learned shortcut fused into
+    conv_1 (csrc/conv_tc.cu, side input): ``<block>.conv_1x`` holds conv_s as a [3 (kw), Cout, Cin] stack whose kw = 1
+    slab is the 1x1x1 kernel, split with the scale conv_1 uses (one accumulator, one epilogue factor)."""
     import math
     t, scalars = {}, {}
     c0 = 16 * nf
@@ -166,6 +171,16 @@ def pack_decoder(sd, nf, engine=0, upsample_t=(2, 1)):
             if ut == 2:
                 ph, pl, ps = split_fp16(phase_weights(t[f"{name}.conv_0.w"]), ACT_SPLIT_SCALE)   # float64 sums -> split
                 tc[f"{name}.conv_0.wph"], tc[f"{name}.conv_0.wpl"], tc[f"{name}.conv_0.wps"] = ph, pl, ps
+            us = {"g_1": 2, "g_2": 2, "g_3": upsample_s[0], "g_4": upsample_s[1]}.get(name, 0)
+            if "conv_s" in convs and ut == 1 and us == 1:
+                w1, wsc = t[f"{name}.conv_1.w"], t[f"{name}.conv_s.w"]                # [27,Cout,Cmid], [1,Cout,Cin]
+                wmax = max(float(w1.abs().max()), float(wsc.abs().max()))
+                stack = torch.zeros(3, *wsc.shape[1:])
+                stack[1] = wsc[0]
+                tc[f"{name}.conv_1x.wh"], tc[f"{name}.conv_1x.wl"], _ = split_fp16(stack, ACT_SPLIT_SCALE, wmax)
+                tc[f"{name}.conv_1.wh"], tc[f"{name}.conv_1.wl"], tc[f"{name}.conv_1.ws"] = split_fp16(t.pop(f"{name}.conv_1.w"),
+                                                                                                   ACT_SPLIT_SCALE, wmax)
+                convs = [c for c in convs if c != "conv_1"]
             for c in convs:
                 tc[f"{name}.{c}.wh"], tc[f"{name}.{c}.wl"], tc[f"{name}.{c}.ws"] = split_fp16(t.pop(f"{name}.{c}.w"), ACT_SPLIT_SCALE)
             # SPADE hidden map h = lrelu(conv(img) + b) with |img| <= 1 after the bilinear resize:

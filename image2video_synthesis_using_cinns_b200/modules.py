@@ -200,7 +200,7 @@ class Generator(_Native):
         self.h = self.L.i2v_decoder_create(self.nf, self.z_dim, us, ut, conv_engine)
         if not self.h:
             raise RuntimeError(self.L.i2v_last_error().decode())
-        tensors, scalars = loader.pack_decoder(state_dict, self.nf, conv_engine, self.upsample_t)
+        tensors, scalars = loader.pack_decoder(state_dict, self.nf, conv_engine, self.upsample_t, self.upsample_s)
         self._register(self.L.i2v_decoder_set_tensor, tensors)
         for name, v in scalars.items():
             _lib.check(self.L.i2v_decoder_set_scalar(self.h, name.encode(), float(v)), f"set_scalar({name})")

@@ -122,6 +122,13 @@ int i2v_op_conv_tc(const float* dev_x, const float* dev_w, const float* dev_bias
                    int B, int T, int H, int W, int Cin, int Cout, int cout_pad, int kt, int kh, int kw, int res_ut,
                    int res_uh, int res_uw, int act, int out_mode, int terms, int variant, float scale_a, float scale_w,
                    void* dev_ws, size_t ws_bytes, void* stream);
+/* 3x3x3 tensor-core conv with a side input: y = conv3x3x3(x, w) + conv1x1x1(x2, w2) + bias as ONE implicit GEMM (the
+ * GeneratorBlock's learned shortcut fused into conv_1, decoder.py:44-50).  w2 is [3 (kw)][cout_pad][Cin2] with only
+ * the kw = 1 slab non-zero. */
+int i2v_op_conv_tc_side(const float* dev_x, const float* dev_w, const float* dev_x2, const float* dev_w2, const float* dev_bias,
+                        float* dev_y, int B, int T, int H, int W, int Cin, int Cin2, int Cout, int cout_pad, int act,
+                        int out_mode, int terms, int variant, float scale_a, float scale_w, void* ws, size_t ws_bytes,
+                        void* stream);
 /* profiling aid: when dev_buf != NULL the halo conv kernel writes 8 x uint64 %globaltimer stamps per CTA (first `ctas`
  * CTAs of grid row 0): 0 start, 1 prologue done, 2 first stage landed, 3 last MMA issued, 4 accumulators complete,
  * 5 epilogue stores issued, 6 CTA end */
@@ -136,6 +143,9 @@ int i2v_op_norm_coeffs(const double* dev_sums, float* dev_coef, int B, int C, in
 int i2v_op_modulate(const float* dev_x, const float* dev_coef, const float* dev_gb, const float* dev_r,
                     const float* dev_coef2, float* dev_out, int B, int T, int H, int W, int C, int ut, int uh, int uw,
                     int act, void* stream);
+/* The same pass writing the conv-ready fp16 pair of the tensor-core engine: hi = fp16(s*v), lo = fp16(s*v - hi). */
+int i2v_op_modulate_split(const float* dev_x, const float* dev_coef, const float* dev_gb, void* dev_out_hi, void* dev_out_lo,
+                          int B, int T, int H, int W, int C, int ut, int uh, int uw, int act, float split_scale, void* stream);
 int i2v_op_linear(const float* dev_x, const float* dev_w, const float* dev_bias, float* dev_y, int B, int K, int N,
                   int act, void* stream);
 int i2v_op_resize_bilinear(const float* dev_img, float* dev_out, int B, int C, int H0, int W0, int H, int W,

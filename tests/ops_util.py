@@ -74,6 +74,18 @@ def modulate(x_cl, coef, out_dims, up=(1, 1, 1), gb=None, r=None, coef2=None, ac
     return out
 
 
+def modulate_split(x_cl, coef, out_dims, up=(1, 1, 1), gb=None, act=0, scale=16.0):
+    """Conv-ready fp16 pair (hi, lo) of scale * modulate(...)."""
+    L = _lib.load()
+    B, C = x_cl.shape[0], x_cl.shape[-1]
+    T, H, W = out_dims
+    hi = torch.empty(B, T, H, W, C, dtype=torch.float16, device="cuda")
+    lo = torch.empty_like(hi)
+    _lib.check(L.i2v_op_modulate_split(P(x_cl), P(coef), P(gb), P(hi), P(lo), B, T, H, W, C, *up, act, scale, S()),
+               "op_modulate_split")
+    return hi, lo
+
+
 def linear(x, w, b, act=0):
     L = _lib.load()
     B, K = x.shape
@@ -115,4 +127,25 @@ def conv_tc(x_cl, w_taps, bias, res_cl, k, res_up=(1, 1, 1), act=0, out_mode=0, 
     ws = torch.empty(4 * (x_cl.numel() + wp.numel()) + 4096, dtype=torch.uint8, device="cuda")
     _lib.check(L.i2v_op_conv_tc(P(x_cl), P(wp), P(bias), P(res_cl), P(y), B, T, H, W, Cin, Cout, cpad, *k, *res_up, act,
                                 out_mode, terms, variant, scale_a, scale_w, P(ws), ws.numel(), S()), "op_conv_tc")
+    return y
+
+
+def conv_tc_side(x_cl, w_taps, x2_cl, w2, bias, act=0, terms=3, scale_a=16.0, variant=0):
+    """3x3x3 tensor-core conv of x plus a fused 1x1x1 conv of the side input x2 (w2 [Cout, Cin2])."""
+    import math
+    L = _lib.load()
+    B, T, H, W, Cin = x_cl.shape
+    Cin2 = x2_cl.shape[-1]
+    Cout = w_taps.shape[1]
+    cpad = (Cout + 15) // 16 * 16
+    wp = torch.zeros(27, cpad, Cin, device="cuda")
+    wp[:, :Cout] = w_taps
+    w2p = torch.zeros(3, cpad, Cin2, device="cuda")
+    w2p[1, :Cout] = w2
+    wmax = max(float(w_taps.abs().max()), float(w2.abs().max()))
+    scale_w = 2.0 ** math.floor(math.log2(2.0 ** 14 / wmax))
+    y = torch.empty(B, T, H, W, Cout, dtype=torch.float32, device="cuda")
+    ws = torch.empty(4 * (x_cl.numel() + wp.numel() + x2_cl.numel() + w2p.numel()) + 8192, dtype=torch.uint8, device="cuda")
+    _lib.check(L.i2v_op_conv_tc_side(P(x_cl), P(wp), P(x2_cl), P(w2p), P(bias), P(y), B, T, H, W, Cin, Cin2, Cout, cpad, act, 0,
+                                     terms, variant, scale_a, scale_w, P(ws), ws.numel(), S()), "op_conv_tc_side")
     return y

@@ -119,3 +119,31 @@ def test_decoder_tensor_core_engine_matches_oracle(engine, ckpt_cache):
         e = rel_inf(m.decoder(x0.cuda(), z.cuda()).cpu(), want)
         report(f"decoder_tc{engine}:{dataset}", decoder=e)
         assert e < 1e-4
+
+
+SIDE_CASES = [
+    # name, (B, Cmid, T, H, W), Cin2, Cout, variant
+    ("bair_g4_stacked", (1, 64, 4, 8, 64), 128, 64, 0),      # BAIR g_4.conv_1: kw-stacked N = 192, kc = 64, 2 side chunks
+    ("plain_halo_n128", (1, 128, 2, 16, 32), 256, 128, 0),   # N = 128: plain halo form, weight slab kw = 1 of the stack
+    ("small_nf32", (2, 32, 4, 16, 16), 64, 32, 0),           # narrow net: kc = 32 (64-byte rows), stacked N = 96
+    ("stacked_forced_off", (1, 64, 2, 8, 64), 128, 64, 2),   # same layer through the plain halo form
+    ("single_product", (1, 64, 2, 8, 64), 128, 64, 0),       # terms = 1 (conv_engine 2)
+]
+
+
+@pytest.mark.parametrize("name,xs,cin2,cout,variant", SIDE_CASES, ids=[c[0] for c in SIDE_CASES])
+def test_conv_tc_side_input_is_fused_shortcut(name, xs, cin2, cout, variant):
+    """y = conv3x3x3(x) + conv1x1x1(x2) + b in one launch (GeneratorBlock shortcut fused into conv_1, decoder.py:44-50)."""
+    g = G(sum(map(ord, name)))
+    B, C, T, H, W = xs
+    x = torch.randn(xs, generator=g)
+    x2 = torch.randn(B, cin2, T, H, W, generator=g)
+    w = torch.randn(cout, C, 3, 3, 3, generator=g) / (27 * C) ** 0.5
+    w2 = torch.randn(cout, cin2, generator=g) / cin2 ** 0.5
+    b = torch.randn(cout, generator=g)
+    want = F.conv3d(x.double(), w.double(), b.double(), 1, 1) + F.conv3d(x2.double(), w2.double()[:, :, None, None, None])
+    terms = 1 if name == "single_product" else 3
+    got = ou.from_cl(ou.conv_tc_side(ou.to_cl(x), ou.taps(w), ou.to_cl(x2), w2.cuda(), b.cuda(), terms=terms, variant=variant))
+    e = rel_inf(got, want)
+    report("conv_tc_side:" + name, err=e)
+    assert e < (1e-3 if terms == 1 else 1e-5)

@@ -138,3 +138,24 @@ def test_linear_resize_maxpool():
     assert torch.equal(ou.resize(img.cuda(), 64, 64).permute(0, 3, 1, 2).cpu(), img)
     x = torch.randn(2, 64, 32, 32, generator=g)
     assert torch.equal(ou.from_cl(ou.maxpool(ou.to_cl(x))), F.max_pool2d(x, 3, 2, 1))
+
+
+@pytest.mark.parametrize("C,dims,up,with_gb,with_coef", [
+    (64, (4, 16, 16), (2, 2, 2), True, True),      # SPADE pass through the full upsample map (8-channel fast path)
+    (128, (4, 8, 8), (1, 2, 2), True, True),       # phase form: a0 kept at T/2, spatial upsample only
+    (32, (8, 16, 16), (1, 1, 1), False, True),     # AdaIN pass
+    (16, (2, 8, 8), (1, 1, 1), False, False),      # plain lrelu split ahead of conv_img
+    (24, (2, 8, 8), (2, 1, 1), True, True),        # C/8 not a power of two -> generic kernel
+])
+def test_modulate_split_matches_fp32_pass(C, dims, up, with_gb, with_coef):
+    """The fp16 (hi, lo) pair is the exact split of 16 x the fp32 pass: hi = fp16(16 v), lo = fp16(16 v - hi)."""
+    g = torch.Generator().manual_seed(C)
+    B, (T, H, W) = 3, dims
+    x = torch.randn(B, T // up[0], H // up[1], W // up[2], C, generator=g).cuda()
+    coef = torch.randn(B, C, 2, generator=g).cuda() if with_coef else None
+    gb = (0.3 * torch.randn(B, H, W, 2 * C, generator=g)).cuda() if with_gb else None
+    want = ou.modulate(x, coef, dims, up=up, gb=gb, act=2)
+    hi, lo = ou.modulate_split(x, coef, dims, up=up, gb=gb, act=2, scale=16.0)
+    w16 = want * 16.0
+    assert torch.equal(hi, w16.half())
+    assert torch.equal(lo, (w16 - w16.half().float()).half())
