@@ -487,12 +487,14 @@ static int decoder_run(const i2v_decoder* m, const float* img, const float* z, f
     };
     // fused modulate pass writing either fp32 (SIMT engine) or the fp16 split (tensor-core engine)
     auto modulate_to = [&](const float* x_, const float* coef_, const float* gb_, float* out_, size_t n_out, int Bc, int Tc,
-                           int Hc_, int Wc_, int C_, int ut_, int uh_, int uw_, int act) -> int {
+                           int Hc_, int Wc_, int C_, int ut_, int uh_, int uw_, int act, const float* coef_b = nullptr,
+                           float* outb = nullptr) -> int {
         ModArgs ma;
         ma.x = x_; ma.coef = coef_; ma.gb = gb_; ma.r = nullptr; ma.coef2 = nullptr; ma.out = out_;
         ma.B = Bc; ma.T = Tc; ma.H = Hc_; ma.W = Wc_; ma.C = C_; ma.ut = ut_; ma.uh = uh_; ma.uw = uw_; ma.act = act;
         if (tc) {
             ma.out_hi = reinterpret_cast<__half*>(out_); ma.out_lo = ma.out_hi + n_out; ma.split_scale = ACT_SPLIT_SCALE;
+            if (outb != nullptr) { ma.coef_b = coef_b; ma.outb_hi = reinterpret_cast<__half*>(outb); ma.outb_lo = ma.outb_hi + n_out; }
         }
         return launch_modulate(ma, s);
     };
@@ -548,18 +550,24 @@ static int decoder_run(const i2v_decoder* m, const float* img, const float* z, f
         const bool phase = tc && k.ut == 2 && m->tt.has(nm + ".conv_0.wph") && conv_tc_halo_eligible(Hc, Wc, 3);
         const int Ta = phase ? T / 2 : T;                       // stored planes of a0
         const size_t n_a0 = (size_t)B * Ta * Hc * Wc * cin;
-        I2V_TRY(modulate_to(x, coef, gb, bufp, n_a0, B, Ta, Hc, Wc, cin, phase ? 1 : k.ut, k.uh, k.uw, ACT_LRELU02));
-        // shortcut at low resolution
-        const float* xs = x;
         // a block that keeps the resolution runs its learned shortcut inside conv_1 (side input through the centre tap)
         static const bool no_fuse_s = getenv("I2V_NO_FUSE_S") != nullptr;      // A/B switch (tuning aid)
         const bool fuse_s = !no_fuse_s && tc && cin != cout && k.ut == 1 && k.uh == 1 && k.uw == 1 && m->tt.has(nm + ".conv_1x.wh") &&
                             conv_tc_side_eligible(Hc, Wc, cmid, cin, (cout + 15) / 16 * 16, eng == 1 ? 3 : 1);
+        // ... and its GroupNorm-affine input comes out of the same read of x as a0 (8-channel split path only)
+        auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
+        const bool dual = fuse_s && cin % 8 == 0 && pow2(cin / 8) && pow2(Wc);
         if (cin != cout) {
             I2V_PTR(nsw, G(nm + ".norm_s.w", cin));
             I2V_PTR(nsb, G(nm + ".norm_s.b", cin));
             I2V_TRY(launch_norm_coeffs(sums, coefs, B, cin, vlow, 16, 1e-5f, nsw, nsb, nullptr, s));
-            I2V_TRY(modulate_to(x, coefs, nullptr, lowin, (size_t)B * vlow * cin, B, Tl, Hl, Wl, cin, 1, 1, 1, ACT_NONE));
+        }
+        I2V_TRY(modulate_to(x, coef, gb, bufp, n_a0, B, Ta, Hc, Wc, cin, phase ? 1 : k.ut, k.uh, k.uw, ACT_LRELU02,
+                            dual ? coefs : nullptr, dual ? lowin : nullptr));
+        // shortcut at low resolution
+        const float* xs = x;
+        if (cin != cout) {
+            if (!dual) I2V_TRY(modulate_to(x, coefs, nullptr, lowin, (size_t)B * vlow * cin, B, Tl, Hl, Wl, cin, 1, 1, 1, ACT_NONE));
             if (fuse_s) {
                 xs = nullptr;                                     // conv_1 below takes lowin as its side input
             } else if (!tc) {
@@ -835,12 +843,14 @@ int i2v_op_modulate(const float* x, const float* coef, const float* gb, const fl
     return modulate(x, coef, gb, r, coef2, out, B, T, H, W, C, ut, uh, uw, act, static_cast<cudaStream_t>(stream));
 }
 int i2v_op_modulate_split(const float* x, const float* coef, const float* gb, void* out_hi, void* out_lo, int B, int T, int H, int W,
-                          int C, int ut, int uh, int uw, int act, float split_scale, void* stream) {
+                          int C, int ut, int uh, int uw, int act, float split_scale, const float* coef_b, void* outb_hi, void* outb_lo,
+                          void* stream) {
     I2V_REQUIRE(x && out_hi && out_lo, "op_modulate_split: null argument");
     ModArgs m;
     m.x = x; m.coef = coef; m.gb = gb; m.r = nullptr; m.coef2 = nullptr; m.out = nullptr;
     m.B = B; m.T = T; m.H = H; m.W = W; m.C = C; m.ut = ut; m.uh = uh; m.uw = uw; m.act = act;
     m.out_hi = static_cast<__half*>(out_hi); m.out_lo = static_cast<__half*>(out_lo); m.split_scale = split_scale;
+    m.coef_b = coef_b; m.outb_hi = static_cast<__half*>(outb_hi); m.outb_lo = static_cast<__half*>(outb_lo);
     return launch_modulate(m, static_cast<cudaStream_t>(stream));
 }
 int i2v_op_linear(const float* x, const float* w, const float* bias, float* y, int B, int K, int N, int act, void* stream) {

@@ -113,7 +113,7 @@ SIGNATURES = {
     "i2v_op_channel_stats": (_I, [_P, _P, _I, _I64, _I, _P]),
     "i2v_op_norm_coeffs": (_I, [_P, _P, _I, _I, _I64, _I, _F, _P, _P, _P, _P]),
     "i2v_op_modulate": (_I, [_P] * 6 + [_I] * 9 + [_P]),
-    "i2v_op_modulate_split": (_I, [_P] * 5 + [_I] * 9 + [_F, _P]),
+    "i2v_op_modulate_split": (_I, [_P] * 5 + [_I] * 9 + [_F, _P, _P, _P, _P]),
     "i2v_op_linear": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "i2v_op_resize_bilinear": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "i2v_op_maxpool3x3s2": (_I, [_P, _P, _I, _I, _I, _I, _P]),

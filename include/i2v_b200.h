@@ -143,9 +143,11 @@ int i2v_op_norm_coeffs(const double* dev_sums, float* dev_coef, int B, int C, in
 int i2v_op_modulate(const float* dev_x, const float* dev_coef, const float* dev_gb, const float* dev_r,
                     const float* dev_coef2, float* dev_out, int B, int T, int H, int W, int C, int ut, int uh, int uw,
                     int act, void* stream);
-/* The same pass writing the conv-ready fp16 pair of the tensor-core engine: hi = fp16(s*v), lo = fp16(s*v - hi). */
+/* The same pass writing the conv-ready fp16 pair of the tensor-core engine: hi = fp16(s*v), lo = fp16(s*v - hi).
+ * Optional second result of the same read (no upsampling): outb = split(s * (coef_b.A * x + coef_b.B)). */
 int i2v_op_modulate_split(const float* dev_x, const float* dev_coef, const float* dev_gb, void* dev_out_hi, void* dev_out_lo,
-                          int B, int T, int H, int W, int C, int ut, int uh, int uw, int act, float split_scale, void* stream);
+                          int B, int T, int H, int W, int C, int ut, int uh, int uw, int act, float split_scale,
+                          const float* dev_coef_b, void* dev_outb_hi, void* dev_outb_lo, void* stream);
 int i2v_op_linear(const float* dev_x, const float* dev_w, const float* dev_bias, float* dev_y, int B, int K, int N,
                   int act, void* stream);
 int i2v_op_resize_bilinear(const float* dev_img, float* dev_out, int B, int C, int H0, int W0, int H, int W,

@@ -74,16 +74,18 @@ def modulate(x_cl, coef, out_dims, up=(1, 1, 1), gb=None, r=None, coef2=None, ac
     return out
 
 
-def modulate_split(x_cl, coef, out_dims, up=(1, 1, 1), gb=None, act=0, scale=16.0):
-    """Conv-ready fp16 pair (hi, lo) of scale * modulate(...)."""
+def modulate_split(x_cl, coef, out_dims, up=(1, 1, 1), gb=None, act=0, scale=16.0, coef_b=None):
+    """Conv-ready fp16 pair (hi, lo) of scale * modulate(...); with coef_b also the pair of scale * (A_b x + B_b)."""
     L = _lib.load()
     B, C = x_cl.shape[0], x_cl.shape[-1]
     T, H, W = out_dims
     hi = torch.empty(B, T, H, W, C, dtype=torch.float16, device="cuda")
     lo = torch.empty_like(hi)
-    _lib.check(L.i2v_op_modulate_split(P(x_cl), P(coef), P(gb), P(hi), P(lo), B, T, H, W, C, *up, act, scale, S()),
-               "op_modulate_split")
-    return hi, lo
+    hb = torch.empty_like(hi) if coef_b is not None else None
+    lb = torch.empty_like(hi) if coef_b is not None else None
+    _lib.check(L.i2v_op_modulate_split(P(x_cl), P(coef), P(gb), P(hi), P(lo), B, T, H, W, C, *up, act, scale, P(coef_b), P(hb),
+                                       P(lb), S()), "op_modulate_split")
+    return (hi, lo) if coef_b is None else (hi, lo, hb, lb)
 
 
 def linear(x, w, b, act=0):

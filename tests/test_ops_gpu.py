@@ -159,3 +159,17 @@ def test_modulate_split_matches_fp32_pass(C, dims, up, with_gb, with_coef):
     w16 = want * 16.0
     assert torch.equal(hi, w16.half())
     assert torch.equal(lo, (w16 - w16.half().float()).half())
+
+
+def test_modulate_split_second_result_shares_the_read():
+    """a0 = lrelu(SPADE(x)) and the shortcut's GroupNorm-affine input from one pass over x (BAIR g_4 geometry, scaled down)."""
+    g = torch.Generator().manual_seed(9)
+    B, T, H, W, C = 2, 4, 16, 16, 64
+    x = torch.randn(B, T, H, W, C, generator=g).cuda()
+    coef, coef_b = torch.randn(B, C, 2, generator=g).cuda(), torch.randn(B, C, 2, generator=g).cuda()
+    gb = (0.3 * torch.randn(B, H, W, 2 * C, generator=g)).cuda()
+    hi, lo, hb, lb = ou.modulate_split(x, coef, (T, H, W), gb=gb, act=2, coef_b=coef_b)
+    w16 = ou.modulate(x, coef, (T, H, W), gb=gb, act=2) * 16.0
+    assert torch.equal(hi, w16.half()) and torch.equal(lo, (w16 - w16.half().float()).half())
+    b16 = ou.modulate(x, coef_b, (T, H, W), act=0) * 16.0
+    assert torch.equal(hb, b16.half()) and torch.equal(lb, (b16 - b16.half().float()).half())
