@@ -66,6 +66,7 @@ struct ConvTcKArgs {
 struct EpiArgs {
     const float* bias; const float* res; float* y;
     int T, H, W, Cout, res_ut, res_uh, res_uw, act, out_mode;
+    int contig;       // the 128 rows of a (sub-)tile are consecutive voxels of the output tensor
 };
 
 // Finish 16 consecutive output columns [nb, nb+16) of ONE output row held in registers: scale, bias, residual,
@@ -131,6 +132,39 @@ __device__ __forceinline__ void epilogue_row(const EpiArgs& e, uint32_t tmem_lan
     }
 }
 
+// Branch-free write-out for the common case: linear epilogue (ACT_NONE), every lane owns a whole float4 column group
+// of N_IT real rows (slice width 32 or 64 columns, all inside Cout).  The generic loop below carries per-row
+// predicates and a runtime activation switch, which ptxas turns into branches; with ONE epilogue warp per scheduler
+// that code ran at ~14 cycles per instruction (ncu: stall_wait / no_inst / branch_resolving).  Here everything is
+// unrolled straight-line code: all residual loads first, then rows in independent groups.
+template <int N_IT, bool HAS_RES>
+__device__ __forceinline__ void writeout_fast(const EpiArgs& e, const float* stile, int ld, int c, int n, int rsub, long long vox_lane,
+                                              long long roff_lane, const float4 b4, float (&ssum)[4], float (&ssq)[4]) {
+    constexpr int RPI = 32 / N_IT;               // rows per iteration (lanes_per_row = N_IT)
+    // the 32 rows of a warp slice are consecutive voxels (a box row is a full-width run, see the tile shapes), so the
+    // output row pointer is linear in r; only the residual goes through the (non-linear) upsample map
+    float* const y0 = e.y + __shfl_sync(0xffffffffu, vox_lane, 0) * e.Cout + n;
+    float4 rv[HAS_RES ? N_IT : 1];
+    if (HAS_RES) {
+#pragma unroll
+        for (int k = 0; k < N_IT; ++k) {
+            const long long roff = __shfl_sync(0xffffffffu, roff_lane, k * RPI + rsub);
+            rv[k] = __ldg(reinterpret_cast<const float4*>(e.res + roff + n));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < N_IT; ++k) {
+        const int r = k * RPI + rsub;
+        const float4 a4 = *reinterpret_cast<const float4*>(stile + r * ld + c);
+        float4 o4 = make_float4(a4.x + b4.x, a4.y + b4.y, a4.z + b4.z, a4.w + b4.w);
+        if (HAS_RES) { o4.x += rv[k].x; o4.y += rv[k].y; o4.z += rv[k].z; o4.w += rv[k].w; }
+        *reinterpret_cast<float4*>(y0 + r * e.Cout) = o4;
+        ssum[0] += o4.x; ssum[1] += o4.y; ssum[2] += o4.z; ssum[3] += o4.w;
+        ssq[0] = fmaf(o4.x, o4.x, ssq[0]); ssq[1] = fmaf(o4.y, o4.y, ssq[1]);
+        ssq[2] = fmaf(o4.z, o4.z, ssq[2]); ssq[3] = fmaf(o4.w, o4.w, ssq[3]);
+    }
+}
+
 // Write-out half of the coalesced epilogue: `stile` holds this warp's 32 rows x ncols scaled sums (row stride
 // ncols+4); lanes own fixed column groups, rows are walked with shuffled voxel / residual offsets.
 __device__ __forceinline__ void epilogue_writeout(const EpiArgs& e, const float* stile, int col0, int ncols, int n0, int lane,
@@ -157,6 +191,17 @@ __device__ __forceinline__ void epilogue_writeout(const EpiArgs& e, const float*
             }
         }
         const int n_it = 32 / rows_per_iter;         // rows per lane: 8, 16 or 32
+        // warp-uniform: whole slice inside Cout, 8 or 16 float4 column groups, linear epilogue
+        if (e.contig && e.act == ACT_NONE && vec_ok && (c4n == 8 || c4n == 16) && n0 + col0 + ncols <= e.Cout) {
+            if (c4n == 16) {
+                if (e.res != nullptr) writeout_fast<16, true>(e, stile, ld, c, n, rsub, vox_lane, roff_lane, b4, ssum, ssq);
+                else writeout_fast<16, false>(e, stile, ld, c, n, rsub, vox_lane, roff_lane, b4, ssum, ssq);
+            } else {
+                if (e.res != nullptr) writeout_fast<8, true>(e, stile, ld, c, n, rsub, vox_lane, roff_lane, b4, ssum, ssq);
+                else writeout_fast<8, false>(e, stile, ld, c, n, rsub, vox_lane, roff_lane, b4, ssum, ssq);
+            }
+            continue;
+        }
         if (e.res != nullptr && n_it <= 16) {
             // Residual rows come from L2 / HBM and each is a dependent-latency stall for the single warp a scheduler
             // runs here: issue ALL of this lane's residual loads first (<= 16 x 16 B in flight per lane), then finish
@@ -557,7 +602,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
         const int hi = r % a.bh; r /= a.bh;
         const int ti = r % a.bt;
         const int bi = r / a.bt;
-        EpiArgs e{a.bias, a.res, a.y, a.T, a.H, a.W, a.Cout, a.res_ut, a.res_uh, a.res_uw, a.act, a.out_mode};
+        // box dims grow only once the lower ones span the tensor (launch_conv_tc), so the 128 rows are consecutive voxels
+        EpiArgs e{a.bias, a.res, a.y, a.T, a.H, a.W, a.Cout, a.res_ut, a.res_uh, a.res_uw, a.act, a.out_mode, 1};
         const int nacc_used = a.nacc;       // host guarantees every accumulator is written by every CTA
         // column split between the two warps of a quarter (multiples of 16)
         const int nh0 = ((a.n_tile / 16 + 1) / 2) * 16;
@@ -617,9 +663,9 @@ struct ConvTcHArgs {
     int cc2;
 };
 
-// 320 threads x 200 registers = one CTA per SM (shared memory and TMEM allow no more anyway); the epilogue keeps up to
+// 320 threads x 192 registers (allocation granularity: 512 per warp) = one CTA per SM (shared memory and TMEM allow no more anyway); the epilogue keeps up to
 // 16 residual float4 per lane in flight on top of the TMEM fragments
-__global__ void __maxnreg__(200)
+__global__ void __maxnreg__(192)
 conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
                     const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl,
                     const __grid_constant__ CUtensorMap mA2h, const __grid_constant__ CUtensorMap mA2l,
@@ -837,7 +883,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
         const int m = q * 32 + lane;
         const int wi = m % a.bw, hi = m / a.bw;
         const float scale = __ldg(a.scale_ptr);
-        EpiArgs e{a.bias, a.res, a.y, a.T, a.H, a.W, a.Cout, a.res_ut, a.res_uh, a.res_uw, a.act, a.out_mode};
+        EpiArgs e{a.bias, a.res, a.y, a.T, a.H, a.W, a.Cout, a.res_ut, a.res_uh, a.res_uw, a.act, a.out_mode, a.bw == a.W ? 1 : 0};
         const int nh0 = ((a.n_tile / 16 + 1) / 2) * 16;
         const int col0 = half == 0 ? 0 : nh0, ncols = half == 0 ? nh0 : a.n_tile - nh0;
         const size_t stile_bytes = (size_t)32 * (nh0 + 4) * sizeof(float);
