@@ -144,24 +144,28 @@ __device__ __forceinline__ void writeout_fast(const EpiArgs& e, const float* sti
     // the 32 rows of a warp slice are consecutive voxels (a box row is a full-width run, see the tile shapes), so the
     // output row pointer is linear in r; only the residual goes through the (non-linear) upsample map
     float* const y0 = e.y + __shfl_sync(0xffffffffu, vox_lane, 0) * e.Cout + n;
-    float4 rv[HAS_RES ? N_IT : 1];
-    if (HAS_RES) {
+    constexpr int BATCH = 8;                     // residual float4 in flight per lane (register budget: 168 per thread)
 #pragma unroll
-        for (int k = 0; k < N_IT; ++k) {
-            const long long roff = __shfl_sync(0xffffffffu, roff_lane, k * RPI + rsub);
-            rv[k] = __ldg(reinterpret_cast<const float4*>(e.res + roff + n));
+    for (int k0 = 0; k0 < N_IT; k0 += BATCH) {
+        float4 rv[HAS_RES ? BATCH : 1];
+        if (HAS_RES) {
+#pragma unroll
+            for (int k = 0; k < BATCH; ++k) {
+                const long long roff = __shfl_sync(0xffffffffu, roff_lane, (k0 + k) * RPI + rsub);
+                rv[k] = __ldg(reinterpret_cast<const float4*>(e.res + roff + n));
+            }
         }
-    }
 #pragma unroll
-    for (int k = 0; k < N_IT; ++k) {
-        const int r = k * RPI + rsub;
-        const float4 a4 = *reinterpret_cast<const float4*>(stile + r * ld + c);
-        float4 o4 = make_float4(a4.x + b4.x, a4.y + b4.y, a4.z + b4.z, a4.w + b4.w);
-        if (HAS_RES) { o4.x += rv[k].x; o4.y += rv[k].y; o4.z += rv[k].z; o4.w += rv[k].w; }
-        *reinterpret_cast<float4*>(y0 + r * e.Cout) = o4;
-        ssum[0] += o4.x; ssum[1] += o4.y; ssum[2] += o4.z; ssum[3] += o4.w;
-        ssq[0] = fmaf(o4.x, o4.x, ssq[0]); ssq[1] = fmaf(o4.y, o4.y, ssq[1]);
-        ssq[2] = fmaf(o4.z, o4.z, ssq[2]); ssq[3] = fmaf(o4.w, o4.w, ssq[3]);
+        for (int k = 0; k < BATCH; ++k) {
+            const int r = (k0 + k) * RPI + rsub;
+            const float4 a4 = *reinterpret_cast<const float4*>(stile + r * ld + c);
+            float4 o4 = make_float4(a4.x + b4.x, a4.y + b4.y, a4.z + b4.z, a4.w + b4.w);
+            if (HAS_RES) { o4.x += rv[k].x; o4.y += rv[k].y; o4.z += rv[k].z; o4.w += rv[k].w; }
+            *reinterpret_cast<float4*>(y0 + r * e.Cout) = o4;
+            ssum[0] += o4.x; ssum[1] += o4.y; ssum[2] += o4.z; ssum[3] += o4.w;
+            ssq[0] = fmaf(o4.x, o4.x, ssq[0]); ssq[1] = fmaf(o4.y, o4.y, ssq[1]);
+            ssq[2] = fmaf(o4.z, o4.z, ssq[2]); ssq[3] = fmaf(o4.w, o4.w, ssq[3]);
+        }
     }
 }
 
@@ -190,7 +194,6 @@ __device__ __forceinline__ void epilogue_writeout(const EpiArgs& e, const float*
                 if (n + 3 < e.Cout) b4.w = __ldg(e.bias + n + 3);
             }
         }
-        const int n_it = 32 / rows_per_iter;         // rows per lane: 8, 16 or 32
         // warp-uniform: whole slice inside Cout, 8 or 16 float4 column groups, linear epilogue
         if (e.contig && e.act == ACT_NONE && vec_ok && (c4n == 8 || c4n == 16) && n0 + col0 + ncols <= e.Cout) {
             if (c4n == 16) {
@@ -199,56 +202,6 @@ __device__ __forceinline__ void epilogue_writeout(const EpiArgs& e, const float*
             } else {
                 if (e.res != nullptr) writeout_fast<8, true>(e, stile, ld, c, n, rsub, vox_lane, roff_lane, b4, ssum, ssq);
                 else writeout_fast<8, false>(e, stile, ld, c, n, rsub, vox_lane, roff_lane, b4, ssum, ssq);
-            }
-            continue;
-        }
-        if (e.res != nullptr && n_it <= 16) {
-            // Residual rows come from L2 / HBM and each is a dependent-latency stall for the single warp a scheduler
-            // runs here: issue ALL of this lane's residual loads first (<= 16 x 16 B in flight per lane), then finish
-            // the rows.  (Measured before: +4 us per 128-row sub-tile with 4 loads in flight.)
-            float4 rv[16];
-            const bool mine = n < e.Cout && rsub < rows_per_iter;
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                if (k < n_it) {
-                    const int r = (k * rows_per_iter + rsub) & 31;
-                    const long long roff = __shfl_sync(0xffffffffu, roff_lane, r);
-                    rv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (mine) {
-                        if (full4) {
-                            rv[k] = __ldg(reinterpret_cast<const float4*>(e.res + roff + n));
-                        } else {
-                            rv[k].x = __ldg(e.res + roff + n);
-                            if (n + 1 < e.Cout) rv[k].y = __ldg(e.res + roff + n + 1);
-                            if (n + 2 < e.Cout) rv[k].z = __ldg(e.res + roff + n + 2);
-                            if (n + 3 < e.Cout) rv[k].w = __ldg(e.res + roff + n + 3);
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                if (k < n_it) {
-                    const int r = (k * rows_per_iter + rsub) & 31;
-                    const long long vox = __shfl_sync(0xffffffffu, vox_lane, r);
-                    if (mine) {
-                        const float4 a4 = *reinterpret_cast<const float4*>(stile + r * ld + c);
-                        const float v[4] = {apply_act(a4.x + b4.x + rv[k].x, e.act), apply_act(a4.y + b4.y + rv[k].y, e.act),
-                                            apply_act(a4.z + b4.z + rv[k].z, e.act), apply_act(a4.w + b4.w + rv[k].w, e.act)};
-                        if (full4) {
-                            *reinterpret_cast<float4*>(e.y + vox * e.Cout + n) = make_float4(v[0], v[1], v[2], v[3]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                if (n + j < e.Cout) e.y[vox * e.Cout + n + j] = v[j];
-                        }
-                        if (want_stats) {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                if (full4 || n + j < e.Cout) { ssum[j] += v[j]; ssq[j] = fmaf(v[j], v[j], ssq[j]); }
-                        }
-                    }
-                }
             }
             continue;
         }
@@ -663,9 +616,8 @@ struct ConvTcHArgs {
     int cc2;
 };
 
-// 320 threads x 192 registers (allocation granularity: 512 per warp) = one CTA per SM (shared memory and TMEM allow no more anyway); the epilogue keeps up to
-// 16 residual float4 per lane in flight on top of the TMEM fragments
-__global__ void __maxnreg__(192)
+// 10 warps = 3 on one scheduler: 16384 / 3 / 32 -> 168 registers per thread is the cap (more needs an 8-warp layout)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
                     const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl,
                     const __grid_constant__ CUtensorMap mA2h, const __grid_constant__ CUtensorMap mA2l,
