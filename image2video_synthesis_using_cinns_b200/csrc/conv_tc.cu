@@ -41,11 +41,11 @@ constexpr int TC_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 // optional phase timestamps (i2v_debug_conv_tc_timestamps): 16 x u64 per CTA, %globaltimer in ns
 __device__ unsigned long long* g_dbg = nullptr;
 __device__ int g_dbg_ctas = 0;
-__device__ __forceinline__ void dbg_stamp(int slot) {
-    if (g_dbg != nullptr && (int)blockIdx.x < g_dbg_ctas && blockIdx.y == 0) {
+__device__ __forceinline__ void dbg_stamp(int slot, int tile) {      // one row of stamps per output tile
+    if (g_dbg != nullptr && tile < g_dbg_ctas && blockIdx.y == 0) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        g_dbg[(size_t)blockIdx.x * 16 + slot] = t;
+        g_dbg[(size_t)tile * 16 + slot] = t;
     }
 }
 constexpr int TILE_M = 128;
@@ -251,7 +251,7 @@ __device__ __forceinline__ void epilogue_writeout(const EpiArgs& e, const float*
 __device__ __forceinline__ void epilogue_warp_coalesced(const EpiArgs& e, float* stile /* [32][ncols+4] */, uint32_t tmem_lane_base,
                                                         int col0, int ncols, int nacc, int acc_stride, int n0, float scale, int lane,
                                                         long long vox_lane, long long roff_lane, bool want_stats, float (&ssum)[4],
-                                                        float (&ssq)[4], int dbg_slot = -1) {
+                                                        float (&ssq)[4], int dbg_slot = -1, int dbg_tile = 0) {
     // this warp owns tile columns [col0, col0+ncols) of its 32 rows
     const int ld = ncols + 4;
     int c0 = 0;
@@ -295,9 +295,9 @@ __device__ __forceinline__ void epilogue_warp_coalesced(const EpiArgs& e, float*
             dst[j] = make_float4(accv[4 * j] * scale, accv[4 * j + 1] * scale, accv[4 * j + 2] * scale, accv[4 * j + 3] * scale);
     }
     __syncwarp();
-    if (dbg_slot >= 0 && threadIdx.x == 64) dbg_stamp(dbg_slot);          // this sub-tile is out of TMEM
+    if (dbg_slot >= 0 && threadIdx.x == 64) dbg_stamp(dbg_slot, dbg_tile);          // this sub-tile is out of TMEM
     epilogue_writeout(e, stile, col0, ncols, n0, lane, vox_lane, roff_lane, want_stats, ssum, ssq);
-    if (dbg_slot >= 0 && threadIdx.x == 64) dbg_stamp(dbg_slot + 1);      // ... and its stores are issued
+    if (dbg_slot >= 0 && threadIdx.x == 64) dbg_stamp(dbg_slot + 1, dbg_tile);      // ... and its stores are issued
 }
 
 // flush a lane's column-group partial sums into stats[b, c, {sum, sumsq}] (double, device-wide atomics)
@@ -614,7 +614,38 @@ struct ConvTcHArgs {
     // implicit GEMM over K = 27 C_mid + C_in, so the separate shortcut launch, its output tensor and the residual read
     // of this epilogue disappear.  Maps mA2*/mB2* ; weights [kw=3][cout_pad][Cin2] with only the kw = 1 slab non-zero.
     int cc2;
+    // Persistent tiles: a CTA walks output tiles blockIdx.x, blockIdx.x + gridDim.x, ... of its N tile.  Barriers, the
+    // TMEM allocation and the smem ring live across tiles, and while the epilogue of tile i drains TMEM the producer
+    // already loads the first `prefetch_stages` stages of tile i+1.  The 8 transpose tiles of the epilogue sit
+    // `stile_per_slot` to a ring buffer in the buffers that tile i filled LAST (0: this launch does not use them).
+    int n_tiles, prefetch_stages, stile_per_slot;
 };
+
+// Tile coordinates + the temporal tap range of one output tile of the halo kernel.
+struct HaloTile { int t, b, w0, h0, ct_base, wt_base, dt_lo, dt_hi, n_main, n_total; };
+__device__ __forceinline__ HaloTile halo_tile(const ConvTcHArgs& a, int tile, int cchunks) {
+    HaloTile c;
+    const int tw = tile % a.tiles_w; tile /= a.tiles_w;
+    const int th = tile % a.tiles_h; tile /= a.tiles_h;
+    c.t = tile % a.T; c.b = tile / a.T;
+    c.w0 = tw * a.bw; c.h0 = th * a.bh2;
+    // Temporal taps that fall outside the clip contribute only zero padding: both pipeline ends skip them.
+    // t_phase (conv_0 of a block whose input was nearest-upsampled x2 in time, decoder.py:102-111): the input
+    // frames 2j and 2j+1 are identical (SPADE's gamma/beta do not depend on t), so
+    //   out[2j]   = W0 a[j-1] + (W1+W2) a[j]        out[2j+1] = (W0+W1) a[j] + W2 a[j+1]
+    // i.e. TWO temporal taps on the T/2 tensor with per-phase pre-summed weights (loader.py) instead of three
+    // on the upsampled one: 2/3 of the MMAs and of the operand traffic, and the upsampled tensor never exists.
+    // Source plane of temporal tap dt is ct_base + dt, its weight slab wt_base + dt; the valid dt form a range.
+    const int Tin = a.t_phase ? a.T / 2 : a.T;
+    c.ct_base = a.t_phase ? (c.t >> 1) - 1 + (c.t & 1) : c.t - a.kt / 2;
+    c.wt_base = a.t_phase ? (c.t & 1) * 2 : 0;
+    c.dt_lo = c.ct_base < 0 ? -c.ct_base : 0;
+    c.dt_hi = (Tin - 1 - c.ct_base) < (a.kt - 1) ? (Tin - 1 - c.ct_base) : (a.kt - 1);
+    const int kw_iter = a.wstack ? 1 : a.kw;                      // stacked: one unshifted load covers all kw taps
+    c.n_main = (c.dt_hi - c.dt_lo + 1) * kw_iter * cchunks;       // pipeline stages of the 3x3(x3) taps
+    c.n_total = c.n_main + a.cc2;                                 // ... plus the side-input chunks (centre tap only)
+    return c;
+}
 
 // 10 warps = 3 on one scheduler: 16384 / 3 / 32 -> 168 registers per thread is the cap (more needs an 8-warp layout)
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -637,19 +668,13 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)a.stages * stage_bytes);
     uint64_t* empty = full + a.stages;
     uint64_t* tmem_full = empty + a.stages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint64_t* epi_done = tmem_full + 1;       // 8 arrivals per tile: TMEM and the transpose tiles are free again
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_done + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) dbg_stamp(0);                       // CTA start
-    int tile = blockIdx.x;
-    const int tw = tile % a.tiles_w; tile /= a.tiles_w;
-    const int th = tile % a.tiles_h; tile /= a.tiles_h;
-    const int t = tile % a.T;
-    const int b = tile / a.T;
-    const int w0 = tw * a.bw, h0 = th * a.bh2;
+    if (threadIdx.x == 0) dbg_stamp(0, blockIdx.x);           // CTA start
     const int n0 = blockIdx.y * a.n_tile;
     const int cchunks = a.cc_hi - a.cc_lo;
-    const int iters = a.kt * a.kw * cchunks;
     const int bh_sub = a.bh2 / 2;
     uint32_t ncols = 32;
     while (ncols < (uint32_t)(2 * accw * a.nacc)) ncols <<= 1;
@@ -666,6 +691,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
         if (lane == 0) {
             for (int s = 0; s < a.stages; ++s) { ptx::mbar_init(full + s, 1); ptx::mbar_init(empty + s, 1); }
             ptx::mbar_init(tmem_full, 1);
+            ptx::mbar_init(epi_done, 8);
             ptx::fence_barrier_init();
         }
         __syncwarp();
@@ -680,82 +706,84 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
     // next kernel can never take them first and then sit in its own pdl_wait() while this one starves.
     pdl_launch_dependents();
     pdl_wait();      // prologue above touched no global memory: it overlapped the previous kernel's tail
-    if (threadIdx.x == 0) dbg_stamp(1);                       // prologue done
-
-    // Temporal taps that fall outside the clip contribute only zero padding: both pipeline ends skip them.
-    // t_phase (conv_0 of a block whose input was nearest-upsampled x2 in time, decoder.py:102-111): the input
-    // frames 2j and 2j+1 are identical (SPADE's gamma/beta do not depend on t), so
-    //   out[2j]   = W0 a[j-1] + (W1+W2) a[j]        out[2j+1] = (W0+W1) a[j] + W2 a[j+1]
-    // i.e. TWO temporal taps on the T/2 tensor with per-phase pre-summed weights (loader.py) instead of three
-    // on the upsampled one: 2/3 of the MMAs and of the operand traffic, and the upsampled tensor never exists.
-    // `ct` = source plane in the stored tensor, `wt` = temporal index into the weight tensor.
-    // Source plane of temporal tap dt is ct_base + dt, its weight slab wt_base + dt; the valid dt form a range.
-    const int Tin = a.t_phase ? a.T / 2 : a.T;
-    const int ct_base = a.t_phase ? (t >> 1) - 1 + (t & 1) : t - a.kt / 2;
-    const int wt_base = a.t_phase ? (t & 1) * 2 : 0;
-    const int dt_lo = ct_base < 0 ? -ct_base : 0;
-    const int dt_hi = (Tin - 1 - ct_base) < (a.kt - 1) ? (Tin - 1 - ct_base) : (a.kt - 1);
-    const int kw_iter = a.wstack ? 1 : a.kw;                      // stacked: one unshifted load covers all kw taps
-    const int n_main = (dt_hi - dt_lo + 1) * kw_iter * cchunks;   // pipeline stages of the 3x3(x3) taps
-    const int n_total = n_main + a.cc2;                           // ... plus the side-input chunks (centre tap only)
-    (void)iters;
+    if (threadIdx.x == 0) dbg_stamp(1, blockIdx.x);           // prologue done
+    const int kw_iter = a.wstack ? 1 : a.kw;
+    const int tile0 = blockIdx.x, tstep = gridDim.x;
 
     if (warp == 0) {
-        {
-            const uint32_t tx = (a.terms > 1 ? 2u : 1u) * (a_rows * rb + b_bytes);
-            int s = 0;
-            uint32_t ph = 0;
-            for (int dt = dt_lo; dt <= dt_hi; ++dt)
+        const uint32_t tx = (a.terms > 1 ? 2u : 1u) * (a_rows * rb + b_bytes);
+        // side input: same box (the halo rows ride along unused), one weight slab [nw][n_tile][kc] per chunk
+        const uint32_t tx2 = (a.terms > 1 ? 2u : 1u) * (a_rows * rb + b_tap);
+        int s = 0;
+        uint32_t ph = 0, epi_ph = 0;
+        for (int tile = tile0; tile < a.n_tiles; tile += tstep) {
+            const HaloTile c = halo_tile(a, tile, cchunks);
+            if (lane == 0 && tile != tile0) { dbg_stamp(0, tile); dbg_stamp(1, tile); }    // the producer turns to this tile
+            // The first `prefetch_stages` stages of a tile go to ring buffers the previous tile's epilogue does not use:
+            // they are loaded while that epilogue still drains TMEM.  The stage after them (or the end of a short tile)
+            // waits until the transpose tiles have been read back (epi_done).
+            bool epi_waited = tile == tile0;
+            int n = 0;
+            for (int dt = c.dt_lo; dt <= c.dt_hi; ++dt)
             for (int dw = 0; dw < kw_iter; ++dw)
-            for (int cc = a.cc_lo; cc < a.cc_hi; ++cc) {
-                const int ct = ct_base + dt, wt = wt_base + dt, c0 = cc * a.kc;
+            for (int cc = a.cc_lo; cc < a.cc_hi; ++cc, ++n) {
+                const int ct = c.ct_base + dt, wt = c.wt_base + dt, c0 = cc * a.kc;
+                if (!epi_waited && n >= a.prefetch_stages) { ptx::mbar_wait(epi_done, epi_ph); epi_ph ^= 1u; epi_waited = true; }
                 ptx::mbar_wait(empty + s, ph ^ 1u);
                 uint8_t* st = smem + (size_t)s * stage_bytes;
-                const int cw = a.wstack ? w0 : w0 + dw - a.kw / 2, ch = h0 - 1;
+                const int cw = a.wstack ? c.w0 : c.w0 + dw - a.kw / 2, ch = c.h0 - 1;
                 if (ptx::elect_one()) {
                     ptx::mbar_expect_tx(full + s, tx);
-                    ptx::tma_load_5d(st, &mAh, full + s, c0, cw, ch, ct, b);
+                    ptx::tma_load_5d(st, &mAh, full + s, c0, cw, ch, ct, c.b);
                     ptx::tma_load_5d(st + off_bhi, &mBh, full + s, c0, n0, dw, 0, wt);
                     if (a.terms > 1) {
-                        ptx::tma_load_5d(st + off_alo, &mAl, full + s, c0, cw, ch, ct, b);
+                        ptx::tma_load_5d(st + off_alo, &mAl, full + s, c0, cw, ch, ct, c.b);
                         ptx::tma_load_5d(st + off_blo, &mBl, full + s, c0, n0, dw, 0, wt);
                     }
                 }
                 __syncwarp();
                 if (++s == a.stages) { s = 0; ph ^= 1u; }
             }
-            // side input: same box (the halo rows ride along unused), one weight slab [nw][n_tile][kc] per chunk
-            const uint32_t tx2 = (a.terms > 1 ? 2u : 1u) * (a_rows * rb + b_tap);
-            for (int cc = 0; cc < a.cc2; ++cc) {
+            for (int cc = 0; cc < a.cc2; ++cc, ++n) {
                 const int c0 = cc * a.kc;
+                if (!epi_waited && n >= a.prefetch_stages) { ptx::mbar_wait(epi_done, epi_ph); epi_ph ^= 1u; epi_waited = true; }
                 ptx::mbar_wait(empty + s, ph ^ 1u);
                 uint8_t* st = smem + (size_t)s * stage_bytes;
                 if (ptx::elect_one()) {
                     ptx::mbar_expect_tx(full + s, tx2);
-                    ptx::tma_load_5d(st, &mA2h, full + s, c0, w0, h0 - 1, t, b);
+                    ptx::tma_load_5d(st, &mA2h, full + s, c0, c.w0, c.h0 - 1, c.t, c.b);
                     ptx::tma_load_5d(st + off_bhi, &mB2h, full + s, c0, n0, a.wstack ? 0 : 1, 0, 0);
                     if (a.terms > 1) {
-                        ptx::tma_load_5d(st + off_alo, &mA2l, full + s, c0, w0, h0 - 1, t, b);
+                        ptx::tma_load_5d(st + off_alo, &mA2l, full + s, c0, c.w0, c.h0 - 1, c.t, c.b);
                         ptx::tma_load_5d(st + off_blo, &mB2l, full + s, c0, n0, a.wstack ? 0 : 1, 0, 0);
                     }
                 }
                 __syncwarp();
                 if (++s == a.stages) { s = 0; ph ^= 1u; }
             }
+            if (!epi_waited) { ptx::mbar_wait(epi_done, epi_ph); epi_ph ^= 1u; }   // every phase is observed exactly once
         }
     } else if (warp == 1) {
-        {
-            const uint32_t idesc = ptx::make_idesc_f16(TILE_M, accw);
-            const int ksteps = a.kc / 16;
-            const uint64_t dproto = ptx::make_kmajor_desc(0, rb);
-            const uint32_t dlo = (uint32_t)dproto, dhi = (uint32_t)(dproto >> 32);
-            const uint32_t sub_step = (uint32_t)(bh_sub * a.bw) * rb >> 4, kh_step = (uint32_t)a.bw * rb >> 4;
-            int s = 0, ai = 0, asm_ = 0;
-            const int nsmall = a.nacc - a.nmain;
-            uint32_t ph = 0;
-            for (int n = 0; n < n_total; ++n) {
+        const uint32_t idesc = ptx::make_idesc_f16(TILE_M, accw);
+        const int ksteps = a.kc / 16;
+        const uint64_t dproto = ptx::make_kmajor_desc(0, rb);
+        const uint32_t dlo = (uint32_t)dproto, dhi = (uint32_t)(dproto >> 32);
+        const uint32_t sub_step = (uint32_t)(bh_sub * a.bw) * rb >> 4, kh_step = (uint32_t)a.bw * rb >> 4;
+        const int nsmall = a.nacc - a.nmain;
+        int s = 0;
+        uint32_t ph = 0, epi_ph = 0;
+        for (int tile = tile0; tile < a.n_tiles; tile += tstep) {
+            const HaloTile c = halo_tile(a, tile, cchunks);
+            if (tile != tile0) {
+                // the accumulators are overwritten from the first MMA on: the previous tile must be out of TMEM
+                ptx::mbar_wait(epi_done, epi_ph);
+                epi_ph ^= 1u;
+                ptx::tc_fence_after();
+            }
+            int ai = 0, asm_ = 0;
+            for (int n = 0; n < c.n_total; ++n) {
                 ptx::mbar_wait(full + s, ph);
-                if (n == 0 && lane == 0) dbg_stamp(2);        // first stage landed
+                if (n == 0 && lane == 0) dbg_stamp(2, tile);  // first stage landed
                 ptx::tc_fence_after();
                 const uint32_t sa = ptx::smem_u32(smem + (size_t)s * stage_bytes);
                 const uint32_t lah = dlo + (sa >> 4), lal = lah + (off_alo >> 4);
@@ -770,7 +798,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
                 const uint32_t tsm0 = nsmall > 0 ? tmem_base + (uint32_t)((a.nmain + asm_) * accw) : tacc0;
                 const uint32_t tsm1 = tsm0 + (uint32_t)(a.nacc * accw);
                 uint32_t acc_flag = fresh;
-                const bool ext = n >= n_main;                    // side-input stage: centre row only, weight slab 0
+                const bool ext = n >= c.n_main;                  // side-input stage: centre row only, weight slab 0
                 if (ptx::elect_one()) {
 #pragma unroll
                 for (int kh = 0; kh < 3; ++kh) {
@@ -805,137 +833,153 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
             }
             if (ptx::elect_one()) ptx::mma_commit(tmem_full);
             __syncwarp();
-            if (lane == 0) dbg_stamp(3);                      // last MMA issued
+            if (lane == 0) dbg_stamp(3, tile);                // last MMA issued
         }
     } else {
-        if (a.res != nullptr && (a.flags & 1)) {
-            // The epilogue warps idle through the main loop: pull the residual rows they will add (the shortcut through
-            // its upsample map, or the previous K-split partial sum) from HBM into L2 now, so that the latency-bound
-            // residual reads of the epilogue hit L2.
-            const int q = warp & 3, half = (warp - 2) >> 2, m = q * 32 + lane;
-            const int wi = m % a.bw, hi = m / a.bw;
-            const int nh0 = ((a.n_tile / 16 + 1) / 2) * 16;
-            const int col0 = half == 0 ? 0 : nh0, ncols = half == 0 ? nh0 : a.n_tile - nh0;
-            const int Tr = a.T / a.res_ut, Hr = a.H / a.res_uh, Wr = a.W / a.res_uw;
-            for (int sub = 0; sub < 2; ++sub) {
-                const int ww = w0 + wi, hh = h0 + sub * bh_sub + hi;
-                const long long roff = ((((long long)b * Tr + t / a.res_ut) * Hr + hh / a.res_uh) * Wr + ww / a.res_uw) * a.Cout;
-                int c_lo = n0 + col0, c_hi = n0 + col0 + ncols;
-                if (c_hi > a.Cout) c_hi = a.Cout;
-                const char* p = reinterpret_cast<const char*>(a.res + roff + c_lo);
-                for (int off = 0; off < (c_hi - c_lo) * 4; off += 128)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
-            }
-        }
-        ptx::mbar_wait_backoff(tmem_full, 0);
-        if (threadIdx.x == 64) dbg_stamp(4);                  // accumulators complete
-        ptx::tc_fence_after();
-        const int nacc_used = a.nacc;       // host guarantees every accumulator is written by every CTA
+        const int nacc_used = a.nacc;       // host guarantees every accumulator is written by every tile
         const int q = warp & 3, half = (warp - 2) >> 2;       // two warps per TMEM lane quarter: column halves
         const int m = q * 32 + lane;
         const int wi = m % a.bw, hi = m / a.bw;
-        const float scale = __ldg(a.scale_ptr);
-        EpiArgs e{a.bias, a.res, a.y, a.T, a.H, a.W, a.Cout, a.res_ut, a.res_uh, a.res_uw, a.act, a.out_mode, a.bw == a.W ? 1 : 0};
         const int nh0 = ((a.n_tile / 16 + 1) / 2) * 16;
         const int col0 = half == 0 ? 0 : nh0, ncols = half == 0 ? nh0 : a.n_tile - nh0;
         const size_t stile_bytes = (size_t)32 * (nh0 + 4) * sizeof(float);
         const int Tr = a.T / a.res_ut, Hr = a.H / a.res_uh, Wr = a.W / a.res_uw;
-        if (a.wstack) {
-            // stacked kw taps: shifted sum of the three column groups (see wstack_gather).  Host guarantees that the
-            // transpose tiles + exchange rows fit the drained pipeline buffers.
-            const bool coal = a.out_mode == 0;
-            float* stile = reinterpret_cast<float*>(smem + (size_t)(warp - 2) * stile_bytes);
-            float* xbuf = reinterpret_cast<float*>(smem + (coal ? 8 * stile_bytes : 0));      // [slot][quarter][d0|d2][n_tile]
-            const bool left_ok = wi > 0, right_ok = wi < a.bw - 1;
-            const bool fix0 = q > 0 && ((q * 32) % a.bw) > 0, fix31 = q < 3 && ((q * 32 + 31) % a.bw) < a.bw - 1;
-            float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};
-            const bool want_stats = a.stats != nullptr;
-            int slot = 0;
-            for (int sub = 0; sub < 2; ++sub) {
-                const int ww = w0 + wi, hh = h0 + sub * bh_sub + hi;
-                const long long vox_lane = (((long long)b * a.T + t) * a.H + hh) * a.W + ww;
-                const long long roff_lane = ((((long long)b * Tr + t / a.res_ut) * Hr + hh / a.res_uh) * Wr + ww / a.res_uw) * a.Cout;
-                const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * a.nacc * accw);
-                if (coal) {
-                    float* xs = xbuf + (size_t)slot * 8 * a.n_tile;
-                    if (ncols > 0)
-                        wstack_gather(stile, tbase, col0, ncols, a.n_tile, nacc_used, accw, scale, lane, left_ok, right_ok,
-                                      xs + (size_t)(q * 2) * a.n_tile, xs + (size_t)(q * 2 + 1) * a.n_tile);
-                    epi_bar();
-                    if (ncols > 0) {
-                        const int ld = ncols + 4;
-                        for (int c = lane; c < ncols; c += 32) {
-                            if (fix0) stile[c] += scale * xs[(size_t)((q - 1) * 2) * a.n_tile + col0 + c];
-                            if (fix31) stile[31 * ld + c] += scale * xs[(size_t)((q + 1) * 2 + 1) * a.n_tile + col0 + c];
-                        }
-                        __syncwarp();
-                        if (threadIdx.x == 64) dbg_stamp(8 + 2 * sub);
-                        epilogue_writeout(e, stile, col0, ncols, n0, lane, vox_lane, roff_lane, want_stats, ssum, ssq);
-                        if (threadIdx.x == 64) dbg_stamp(9 + 2 * sub);
-                    }
-                    slot ^= 1;
-                } else {
-                    // one output row per thread (frame layout of conv_img): half-0 warps work, all 8 keep the barrier count
-                    for (int c0 = 0; c0 < a.n_tile; c0 += 16) {
-                        float* xs = xbuf + (size_t)slot * 8 * a.n_tile;
-                        float v[16];
-                        if (half == 0) {
-                            float d0[16], d1[16], d2[16];
-                            wstack_chunk16(tbase, a.n_tile, nacc_used, accw, c0, d0, d1, d2);
-                            wstack_combine(d0, d1, d2, lane, left_ok, right_ok, v);
-                            if (lane == 31) {
-#pragma unroll
-                                for (int j = 0; j < 16; ++j) xs[(size_t)(q * 2) * a.n_tile + c0 + j] = d0[j];
-                            }
-                            if (lane == 0) {
-#pragma unroll
-                                for (int j = 0; j < 16; ++j) xs[(size_t)(q * 2 + 1) * a.n_tile + c0 + j] = d2[j];
-                            }
-                        }
-                        epi_bar();
-                        if (half == 0) {
-                            if (lane == 0 && fix0) {
-#pragma unroll
-                                for (int j = 0; j < 16; ++j) v[j] += xs[(size_t)((q - 1) * 2) * a.n_tile + c0 + j];
-                            }
-                            if (lane == 31 && fix31) {
-#pragma unroll
-                                for (int j = 0; j < 16; ++j) v[j] += xs[(size_t)((q + 1) * 2 + 1) * a.n_tile + c0 + j];
-                            }
-                            if (n0 + c0 < a.Cout) row_finish(e, v, n0 + c0, scale, vox_lane, roff_lane, b, t, hh, ww);
-                        }
-                        slot ^= 1;
-                    }
+        const bool use_stile = a.stile_per_slot > 0;          // coalesced channels-last write-out through transpose tiles
+        // edge-row exchange of the stacked form: its own region behind the barriers (the ring belongs to the producer)
+        float* const xbuf = reinterpret_cast<float*>(smem + (size_t)a.stages * stage_bytes + 256);   // [slot][quarter][d0|d2][n_tile]
+        EpiArgs e{a.bias, a.res, a.y, a.T, a.H, a.W, a.Cout, a.res_ut, a.res_uh, a.res_uw, a.act, a.out_mode, a.bw == a.W ? 1 : 0};
+        uint32_t tf_ph = 0;
+        int ring = 0;                                         // ring position behind the last stage of the current tile
+        float scale = 0.f;
+        for (int tile = tile0; tile < a.n_tiles; tile += tstep) {
+            const HaloTile c = halo_tile(a, tile, cchunks);
+            const int b = c.b, t = c.t, w0 = c.w0, h0 = c.h0;
+            ring = (ring + c.n_total) % a.stages;
+            if (a.res != nullptr && (a.flags & 1)) {
+                // The epilogue warps idle through the main loop: pull the residual rows they will add (the shortcut through
+                // its upsample map, or the previous K-split partial sum) from HBM into L2 now, so that the latency-bound
+                // residual reads of the epilogue hit L2.
+                for (int sub = 0; sub < 2; ++sub) {
+                    const int ww = w0 + wi, hh = h0 + sub * bh_sub + hi;
+                    const long long roff = ((((long long)b * Tr + t / a.res_ut) * Hr + hh / a.res_uh) * Wr + ww / a.res_uw) * a.Cout;
+                    int c_lo = n0 + col0, c_hi = n0 + col0 + ncols;
+                    if (c_hi > a.Cout) c_hi = a.Cout;
+                    const char* p = reinterpret_cast<const char*>(a.res + roff + c_lo);
+                    for (int off = 0; off < (c_hi - c_lo) * 4; off += 128)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
                 }
             }
-            if (coal && want_stats && ncols > 0) flush_stats(a.stats + (size_t)b * a.Cout * 2, a.Cout, n0, col0, ncols, lane, ssum, ssq);
-        } else if (a.out_mode == 0 && 8 * stile_bytes <= (size_t)a.stages * stage_bytes) {
-            // pipeline buffers are drained (every TMA landed, every MMA retired): reuse them as transpose tiles
-            float* stile = reinterpret_cast<float*>(smem + (size_t)(warp - 2) * stile_bytes);
-            float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};
-            const bool want_stats = a.stats != nullptr;
-            for (int sub = 0; sub < 2; ++sub) {
-                const int ww = w0 + wi, hh = h0 + sub * bh_sub + hi;
-                const long long vox_lane = (((long long)b * a.T + t) * a.H + hh) * a.W + ww;
-                const long long roff_lane = ((((long long)b * Tr + t / a.res_ut) * Hr + hh / a.res_uh) * Wr + ww / a.res_uw) * a.Cout;
-                if (ncols > 0)
-                    epilogue_warp_coalesced(e, stile, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * a.nacc * a.n_tile), col0,
-                                            ncols, nacc_used, a.n_tile, n0, scale, lane, vox_lane, roff_lane, want_stats, ssum, ssq,
-                                            8 + 2 * sub);
+            if (tile == tile0) scale = __ldg(a.scale_ptr);
+            ptx::mbar_wait_backoff(tmem_full, tf_ph);
+            tf_ph ^= 1u;
+            if (threadIdx.x == 64) dbg_stamp(4, tile);        // accumulators complete
+            ptx::tc_fence_after();
+            // Transpose tiles live in the ring buffers this tile filled LAST (every TMA landed, every MMA retired): the
+            // producer refills those last, so the first stages of the next tile stream in underneath this epilogue.
+            float* stile = nullptr;
+            if (use_stile) {
+                const int idx = warp - 2;
+                int slot = ring - 1 - idx / a.stile_per_slot;
+                while (slot < 0) slot += a.stages;
+                stile = reinterpret_cast<float*>(smem + (size_t)slot * stage_bytes + (size_t)(idx % a.stile_per_slot) * stile_bytes);
             }
-            if (want_stats && ncols > 0) flush_stats(a.stats + (size_t)b * a.Cout * 2, a.Cout, n0, col0, ncols, lane, ssum, ssq);
-            if (threadIdx.x == 64) dbg_stamp(12);
-        } else if (half == 0) {
-            for (int sub = 0; sub < 2; ++sub)
-                epilogue_row(e, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * a.nacc * a.n_tile), a.n_tile, nacc_used,
-                             a.n_tile, n0, scale, b, t, h0 + sub * bh_sub + hi, w0 + wi, true);
+            if (a.wstack) {
+                // stacked kw taps: shifted sum of the three column groups (see wstack_gather)
+                const bool coal = a.out_mode == 0;
+                const bool left_ok = wi > 0, right_ok = wi < a.bw - 1;
+                const bool fix0 = q > 0 && ((q * 32) % a.bw) > 0, fix31 = q < 3 && ((q * 32 + 31) % a.bw) < a.bw - 1;
+                float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};
+                const bool want_stats = a.stats != nullptr;
+                int slot = 0;
+                for (int sub = 0; sub < 2; ++sub) {
+                    const int ww = w0 + wi, hh = h0 + sub * bh_sub + hi;
+                    const long long vox_lane = (((long long)b * a.T + t) * a.H + hh) * a.W + ww;
+                    const long long roff_lane = ((((long long)b * Tr + t / a.res_ut) * Hr + hh / a.res_uh) * Wr + ww / a.res_uw) * a.Cout;
+                    const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * a.nacc * accw);
+                    if (coal) {
+                        float* xs = xbuf + (size_t)slot * 8 * a.n_tile;
+                        if (ncols > 0)
+                            wstack_gather(stile, tbase, col0, ncols, a.n_tile, nacc_used, accw, scale, lane, left_ok, right_ok,
+                                          xs + (size_t)(q * 2) * a.n_tile, xs + (size_t)(q * 2 + 1) * a.n_tile);
+                        epi_bar();
+                        if (ncols > 0) {
+                            const int ld = ncols + 4;
+                            for (int cx = lane; cx < ncols; cx += 32) {
+                                if (fix0) stile[cx] += scale * xs[(size_t)((q - 1) * 2) * a.n_tile + col0 + cx];
+                                if (fix31) stile[31 * ld + cx] += scale * xs[(size_t)((q + 1) * 2 + 1) * a.n_tile + col0 + cx];
+                            }
+                            __syncwarp();
+                            if (threadIdx.x == 64) dbg_stamp(8 + 2 * sub, tile);
+                            epilogue_writeout(e, stile, col0, ncols, n0, lane, vox_lane, roff_lane, want_stats, ssum, ssq);
+                            if (threadIdx.x == 64) dbg_stamp(9 + 2 * sub, tile);
+                        }
+                        slot ^= 1;
+                    } else {
+                        // one output row per thread (frame layout of conv_img): half-0 warps work, all 8 keep the barrier count
+                        for (int c0 = 0; c0 < a.n_tile; c0 += 16) {
+                            float* xs = xbuf + (size_t)slot * 8 * a.n_tile;
+                            float v[16];
+                            if (half == 0) {
+                                float d0[16], d1[16], d2[16];
+                                wstack_chunk16(tbase, a.n_tile, nacc_used, accw, c0, d0, d1, d2);
+                                wstack_combine(d0, d1, d2, lane, left_ok, right_ok, v);
+                                if (lane == 31) {
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j) xs[(size_t)(q * 2) * a.n_tile + c0 + j] = d0[j];
+                                }
+                                if (lane == 0) {
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j) xs[(size_t)(q * 2 + 1) * a.n_tile + c0 + j] = d2[j];
+                                }
+                            }
+                            epi_bar();
+                            if (half == 0) {
+                                if (lane == 0 && fix0) {
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j) v[j] += xs[(size_t)((q - 1) * 2) * a.n_tile + c0 + j];
+                                }
+                                if (lane == 31 && fix31) {
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j) v[j] += xs[(size_t)((q + 1) * 2 + 1) * a.n_tile + c0 + j];
+                                }
+                                if (n0 + c0 < a.Cout) row_finish(e, v, n0 + c0, scale, vox_lane, roff_lane, b, t, hh, ww);
+                            }
+                            slot ^= 1;
+                        }
+                    }
+                }
+                if (coal && want_stats && ncols > 0) flush_stats(a.stats + (size_t)b * a.Cout * 2, a.Cout, n0, col0, ncols, lane, ssum, ssq);
+            } else if (use_stile) {
+                float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};
+                const bool want_stats = a.stats != nullptr;
+                for (int sub = 0; sub < 2; ++sub) {
+                    const int ww = w0 + wi, hh = h0 + sub * bh_sub + hi;
+                    const long long vox_lane = (((long long)b * a.T + t) * a.H + hh) * a.W + ww;
+                    const long long roff_lane = ((((long long)b * Tr + t / a.res_ut) * Hr + hh / a.res_uh) * Wr + ww / a.res_uw) * a.Cout;
+                    if (ncols > 0)
+                        epilogue_warp_coalesced(e, stile, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * a.nacc * a.n_tile), col0,
+                                                ncols, nacc_used, a.n_tile, n0, scale, lane, vox_lane, roff_lane, want_stats, ssum, ssq,
+                                                8 + 2 * sub, tile);
+                }
+                if (want_stats && ncols > 0) flush_stats(a.stats + (size_t)b * a.Cout * 2, a.Cout, n0, col0, ncols, lane, ssum, ssq);
+                if (threadIdx.x == 64) dbg_stamp(12, tile);
+            } else if (half == 0) {
+                for (int sub = 0; sub < 2; ++sub)
+                    epilogue_row(e, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * a.nacc * a.n_tile), a.n_tile, nacc_used,
+                                 a.n_tile, n0, scale, b, t, h0 + sub * bh_sub + hi, w0 + wi, true);
+            }
+            if (threadIdx.x == 64) dbg_stamp(5, tile);        // epilogue stores issued
+            // this warp is done with TMEM and with its transpose tile: hand both back (TMA writes the tile's bytes next)
+            ptx::tc_fence_before();
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(epi_done);
+            if (threadIdx.x == 64) dbg_stamp(6, tile);        // tile end
         }
     }
-    if (threadIdx.x == 64) dbg_stamp(5);                      // epilogue stores issued
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 1) ptx::tmem_dealloc(tmem_base, ncols);
-    if (threadIdx.x == 0) dbg_stamp(6);                       // CTA end
 }
 
 __global__ void split_fp16_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, float scale,
@@ -986,6 +1030,16 @@ int tc_flags() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("I2V_TC_FLAGS");
+        v = e ? atoi(e) : 1;
+    }
+    return v;
+}
+
+// persistent tile loop of the halo kernel (I2V_TC_PERSIST=0 turns it off: A/B switch)
+int tc_persist() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("I2V_TC_PERSIST");
         v = e ? atoi(e) : 1;
     }
     return v;
@@ -1196,21 +1250,38 @@ static int launch_conv_tc_halo(const ConvTcArgs& h, cudaStream_t stream) {
         I2V_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+    // ring + alignment slack + barriers + (stacked form) 2 slots x 4 quarters x 2 edge rows of n_tile floats
+    const size_t smem = (size_t)stages * stage_bytes + 1024 + 256 + (wstack ? 16 * (size_t)a.n_tile * sizeof(float) : 0);
+    I2V_REQUIRE(smem <= 227 * 1024, "conv_tc: halo kernel shared memory (%zu bytes) over the 227 KB limit", smem);
     {
+        // transpose tiles of the coalesced epilogue: whole tiles per ring buffer, in the buffers a tile fills last
         const size_t nh0 = (size_t)((a.n_tile / 16 + 1) / 2) * 16;
-        I2V_REQUIRE(h.stats == nullptr || 8 * 32 * (nh0 + 4) * sizeof(float) <= (size_t)stages * stage_bytes,
-                    "conv_tc: transpose tiles do not fit the pipeline buffers, fused statistics unavailable");
-        // stacked form: transpose tiles + 2 slots x 4 quarters x 2 edge rows of n_tile floats
-        I2V_REQUIRE(!wstack || 8 * 32 * (nh0 + 4) * sizeof(float) + 16 * (size_t)a.n_tile * sizeof(float) <= (size_t)stages * stage_bytes,
-                    "conv_tc: stacked epilogue buffers do not fit the pipeline buffers");
+        const size_t stile_bytes = 32 * (nh0 + 4) * sizeof(float);
+        int sps = h.out_mode == 0 ? (int)(stage_bytes / stile_bytes) : 0;
+        if (sps > 8) sps = 8;
+        int epi_slots = sps > 0 ? (8 + sps - 1) / sps : 0;
+        if (epi_slots > stages) { sps = 0; epi_slots = 0; }          // does not fit: one-row-per-thread write-out
+        I2V_REQUIRE(h.stats == nullptr || sps > 0, "conv_tc: transpose tiles do not fit the pipeline buffers, fused statistics unavailable");
+        I2V_REQUIRE(!wstack || h.out_mode != 0 || sps > 0, "conv_tc: stacked epilogue buffers do not fit the pipeline buffers");
         I2V_REQUIRE(!wstack || (long long)a.tiles_w == 1, "conv_tc: stacked form needs whole rows per tile");
+        a.stile_per_slot = sps;
+        a.prefetch_stages = stages - epi_slots;
     }
     const long long M = (long long)h.B * h.T * h.H * h.W;
     const double K_ = (double)h.kt * h.kh * h.kw * h.Cin + (double)h.Cin2;
     ProfScope ps(PROF_CONV, 2.0 * (double)M * h.Cout * K_,
                  4.0 * ((double)M * (h.Cin + h.Cin2) + (double)M * h.Cout + K_ * h.Cout), stream);
-    dim3 grid((unsigned)((long long)a.tiles_w * a.tiles_h * h.T * h.B), (unsigned)((h.cout_pad + a.n_tile - 1) / a.n_tile));
+    // persistent CTAs: one per SM over all N tiles, each walking its share of the output tiles (I2V_TC_PERSIST=0: one
+    // CTA per tile, the pre-persistent schedule)
+    const long long n_tiles = (long long)a.tiles_w * a.tiles_h * h.T * h.B;
+    const unsigned ny = (unsigned)((h.cout_pad + a.n_tile - 1) / a.n_tile);
+    long long gx = n_tiles;
+    if (tc_persist()) {
+        const long long per_y = kNumSMs / ny > 0 ? kNumSMs / ny : 1;
+        if (gx > per_y) gx = per_y;
+    }
+    a.n_tiles = (int)n_tiles;
+    dim3 grid((unsigned)gx, ny);
     for (int p = 0; p < parts; ++p) {
         a.cc_lo = p * cper;
         a.cc_hi = (p + 1) * cper < cch ? (p + 1) * cper : cch;
