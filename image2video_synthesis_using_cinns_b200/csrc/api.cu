@@ -233,8 +233,13 @@ void i2v_flow_destroy(i2v_flow* h) { delete h; }
 }  // extern "C"
 
 // =============================================================================== embedder
+// Activations entering a tensor-core conv are split as fp16(ACT_SPLIT_SCALE * x): they are normalised /
+// modulated values of O(1); 16 keeps |x| < 4094 representable and pushes the fp16 subnormal floor of
+// the low word to ~4e-9.  loader.py folds 1/(ACT_SPLIT_SCALE * s_w) into each layer's "<conv>.ws".
+static constexpr float ACT_SPLIT_SCALE = 16.f;
 struct i2v_embedder {
     int zc, norm_mode;
+    int tc_mode = 1;      // 0: fp32 SIMT convs only  1: tensor-core convs where the GEMM fills the machine  2: wherever supported
     TensorTable tt;
 };
 
@@ -242,6 +247,12 @@ struct i2v_embedder {
 // by InstanceNorm2d(affine=False) -> statistics pass + fused normalise/ReLU(/residual) pass;
 // norm_mode 1: BatchNorm (eval) was folded into conv weight+bias at load, ReLU/residual ride in the
 // conv epilogue.
+//
+// InstanceNorm variant, tc_mode >= 1: the stride-1 convs whose GEMM fills the machine (layer1/layer2 at 64x64 input,
+// one more stage at 128x128) run on the tensor-core engine (error-compensated fp16 split, fp32-grade, conv_tc.cu).
+// The normalise/ReLU pass that feeds such a conv writes the fp16 split directly, and the block's final pass
+// writes both the fp32 tensor (the next identity branch) and its split.  Small-M layers (layer3/4: a handful of
+// 128-row tiles) stay on the fp32 SIMT engine with its split-K.
 static int embedder_run(const i2v_embedder* m, const float* x0, float* embed, int B, int H, int W, Arena& ar,
                         cudaStream_t s, bool dry) {
     const bool inorm = m->norm_mode == 0;
@@ -251,6 +262,10 @@ static int embedder_run(const i2v_embedder* m, const float* x0, float* embed, in
     float* xin = ar.take<float>((size_t)B * H * W * 3);
     float* buf[5];
     for (auto& b : buf) b = ar.take<float>(act_max);
+    // fp16 (hi | lo) copies of conv inputs for the tensor-core engine: same bytes as the fp32 tensor
+    float* sbuf[3] = {nullptr, nullptr, nullptr};
+    const bool any_tc = inorm && m->tc_mode != 0;
+    if (any_tc) for (auto& b : sbuf) b = ar.take<float>(act_max);
     double* sums = ar.take<double>((size_t)B * 2048 * 2);
     double* sums2 = ar.take<double>((size_t)B * 2048 * 2);
     float* coef = ar.take<float>((size_t)B * 2048 * 2);
@@ -265,21 +280,67 @@ static int embedder_run(const i2v_embedder* m, const float* x0, float* embed, in
 
     auto W_ = [&](const std::string& n, size_t e) { return m->tt.get(n, e); };
     auto Bv = [&](const std::string& n, size_t e) -> const float* { return inorm ? nullptr : m->tt.get(n, e); };
-    // conv (+ IN + ReLU) : in -> out ; raw conv output goes through `tmp` when instance-normalised
-    auto conv_norm_relu = [&](const std::string& name, const float* in, float* tmp, float* out, int Hi, int Wi, int Cin,
-                              int Cout, int k, int stride, int pad, int relu) -> int {
+    // does this conv run on the tensor-core engine?  (mode 2 forces it wherever the shape is supported: test aid)
+    auto tc_ok = [&](const std::string& name, int Hi, int Wi, int Cin, int Cout, int k, int stride) -> bool {
+        if (!any_tc || stride != 1 || !m->tt.has(name + ".wh")) return false;
+        if (!conv_tc_supported(B, 1, Hi, Wi, Cin, Cout, 1, k, k)) return false;
+        const long long ctas = (((long long)B * Hi * Wi + 127) / 128) * ((Cout + 127) / 128);
+        return m->tc_mode == 2 || ctas >= 32;
+    };
+    // raw = conv(in) + per-(sample, channel) sums of raw; `xs` != nullptr: split input, tensor-core engine
+    auto conv_stats = [&](const std::string& name, const float* in, const float* xs, float* raw, double* sums_, int Hi, int Wi, int Cin,
+                          int Cout, int k, int stride, int pad) -> int {
+        const int Ho = (Hi + 2 * pad - k) / stride + 1, Wo = (Wi + 2 * pad - k) / stride + 1;
+        if (xs != nullptr) {
+            const int cpad = (Cout + 15) / 16 * 16;
+            const size_t wn = (size_t)k * k * cpad * Cin, n_in = (size_t)B * Hi * Wi * Cin;
+            const __half* wh = m->tt.get<__half>(name + ".wh", wn);
+            const __half* wl = m->tt.get<__half>(name + ".wl", wn);
+            const float* ws = m->tt.get(name + ".ws", 1);
+            if (!wh || !wl || !ws) return -3;
+            ConvTcArgs a;
+            a.x_hi = reinterpret_cast<const __half*>(xs); a.x_lo = a.x_hi + n_in;
+            a.w_hi = wh; a.w_lo = wl; a.scale_ptr = ws; a.bias = nullptr; a.res = nullptr; a.y = raw;
+            a.B = B; a.T = 1; a.H = Hi; a.W = Wi; a.Cin = Cin; a.Cout = Cout; a.cout_pad = cpad;
+            a.kt = 1; a.kh = k; a.kw = k; a.res_ut = a.res_uh = a.res_uw = 1; a.act = ACT_NONE; a.out_mode = 0;
+            a.terms = 3;
+            const bool fuse = conv_tc_fuses_stats(1, Ho, Wo);
+            if (fuse) {
+                I2V_CHECK_CUDA(cudaMemsetAsync(sums_, 0, sizeof(double) * 2 * (size_t)B * Cout, s));
+                a.stats = sums_;
+            }
+            I2V_TRY(launch_conv_tc(a, s));
+            if (!fuse) I2V_TRY(launch_channel_stats(raw, sums_, B, (long long)Ho * Wo, Cout, s));
+            return 0;
+        }
         const float* w = W_(name + ".w", (size_t)k * k * Cout * Cin);
         if (!w) return -3;
+        I2V_TRY(conv(0, in, w, nullptr, nullptr, raw, B, 1, Hi, Wi, Cin, Cout, 1, k, k, 1, stride, stride, 0, pad, pad, 1, 1, 1, ACT_NONE, 0,
+                     s, &sk));
+        return launch_channel_stats(raw, sums_, B, (long long)Ho * Wo, Cout, s);
+    };
+    // normalise (+ ReLU) pass: fp32 result, or the fp16 split a following tensor-core conv consumes
+    auto norm_act = [&](const float* raw, const float* coef_, float* out, bool split, int Ho, int Wo, int C, int relu) -> int {
+        ModArgs ma;
+        ma.x = raw; ma.coef = coef_; ma.gb = nullptr; ma.r = nullptr; ma.coef2 = nullptr; ma.out = out;
+        ma.B = B; ma.T = 1; ma.H = Ho; ma.W = Wo; ma.C = C; ma.ut = ma.uh = ma.uw = 1; ma.act = relu ? ACT_RELU : ACT_NONE;
+        if (split) {
+            ma.out_hi = reinterpret_cast<__half*>(out); ma.out_lo = ma.out_hi + (size_t)B * Ho * Wo * C; ma.split_scale = ACT_SPLIT_SCALE;
+        }
+        return launch_modulate(ma, s);
+    };
+    // conv (+ IN + ReLU) : in -> out ; raw conv output goes through `tmp` when instance-normalised
+    auto conv_norm_relu = [&](const std::string& name, const float* in, const float* in_split, float* tmp, float* out, bool out_split,
+                              int Hi, int Wi, int Cin, int Cout, int k, int stride, int pad, int relu) -> int {
         const int Ho = (Hi + 2 * pad - k) / stride + 1, Wo = (Wi + 2 * pad - k) / stride + 1;
         if (inorm) {
-            I2V_TRY(conv(0, in, w, nullptr, nullptr, tmp, B, 1, Hi, Wi, Cin, Cout, 1, k, k, 1, stride, stride, 0, pad, pad, 1, 1,
-                         1, ACT_NONE, 0, s, &sk));
-            I2V_TRY(launch_channel_stats(tmp, sums, B, (long long)Ho * Wo, Cout, s));
+            I2V_TRY(conv_stats(name, in, in_split, tmp, sums, Hi, Wi, Cin, Cout, k, stride, pad));
             I2V_TRY(launch_norm_coeffs(sums, coef, B, Cout, (long long)Ho * Wo, 0, 1e-5f, nullptr, nullptr, nullptr, s));
-            I2V_TRY(modulate(tmp, coef, nullptr, nullptr, nullptr, out, B, 1, Ho, Wo, Cout, 1, 1, 1, relu ? ACT_RELU : ACT_NONE, s));
+            I2V_TRY(norm_act(tmp, coef, out, out_split, Ho, Wo, Cout, relu));
         } else {
+            const float* w = W_(name + ".w", (size_t)k * k * Cout * Cin);
             const float* b = Bv(name + ".b", Cout);
-            if (!b) return -3;
+            if (!w || !b) return -3;
             I2V_TRY(conv(0, in, w, b, nullptr, out, B, 1, Hi, Wi, Cin, Cout, 1, k, k, 1, stride, stride, 0, pad, pad, 1, 1, 1,
                          relu ? ACT_RELU : ACT_NONE, 0, s, &sk));
         }
@@ -287,10 +348,12 @@ static int embedder_run(const i2v_embedder* m, const float* x0, float* embed, in
     };
 
     I2V_TRY(launch_resize_bilinear_nchw_to_nhwc(x0, xin, B, 3, H, W, H, W, s));
-    I2V_TRY(conv_norm_relu("conv1", xin, buf[1], buf[0], H, W, 3, 64, 7, 2, 3, 1));
+    I2V_TRY(conv_norm_relu("conv1", xin, nullptr, buf[1], buf[0], false, H, W, 3, 64, 7, 2, 3, 1));
     I2V_TRY(launch_maxpool3x3s2(buf[0], buf[1], B, H1, W1, 64, s));
     float* cur = buf[1];
     float* t1 = buf[0]; float* t2 = buf[2]; float* t3 = buf[3]; float* t4 = buf[4];
+    float* cur_s = sbuf[0]; float* t1s = sbuf[1]; float* t2s = sbuf[2];
+    bool cur_split = false;                 // cur_s holds the split of cur
     int Hc = H2, Wc = W2, Cc = 64;
     const int nblocks[4] = {3, 4, 6, 3}, planes[4] = {64, 128, 256, 512};
     for (int li = 0; li < 4; ++li) {
@@ -298,30 +361,51 @@ static int embedder_run(const i2v_embedder* m, const float* x0, float* embed, in
             const std::string p = "layer" + std::to_string(li + 1) + "." + std::to_string(bi) + ".";
             const int pl = planes[li], stride = (li > 0 && bi == 0) ? 2 : 1;
             const int Ho = (Hc + 2 - 3) / stride + 1, Wo = (Wc + 2 - 3) / stride + 1;
+            const bool tc1 = tc_ok(p + "conv1", Hc, Wc, Cc, pl, 1, 1), tc2 = tc_ok(p + "conv2", Hc, Wc, pl, pl, 3, stride);
+            const bool tc3 = tc_ok(p + "conv3", Ho, Wo, pl, 4 * pl, 1, 1);
+            const bool tcd = bi == 0 && tc_ok(p + "ds", Hc, Wc, Cc, 4 * pl, 1, stride);
+            // does the next block's first conv want the split of this block's output?
+            bool next_tc = false;
+            {
+                int nli = li, nbi = bi + 1;
+                if (nbi == nblocks[li]) { nli = li + 1; nbi = 0; }
+                if (nli < 4) {
+                    const std::string np = "layer" + std::to_string(nli + 1) + "." + std::to_string(nbi) + ".";
+                    next_tc = tc_ok(np + "conv1", Ho, Wo, 4 * pl, planes[nli], 1, 1) ||
+                              (nbi == 0 && tc_ok(np + "ds", Ho, Wo, 4 * pl, 4 * planes[nli], 1, 2));
+                }
+            }
+            if ((tc1 || tcd) && !cur_split) {
+                I2V_TRY(launch_split_fp16(cur, reinterpret_cast<__half*>(cur_s), reinterpret_cast<__half*>(cur_s) + (size_t)B * Hc * Wc * Cc,
+                                          ACT_SPLIT_SCALE, (long long)B * Hc * Wc * Cc, s));
+                cur_split = true;
+            }
             // conv1 1x1 -> t1 ; conv2 3x3 (stride) -> t2
-            I2V_TRY(conv_norm_relu(p + "conv1", cur, t3, t1, Hc, Wc, Cc, pl, 1, 1, 0, 1));
-            I2V_TRY(conv_norm_relu(p + "conv2", t1, t3, t2, Hc, Wc, pl, pl, 3, stride, 1, 1));
-            const float* w3 = W_(p + "conv3.w", (size_t)4 * pl * pl);
-            if (!w3) return -3;
+            I2V_TRY(conv_norm_relu(p + "conv1", cur, tc1 ? cur_s : nullptr, t3, tc2 ? t1s : t1, tc2, Hc, Wc, Cc, pl, 1, 1, 0, 1));
+            I2V_TRY(conv_norm_relu(p + "conv2", t1, tc2 ? t1s : nullptr, t3, tc3 ? t2s : t2, tc3, Hc, Wc, pl, pl, 3, stride, 1, 1));
             if (inorm) {
                 // o3 raw -> t1 ; identity branch raw (downsample conv) -> t3 ; out = relu(IN(o3) + IN(ds) | h) -> t4
-                I2V_TRY(conv(0, t2, w3, nullptr, nullptr, t1, B, 1, Ho, Wo, pl, 4 * pl, 1, 1, 1, 1, 1, 1, 0, 0, 0, 1, 1, 1, ACT_NONE, 0, s, &sk));
-                I2V_TRY(launch_channel_stats(t1, sums, B, (long long)Ho * Wo, 4 * pl, s));
+                I2V_TRY(conv_stats(p + "conv3", t2, tc3 ? t2s : nullptr, t1, sums, Ho, Wo, pl, 4 * pl, 1, 1, 0));
                 I2V_TRY(launch_norm_coeffs(sums, coef, B, 4 * pl, (long long)Ho * Wo, 0, 1e-5f, nullptr, nullptr, nullptr, s));
                 const float* idt = cur; const float* c2 = nullptr;
                 if (bi == 0) {
-                    const float* wd = W_(p + "ds.w", (size_t)4 * pl * Cc);
-                    if (!wd) return -3;
-                    I2V_TRY(conv(0, cur, wd, nullptr, nullptr, t3, B, 1, Hc, Wc, Cc, 4 * pl, 1, 1, 1, 1, stride, stride, 0, 0, 0, 1, 1, 1,
-                                 ACT_NONE, 0, s, &sk));
-                    I2V_TRY(launch_channel_stats(t3, sums2, B, (long long)Ho * Wo, 4 * pl, s));
+                    I2V_TRY(conv_stats(p + "ds", cur, tcd ? cur_s : nullptr, t3, sums2, Hc, Wc, Cc, 4 * pl, 1, stride, 0));
                     I2V_TRY(launch_norm_coeffs(sums2, coef2, B, 4 * pl, (long long)Ho * Wo, 0, 1e-5f, nullptr, nullptr, nullptr, s));
                     idt = t3; c2 = coef2;
                 }
-                I2V_TRY(modulate(t1, coef, nullptr, idt, c2, t4, B, 1, Ho, Wo, 4 * pl, 1, 1, 1, ACT_RELU, s));
+                ModArgs ma;
+                ma.x = t1; ma.coef = coef; ma.gb = nullptr; ma.r = idt; ma.coef2 = c2; ma.out = t4;
+                ma.B = B; ma.T = 1; ma.H = Ho; ma.W = Wo; ma.C = 4 * pl; ma.ut = ma.uh = ma.uw = 1; ma.act = ACT_RELU;
+                if (next_tc) {      // fp32 result (the next identity branch) AND its split (the next conv1's operand)
+                    ma.out_hi = reinterpret_cast<__half*>(cur_s); ma.out_lo = ma.out_hi + (size_t)B * Ho * Wo * 4 * pl;
+                    ma.split_scale = ACT_SPLIT_SCALE; ma.out_f32 = t4;
+                }
+                I2V_TRY(launch_modulate(ma, s));
+                cur_split = next_tc;
             } else {
+                const float* w3 = W_(p + "conv3.w", (size_t)4 * pl * pl);
                 const float* b3 = m->tt.get(p + "conv3.b", (size_t)4 * pl);
-                if (!b3) return -3;
+                if (!w3 || !b3) return -3;
                 const float* idt = cur;
                 if (bi == 0) {
                     const float* wd = W_(p + "ds.w", (size_t)4 * pl * Cc);
@@ -355,6 +439,12 @@ i2v_embedder* i2v_embedder_create(int zc, int norm_mode) {
     return h;
 }
 int i2v_embedder_set_tensor(i2v_embedder* h, const char* n, const void* p, size_t b) { return h ? h->tt.set(n, p, b) : -1; }
+int i2v_embedder_set_scalar(i2v_embedder* h, const char* n, double v) {
+    I2V_REQUIRE(h && n, "embedder_set_scalar: null argument");
+    I2V_REQUIRE(std::string(n) == "tc_mode" && (v == 0 || v == 1 || v == 2), "embedder_set_scalar: unknown option '%s' = %g", n, v);
+    h->tc_mode = (int)v;
+    return 0;
+}
 size_t i2v_embedder_workspace_bytes(const i2v_embedder* h, int batch, int height, int width) {
     Arena ar(nullptr, 0, true);
     embedder_run(h, nullptr, nullptr, batch, height, width, ar, nullptr, true);
@@ -377,10 +467,6 @@ struct i2v_decoder {
     std::unordered_map<std::string, double> scalars;   // host-side per-layer constants (split scales)
 };
 
-// Activations entering a tensor-core conv are split as fp16(ACT_SPLIT_SCALE * x): they are normalised /
-// modulated values of O(1); 16 keeps |x| < 4094 representable and pushes the fp16 subnormal floor of
-// the low word to ~4e-9.  loader.py folds 1/(ACT_SPLIT_SCALE * s_w) into each layer's "<conv>.ws".
-static constexpr float ACT_SPLIT_SCALE = 16.f;
 
 struct DecBlock { const char* name; int cin, cout, ut, uh, uw; };
 

@@ -363,6 +363,37 @@ __device__ __forceinline__ void wstack_chunk16(uint32_t tbase, int n_tile, int n
     }
 }
 
+// Same, with the first two accumulators in flight under ONE wait (a TMEM load round trip costs ~0.5 us; conv_img's
+// one-row-per-thread write-out is nothing but such round trips).
+__device__ __forceinline__ void wstack_chunk16_x2(uint32_t tbase, int n_tile, int nacc, int accw, int c, float (&d0)[16], float (&d1)[16],
+                                                  float (&d2)[16]) {
+    if (nacc < 2) { wstack_chunk16(tbase, n_tile, nacc, accw, c, d0, d1, d2); return; }
+    uint32_t r0[16], r1[16], r2[16], s0[16], s1[16], s2[16];
+    const uint32_t tb1 = tbase + (uint32_t)accw;
+    ptx::tmem_ld_32x32b_x16(tbase + (uint32_t)c, r0);
+    ptx::tmem_ld_32x32b_x16(tbase + (uint32_t)(n_tile + c), r1);
+    ptx::tmem_ld_32x32b_x16(tbase + (uint32_t)(2 * n_tile + c), r2);
+    ptx::tmem_ld_32x32b_x16(tb1 + (uint32_t)c, s0);
+    ptx::tmem_ld_32x32b_x16(tb1 + (uint32_t)(n_tile + c), s1);
+    ptx::tmem_ld_32x32b_x16(tb1 + (uint32_t)(2 * n_tile + c), s2);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        d0[j] = __uint_as_float(r0[j]) + __uint_as_float(s0[j]);
+        d1[j] = __uint_as_float(r1[j]) + __uint_as_float(s1[j]);
+        d2[j] = __uint_as_float(r2[j]) + __uint_as_float(s2[j]);
+    }
+    for (int ai = 2; ai < nacc; ++ai) {
+        const uint32_t tb = tbase + (uint32_t)(ai * accw);
+        ptx::tmem_ld_32x32b_x16(tb + (uint32_t)c, r0);
+        ptx::tmem_ld_32x32b_x16(tb + (uint32_t)(n_tile + c), r1);
+        ptx::tmem_ld_32x32b_x16(tb + (uint32_t)(2 * n_tile + c), r2);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { d0[j] += __uint_as_float(r0[j]); d1[j] += __uint_as_float(r1[j]); d2[j] += __uint_as_float(r2[j]); }
+    }
+}
+
 // in-warp part of the shifted sum; lanes 0 / 31 still miss their cross-warp neighbour (added after the barrier)
 __device__ __forceinline__ void wstack_combine(const float (&d0)[16], const float (&d1)[16], const float (&d2)[16], int lane, bool left_ok,
                                                bool right_ok, float (&v)[16]) {
@@ -921,7 +952,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
                             float v[16];
                             if (half == 0) {
                                 float d0[16], d1[16], d2[16];
-                                wstack_chunk16(tbase, a.n_tile, nacc_used, accw, c0, d0, d1, d2);
+                                wstack_chunk16_x2(tbase, a.n_tile, nacc_used, accw, c0, d0, d1, d2);
                                 wstack_combine(d0, d1, d2, lane, left_ok, right_ok, v);
                                 if (lane == 31) {
 #pragma unroll
@@ -1175,6 +1206,11 @@ static int launch_conv_tc_halo(const ConvTcArgs& h, cudaStream_t stream) {
     if (shared_acc) nmain = 1;
     if (nmain < 1) return 1;                                                   // needs 2 accumulators per sub-tile
     if (nmain > 2) nmain = 2;
+    const int main_per_stage0 = 3 * (kc / 16) * (shared_acc ? 3 : 1);
+    // short reductions (conv_img: 36 chained MMAs) do not need a second main accumulator: one fewer TMEM round trip per
+    // epilogue chunk
+    if (nmain > 1 && (long long)kt_eff * kw_iter * cch * main_per_stage0 + (long long)(h.Cin2 / kc) * (main_per_stage0 / 3) <= kMaxChain / 2)
+        nmain = 1;
     const int main_per_stage = 3 * (kc / 16) * (shared_acc ? 3 : 1);           // chained MMAs per stage and sub-tile
     // side input: Cin2 / kc extra stages through the centre tap (one kh row each)
     I2V_REQUIRE(h.Cin2 == 0 || (h.x2_hi && h.w2_hi && h.Cin2 % kc == 0 && !h.t_phase && h.kt == 3 && h.kw == 3),

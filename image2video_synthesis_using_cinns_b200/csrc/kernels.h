@@ -83,6 +83,8 @@ struct ModArgs {
     int act;
     // when out_hi != nullptr the result is written as an fp16 (hi, lo) split of split_scale*v instead of fp32
     __half* out_hi = nullptr; __half* out_lo = nullptr; float split_scale = 1.f;
+    // with out_hi set: ALSO store the fp32 result here (a tensor that is both a conv operand and a later residual)
+    float* out_f32 = nullptr;
     // optional second result of the same read of x (split output, no upsampling only): outb = coef_b.A * x + coef_b.B,
     // no maps, no activation -- the GroupNorm-affine input of a block's learned shortcut (decoder.py:44-50)
     const float* coef_b = nullptr; __half* outb_hi = nullptr; __half* outb_lo = nullptr;

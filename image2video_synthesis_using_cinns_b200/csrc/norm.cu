@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(256) modulate_kernel(const ModArgs a, long lon
             for (int j = 0; j < 4; ++j) { hh[j] = __float2half_rn(f[j]); ll[j] = __float2half_rn(f[j] - __half2float(hh[j])); }
             reinterpret_cast<uint2*>(a.out_hi)[i] = *reinterpret_cast<const uint2*>(hh);
             reinterpret_cast<uint2*>(a.out_lo)[i] = *reinterpret_cast<const uint2*>(ll);
+            if (a.out_f32 != nullptr) reinterpret_cast<float4*>(a.out_f32)[i] = o;
         } else {
             reinterpret_cast<float4*>(a.out)[i] = o;
         }
@@ -332,7 +333,7 @@ int launch_modulate(const ModArgs& a, cudaStream_t stream) {
     I2V_REQUIRE(a.outb_hi == nullptr || (a.coef_b && a.outb_lo && a.out_hi && a.r == nullptr && a.ut == 1 && a.uh == 1 && a.uw == 1 &&
                                          a.C % 8 == 0 && pow2(a.C / 8) && pow2(a.W)),
                 "modulate: the second result needs the 8-channel split path without upsampling");
-    if (a.out_hi != nullptr && a.r == nullptr && a.C % 8 == 0 && pow2(a.C / 8) && pow2(a.W) &&
+    if (a.out_hi != nullptr && a.r == nullptr && a.out_f32 == nullptr && a.C % 8 == 0 && pow2(a.C / 8) && pow2(a.W) &&
         (long long)a.T * a.H * a.W * (a.C / 8) < (1ll << 31) && (long long)a.B * a.T < 65536) {
         const int per_plane = a.H * a.W * (a.C / 8);
         int bx = (per_plane + 255) / 256;

@@ -196,11 +196,15 @@ def pack_decoder(sd, nf, engine=0, upsample_t=(2, 1), upsample_s=(2, 2)):
 
 
 # -------------------------------------------------------------------------------------- embedder
-def pack_embedder(sd, zc, norm):
-    """torchvision-resnet50 keys under ``model.`` (AE.py:109) -> channels-last conv stacks."""
+def pack_embedder(sd, zc, norm, tensor_core=True):
+    """torchvision-resnet50 keys under ``model.`` (AE.py:109) -> channels-last conv stacks.
+
+    InstanceNorm variant: every stride-1 conv also gets the split fp16 weights of the tensor-core engine
+    (``.wh/.wl/.ws``, csrc/conv_tc.cu); the kernel side decides per call which layers use them (csrc/api.cu,
+    embedder_run), so the fp32 copy stays registered too."""
     t = {}
 
-    def put(dst, conv_key, bn_key):
+    def put(dst, conv_key, bn_key, stride=1):
         w = sd[conv_key].double()
         if norm == "bn":
             g, b = sd[bn_key + ".weight"].double(), sd[bn_key + ".bias"].double()
@@ -209,15 +213,18 @@ def pack_embedder(sd, zc, norm):
             w = w * sc.reshape(-1, 1, 1, 1)
             t[dst + ".b"] = (b - mean * sc).float()
         t[dst + ".w"] = _taps2(w.float())
+        if tensor_core and norm == "in" and stride == 1 and w.shape[1] % 16 == 0:
+            t[dst + ".wh"], t[dst + ".wl"], t[dst + ".ws"] = split_fp16(t[dst + ".w"], ACT_SPLIT_SCALE)
 
-    put("conv1", "model.conv1.weight", "model.bn1")
+    put("conv1", "model.conv1.weight", "model.bn1", stride=2)
     for li, nb in enumerate((3, 4, 6, 3)):
         for bi in range(nb):
             p, q = f"model.layer{li + 1}.{bi}.", f"layer{li + 1}.{bi}."
+            down = 2 if (li > 0 and bi == 0) else 1          # resnet v1.5: the stride sits on conv2 and the downsample conv
             for j in (1, 2, 3):
-                put(f"{q}conv{j}", f"{p}conv{j}.weight", f"{p}bn{j}")
+                put(f"{q}conv{j}", f"{p}conv{j}.weight", f"{p}bn{j}", stride=down if j == 2 else 1)
             if bi == 0:
-                put(f"{q}ds", f"{p}downsample.0.weight", f"{p}downsample.1")
+                put(f"{q}ds", f"{p}downsample.0.weight", f"{p}downsample.1", stride=down)
     fcw = sd["model.fc.sub_layers.0.weight"].float()
     if fcw.shape[2] != 1 or fcw.shape[3] != 1:
         raise ValueError("embedder fc kernel is not 1x1: input size does not reduce to 1x1 before the fc")

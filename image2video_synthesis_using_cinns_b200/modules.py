@@ -148,7 +148,9 @@ class ResnetEncoder(_Native):
 
     _destroy = "i2v_embedder_destroy"
 
-    def __init__(self, state_dict, config, device="cuda"):
+    def __init__(self, state_dict, config, device="cuda", tc_mode=1):
+        """``tc_mode``: 0 = fp32 SIMT convs only, 1 = tensor-core convs (fp32-grade fp16 split) where the GEMM fills
+        the machine (InstanceNorm variant), 2 = wherever the shape is supported."""
         super().__init__(device)
         self.config = config
         self.z_dim = config["z_dim"]
@@ -160,7 +162,12 @@ class ResnetEncoder(_Native):
         self.h = self.L.i2v_embedder_create(self.z_dim, 0 if norm == "in" else 1)
         if not self.h:
             raise RuntimeError(self.L.i2v_last_error().decode())
-        self._register(self.L.i2v_embedder_set_tensor, loader.pack_embedder(state_dict, self.z_dim, norm))
+        self._register(self.L.i2v_embedder_set_tensor, loader.pack_embedder(state_dict, self.z_dim, norm, tensor_core=tc_mode != 0))
+        self.set_tc_mode(tc_mode)
+
+    def set_tc_mode(self, tc_mode):
+        _lib.check(self.L.i2v_embedder_set_scalar(self.h, b"tc_mode", float(tc_mode)), "embedder_set_scalar(tc_mode)")
+        self.tc_mode = int(tc_mode)
 
     def forward(self, x):
         x = _f32c(x, self.device)

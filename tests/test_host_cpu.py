@@ -122,3 +122,19 @@ def test_split_fp16_is_fp32_grade():
     t, scalars = loader.pack_decoder(sd, 16, engine=1)
     assert "g_1.conv_0.wh" in t and "g_1.conv_0.w" not in t and "g_1.spade.sa" in scalars
     assert t["conv_img.wh"].shape == (27, 16, 16)
+
+
+def test_pack_embedder_in_adds_tensor_core_split():
+    gen = torch.Generator().manual_seed(6)
+    sd = synthetic.embedder_state_dict(gen, 64, "in")
+    t = loader.pack_embedder(sd, 64, "in")
+    # stride-1 convs carry the split fp16 copy next to the fp32 weights; strided ones and the 3-channel stem do not
+    assert "layer1.0.conv1.wh" in t and "layer1.0.ds.wh" in t and "layer2.1.conv2.wh" in t
+    assert "conv1.wh" not in t and "layer2.0.conv2.wh" not in t and "layer2.0.ds.wh" not in t
+    w = t["layer3.2.conv2.w"]
+    hi, lo, ws = t["layer3.2.conv2.wh"], t["layer3.2.conv2.wl"], t["layer3.2.conv2.ws"]
+    assert hi.shape == w.shape and hi.dtype == torch.float16
+    s = 1.0 / (loader.ACT_SPLIT_SCALE * float(ws))
+    assert ((hi.double() + lo.double()) / s - w.double()).abs().max() / w.abs().max() < 2 ** -21
+    assert not any(k.endswith(".wh") for k in loader.pack_embedder(sd, 64, "in", tensor_core=False))
+    assert not any(k.endswith(".wh") for k in loader.pack_embedder(synthetic.embedder_state_dict(gen, 64, "bn"), 64, "bn"))
