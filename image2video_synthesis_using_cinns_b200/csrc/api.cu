@@ -240,6 +240,7 @@ static constexpr float ACT_SPLIT_SCALE = 16.f;
 struct i2v_embedder {
     int zc, norm_mode;
     int tc_mode = 1;      // 0: fp32 SIMT convs only  1: tensor-core convs where the GEMM fills the machine  2: wherever supported
+    int tc_min_ctas = 8;  // mode 1: fewest 128-row x 128-column tiles for which the tensor-core engine is used
     TensorTable tt;
 };
 
@@ -285,7 +286,7 @@ static int embedder_run(const i2v_embedder* m, const float* x0, float* embed, in
         if (!any_tc || stride != 1 || !m->tt.has(name + ".wh")) return false;
         if (!conv_tc_supported(B, 1, Hi, Wi, Cin, Cout, 1, k, k)) return false;
         const long long ctas = (((long long)B * Hi * Wi + 127) / 128) * ((Cout + 127) / 128);
-        return m->tc_mode == 2 || ctas >= 32;
+        return m->tc_mode == 2 || ctas >= m->tc_min_ctas;
     };
     // raw = conv(in) + per-(sample, channel) sums of raw; `xs` != nullptr: split input, tensor-core engine
     auto conv_stats = [&](const std::string& name, const float* in, const float* xs, float* raw, double* sums_, int Hi, int Wi, int Cin,
@@ -441,7 +442,9 @@ i2v_embedder* i2v_embedder_create(int zc, int norm_mode) {
 int i2v_embedder_set_tensor(i2v_embedder* h, const char* n, const void* p, size_t b) { return h ? h->tt.set(n, p, b) : -1; }
 int i2v_embedder_set_scalar(i2v_embedder* h, const char* n, double v) {
     I2V_REQUIRE(h && n, "embedder_set_scalar: null argument");
-    I2V_REQUIRE(std::string(n) == "tc_mode" && (v == 0 || v == 1 || v == 2), "embedder_set_scalar: unknown option '%s' = %g", n, v);
+    const std::string k(n);
+    if (k == "tc_min_ctas" && v >= 1 && v <= 65536) { h->tc_min_ctas = (int)v; return 0; }
+    I2V_REQUIRE(k == "tc_mode" && (v == 0 || v == 1 || v == 2), "embedder_set_scalar: unknown option '%s' = %g", n, v);
     h->tc_mode = (int)v;
     return 0;
 }

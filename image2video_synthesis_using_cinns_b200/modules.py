@@ -16,6 +16,7 @@ CUDA device or without the built library raises.
 from __future__ import annotations
 
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -164,6 +165,9 @@ class ResnetEncoder(_Native):
             raise RuntimeError(self.L.i2v_last_error().decode())
         self._register(self.L.i2v_embedder_set_tensor, loader.pack_embedder(state_dict, self.z_dim, norm, tensor_core=tc_mode != 0))
         self.set_tc_mode(tc_mode)
+        if os.environ.get("I2V_EMB_TC_MIN_CTAS"):          # tuning aid
+            _lib.check(self.L.i2v_embedder_set_scalar(self.h, b"tc_min_ctas", float(os.environ["I2V_EMB_TC_MIN_CTAS"])),
+                       "embedder_set_scalar(tc_min_ctas)")
 
     def set_tc_mode(self, tc_mode):
         _lib.check(self.L.i2v_embedder_set_scalar(self.h, b"tc_mode", float(tc_mode)), "embedder_set_scalar(tc_mode)")

@@ -74,7 +74,8 @@ typedef struct i2v_embedder i2v_embedder;
 i2v_embedder* i2v_embedder_create(int zc, int norm_mode);
 int i2v_embedder_set_tensor(i2v_embedder* h, const char* name, const void* dev_ptr, size_t nbytes);
 /* options: "tc_mode" = 0 fp32 SIMT convs only, 1 (default) tensor-core convs (error-compensated fp16 split, fp32-grade)
- * for the stride-1 convs of the InstanceNorm variant whose GEMM fills the machine, 2 wherever the shape is supported */
+ * for the stride-1 convs of the InstanceNorm variant whose GEMM fills the machine, 2 wherever the shape is supported;
+ * "tc_min_ctas" = fewest 128x128 output tiles for which mode 1 picks the tensor-core engine (default 8: measured, B = 64) */
 int i2v_embedder_set_scalar(i2v_embedder* h, const char* name, double value);
 size_t i2v_embedder_workspace_bytes(const i2v_embedder* h, int batch, int height, int width);
 /* x0: [B,3,H,W] fp32 NCHW in [-1,1]  ->  embed: [B, zc] (the posterior mean) */

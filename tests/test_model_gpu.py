@@ -86,8 +86,11 @@ def test_model_matches_oracle_stagewise(dataset, kw, B, ckpt_cache):
     residual = torch.randn(B, 64, generator=g)
     wf, wz = om.forward(x0, residual, return_latent=True, batch_slice=False)
     gf, gz = m.sample(x0, residual=residual, return_latent=True)
-    report("oracle:" + dataset, embed=e_embed, decoder=e_dec, z=rel_inf(gz.cpu(), wz), frames=rel_inf(gf.cpu(), wf))
-    assert rel_inf(gz.cpu(), wz) < TOL and rel_inf(gf.cpu(), wf) < TOL
+    # frames bar as in the fixture test: 1e-4, or the oracle's own noise floor where the path runs through the
+    # ill-conditioned 64x64 InstanceNorm embedder (golden_util.conditioned_tolerance); z and the decoder keep the flat bar
+    tol_f = conditioned_tolerance(lambda a: om.forward(a, residual, batch_slice=False), (x0,))
+    report("oracle:" + dataset, embed=e_embed, decoder=e_dec, z=rel_inf(gz.cpu(), wz), frames=rel_inf(gf.cpu(), wf), frames_tol=tol_f)
+    assert rel_inf(gz.cpu(), wz) < TOL and rel_inf(gf.cpu(), wf) < tol_f
     if transfer:
         q = torch.rand(1, 16, 3, img, img, generator=g) * 2 - 1
         ws = om.transfer(q, x0)
