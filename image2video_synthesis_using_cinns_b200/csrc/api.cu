@@ -628,7 +628,12 @@ static int decoder_run(const i2v_decoder* m, const float* img, const float* z, f
             ca.kt = 1; ca.kh = 3; ca.kw = 3; ca.st = ca.sh = ca.sw = 1; ca.pt = 0; ca.ph = ca.pw = 1;
             ca.res_ut = ca.res_uh = ca.res_uw = 1; ca.act = ACT_LRELU02; ca.out_mode = 0;
             ca.y_hi = reinterpret_cast<__half*>(sh); ca.y_lo = ca.y_hi + nsh; ca.split_scale = (float)it->second;
-            I2V_TRY(launch_conv_simt(ca, s));
+            // dedicated K = 27 kernel (same bits as the SIMT engine); I2V_SPADE_SIMT=1 keeps the implicit-GEMM path (A/B switch)
+            static const bool spade_simt = getenv("I2V_SPADE_SIMT") != nullptr;
+            const int hw = Hc * Wc, tv = hw < 64 ? hw : 64;
+            const bool tiles = hw % tv == 0 && (Wc >= tv ? Wc % tv == 0 : tv % Wc == 0);
+            if (!spade_simt && tiles) I2V_TRY(launch_spade_conv3(imgr, scw, scb, ca.y_hi, ca.y_lo, ca.split_scale, B, Hc, Wc, ACT_LRELU02, s));
+            else I2V_TRY(launch_conv_simt(ca, s));
             I2V_TRY(conv_tc(nm + ".spade.gb", sh, nsh, sgb, nullptr, gb, B, 1, Hc, Wc, 128, 2 * cin, 1, 3, 3, 1, 1, 1, ACT_NONE, 0));
         }
         // a0 = lrelu(GN16(x) * (1+gamma) + beta), upsampled on the fly
@@ -869,6 +874,12 @@ int i2v_op_conv(const float* x, const float* w, const float* bias, const float* 
     I2V_REQUIRE(x && w && y, "op_conv: null argument");
     return conv(engine, x, w, bias, res, y, B, Ti, Hi, Wi, Cin, Cout, kt, kh, kw, st, sh, sw, pt, ph, pw, rut, ruh, ruw, act, out_mode,
                 static_cast<cudaStream_t>(stream));
+}
+int i2v_op_spade_conv3(const float* img, const float* w, const float* bias, void* y_hi, void* y_lo, float split_scale, int B, int H,
+                       int W, int act, void* stream) {
+    I2V_REQUIRE(img && w && bias && y_hi && y_lo, "op_spade_conv3: null argument");
+    return launch_spade_conv3(img, w, bias, static_cast<__half*>(y_hi), static_cast<__half*>(y_lo), split_scale, B, H, W, act,
+                              static_cast<cudaStream_t>(stream));
 }
 int i2v_op_conv_tc(const float* x, const float* w, const float* bias, const float* res, float* y, int B, int T, int H, int W, int Cin,
                    int Cout, int cout_pad, int kt, int kh, int kw, int rut, int ruh, int ruw, int act, int out_mode, int terms,

@@ -1359,7 +1359,9 @@ int launch_conv_tc(const ConvTcArgs& h, cudaStream_t stream) {
     const int tiles_b = (h.B + a.bb - 1) / a.bb;
     I2V_REQUIRE(h.stats == nullptr || (a.bb == 1 && h.out_mode == 0),
                 "conv_tc: fused statistics need one sample per tile (ask conv_tc_fuses_stats first)");
-    // fp32-grade mode keeps N <= 128 so that four TMEM accumulators fit (see the MMA issuer)
+    // fp32-grade mode keeps N <= 128 so that four TMEM accumulators fit (see the MMA issuer).  (N = 256 with one main + one
+    // cross-term accumulator and twice the K-split parts was measured on g_0, 1024 -> 1024 on 2x8x8 planes: no gain,
+    // profiles/r01_bench_ab_v2.txt call 12.)
     const int n_cap = h.terms == 3 ? 128 : 256;
     a.n_tile = h.cout_pad < n_cap ? h.cout_pad : n_cap;
     a.terms = h.terms;

@@ -99,6 +99,10 @@ int launch_linear(const float* x, const float* w, const float* bias, float* y, i
 // H==H0 && W==W0 degenerates to an exact NCHW->NHWC repack.
 int launch_resize_bilinear_nchw_to_nhwc(const float* img, float* out, int B, int C, int H0, int W0, int H, int W,
                                         cudaStream_t stream);
+// SPADE's Conv2d(3 -> 128, k3, p1) + activation on img [B,H,W,3], result as the fp16 split of split_scale * v
+// (y_hi / y_lo [B,H,W,128]); same bits as launch_conv_simt with y_hi set.  H*W must tile into 64-voxel patches.
+int launch_spade_conv3(const float* img, const float* w, const float* bias, __half* y_hi, __half* y_lo, float split_scale, int B,
+                       int H, int W, int act, cudaStream_t stream);
 // 3x3 stride-2 pad-1 max pool, channels-last [B,H,W,C] -> [B,Ho,Wo,C]
 int launch_maxpool3x3s2(const float* x, float* y, int B, int H, int W, int C, cudaStream_t stream);
 // mean over V from channel sums: y[b,c] = sums[b,c,0] / V

@@ -1,4 +1,6 @@
 // Small ops of the path: nn.Linear, bilinear start-frame resize, max-pool.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "prof.h"
@@ -7,39 +9,105 @@ namespace i2v {
 
 namespace {
 
-// One warp per output feature n, all batch rows; K % 4 == 0.  Used for decoder.fc (decoder.py:99),
-// AdaIN's Linear (normalization_layer.py:44,49), the embedder's 1x1 "fc" conv on the pooled feature
-// (AE.py:121-124) and conv_mu on the flattened 4x4 map (resnet3D.py:179,203).
+// nn.Linear y[b, n] = act(sum_k W[n, k] x[b, k] + bias[n]), K % 4 == 0: decoder.fc (decoder.py:99), AdaIN's Linear
+// (normalization_layer.py:44,49), the conditioning half of every flow subnet's first Linear (flow_blocks.py:33-41), the
+// embedder's 1x1 "fc" conv on the pooled feature (AE.py:121-124) and conv_mu on the flattened 4x4 map
+// (resnet3D.py:179,203).  One warp per (output feature, group of 8 batch rows), lanes stride over k.  (One warp per feature
+// walking all rows left the embedder fc -- K = 2048, N = 64 -- on 8 CTAs: 200 us, now 32.  A thread-per-feature variant with
+// the batch in shared memory was measured slower for the shallow-K shapes: 91 us vs 27 for AdaIN's Linear.)
 __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                      const float* __restrict__ bias, float* __restrict__ y, int B,
                                                      int K, int N, int act) {
     pdl_launch_dependents();
     pdl_wait();
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= N) return;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int groups = (B + 7) >> 3;
+    const int n = gw / groups, b0 = (gw - n * groups) * 8;
+    if (n >= N) return;
     const int K4 = K >> 2;
-    const float4* wr = reinterpret_cast<const float4*>(w + (long long)warp * K);
-    const float bn = bias != nullptr ? __ldg(bias + warp) : 0.f;
-    for (int b0 = 0; b0 < B; b0 += 8) {
-        float acc[8];
+    const float4* wr = reinterpret_cast<const float4*>(w + (long long)n * K);
+    const float bn = bias != nullptr ? __ldg(bias + n) : 0.f;
+    float acc[8];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) acc[r] = 0.f;
-        for (int k = lane; k < K4; k += 32) {
-            const float4 wv = __ldg(wr + k);
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                if (b0 + r < B) {
-                    const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (long long)(b0 + r) * K) + k);
-                    acc[r] = fmaf(wv.x, xv.x, acc[r]); acc[r] = fmaf(wv.y, xv.y, acc[r]);
-                    acc[r] = fmaf(wv.z, xv.z, acc[r]); acc[r] = fmaf(wv.w, xv.w, acc[r]);
-                }
-            }
-        }
+    for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+    for (int k = lane; k < K4; k += 32) {
+        const float4 wv = __ldg(wr + k);
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-            const float s = warp_sum(acc[r]);
-            if (lane == 0 && b0 + r < B) y[(long long)(b0 + r) * N + warp] = apply_act(s + bn, act);
+            if (b0 + r < B) {
+                const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (long long)(b0 + r) * K) + k);
+                acc[r] = fmaf(wv.x, xv.x, acc[r]); acc[r] = fmaf(wv.y, xv.y, acc[r]);
+                acc[r] = fmaf(wv.z, xv.z, acc[r]); acc[r] = fmaf(wv.w, xv.w, acc[r]);
+            }
         }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const float s = warp_sum(acc[r]);
+        if (lane == 0 && b0 + r < B) y[(long long)(b0 + r) * N + n] = apply_act(s + bn, act);
+    }
+}
+
+// SPADE's first conv (normalization_layer.py:13,21): Conv2d(3 -> 128, k3, p1) + LeakyReLU(0.2) on the resized start frame,
+// written as the fp16 (hi, lo) split the gamma|beta conv consumes.  K = 27: as an implicit GEMM it is all overhead (the
+// SIMT engine ran it at 6 TFLOP/s, 220 us per 64x64 block at B = 64).  Here a lane keeps the 27 x 4 weights of its 4
+// output channels in registers, a warp owns a voxel (128 channels = one 256-byte row of each output word), the CTA's
+// input patch sits in shared memory and is read as broadcasts: 108 FMAs per 27 shared loads, FMA-bound.
+// Summation order = the SIMT engine's (taps outer, input channels inner, one fp32 FMA chain), so both produce the same bits.
+constexpr int SP_TILE = 64;      // voxels per CTA
+__global__ void __launch_bounds__(256) spade_conv3_kernel(const float* __restrict__ img, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, __half* __restrict__ y_hi,
+                                                          __half* __restrict__ y_lo, float scale, int H, int W, int act) {
+    __shared__ float in_s[3 * (SP_TILE + 2) * 3 + 8];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int b = blockIdx.y;
+    const int HW = H * W;
+    const int tile_v = HW < SP_TILE ? HW : SP_TILE;
+    const int v0 = blockIdx.x * tile_v;
+    // patch: a segment of one row (W >= tile_v) or tile_v / W whole rows
+    const int cols = W >= tile_v ? tile_v : W, rows = tile_v / cols;
+    const int h0 = v0 / W, w0 = v0 - h0 * W;
+    const int pc = cols + 2, pr = rows + 2;
+    for (int i = threadIdx.x; i < pr * pc * 3; i += blockDim.x) {
+        const int ch = i % 3, c = (i / 3) % pc, r = i / (3 * pc);
+        const int hh = h0 - 1 + r, ww = w0 - 1 + c;
+        in_s[i] = ((unsigned)hh < (unsigned)H && (unsigned)ww < (unsigned)W) ? __ldg(img + (((long long)b * H + hh) * W + ww) * 3 + ch) : 0.f;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n = lane * 4;
+    float wreg[9][4][3];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) wreg[tap][q][c] = __ldg(w + ((long long)tap * 128 + n + q) * 3 + c);
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
+    __syncthreads();
+    for (int j = warp; j < tile_v; j += 8) {
+        const int r = j / cols, c = j - r * cols;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int dh = 0; dh < 3; ++dh)
+#pragma unroll
+            for (int dw = 0; dw < 3; ++dw) {
+                const float* xp = in_s + ((r + dh) * pc + c + dw) * 3;
+                const float x0 = xp[0], x1 = xp[1], x2 = xp[2];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    acc[q] = fmaf(x0, wreg[dh * 3 + dw][q][0], acc[q]);
+                    acc[q] = fmaf(x1, wreg[dh * 3 + dw][q][1], acc[q]);
+                    acc[q] = fmaf(x2, wreg[dh * 3 + dw][q][2], acc[q]);
+                }
+            }
+        const float f[4] = {apply_act(acc[0] + b4.x, act) * scale, apply_act(acc[1] + b4.y, act) * scale,
+                            apply_act(acc[2] + b4.z, act) * scale, apply_act(acc[3] + b4.w, act) * scale};
+        __half hh[4], ll[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { hh[q] = __float2half_rn(f[q]); ll[q] = __float2half_rn(f[q] - __half2float(hh[q])); }
+        const long long o = ((long long)b * HW + v0 + j) * 128 + n;
+        *reinterpret_cast<uint2*>(y_hi + o) = *reinterpret_cast<const uint2*>(hh);
+        *reinterpret_cast<uint2*>(y_lo + o) = *reinterpret_cast<const uint2*>(ll);
     }
 }
 
@@ -100,7 +168,19 @@ int launch_linear(const float* x, const float* w, const float* bias, float* y, i
                   cudaStream_t stream) {
     I2V_REQUIRE(K % 4 == 0, "linear: K=%d must be a multiple of 4", K);
     ProfScope ps(PROF_OTHER, 2.0 * (double)B * K * N, 4.0 * ((double)K * N + (double)B * (K + N)), stream);
-    I2V_CHECK_CUDA(launch_k(linear_kernel, dim3(ceil_div((long long)N * 32, 256)), dim3(256), 0, stream, x, w, bias, y, B, K, N, act));
+    const long long warps = (long long)N * ((B + 7) / 8);
+    I2V_CHECK_CUDA(launch_k(linear_kernel, dim3(ceil_div(warps * 32, 256)), dim3(256), 0, stream, x, w, bias, y, B, K, N, act));
+    return 0;
+}
+
+int launch_spade_conv3(const float* img, const float* w, const float* bias, __half* y_hi, __half* y_lo, float split_scale, int B,
+                       int H, int W, int act, cudaStream_t stream) {
+    const int HW = H * W, tile_v = HW < SP_TILE ? HW : SP_TILE;
+    I2V_REQUIRE(HW % tile_v == 0 && (W >= tile_v ? W % tile_v == 0 : tile_v % W == 0) && B < 65536,
+                "spade_conv3: plane %dx%d does not tile into %d-voxel patches", H, W, tile_v);
+    const double M = (double)B * HW;
+    ProfScope ps(PROF_CONV_SIMT, 2.0 * M * 128 * 27, 4.0 * (M * 3 + M * 128 + 27.0 * 128), stream);
+    I2V_CHECK_CUDA(launch_k(spade_conv3_kernel, dim3(HW / tile_v, B), dim3(256), 0, stream, img, w, bias, y_hi, y_lo, split_scale, H, W, act));
     return 0;
 }
 

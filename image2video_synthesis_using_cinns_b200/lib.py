@@ -107,6 +107,7 @@ SIGNATURES = {
     "i2v_encoder3d_forward": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _SZ, _P]),
     "i2v_encoder3d_destroy": (None, [_P]),
     "i2v_op_conv": (_I, [_P] * 5 + [_I] * 21 + [_P]),
+    "i2v_op_spade_conv3": (_I, [_P] * 5 + [_F, _I, _I, _I, _I, _P]),
     "i2v_op_conv_tc": (_I, [_P] * 5 + [_I] * 17 + [_F, _F, _P, _SZ, _P]),
     "i2v_op_conv_tc_side": (_I, [_P] * 6 + [_I] * 12 + [_F, _F, _P, _SZ, _P]),
     "i2v_debug_conv_tc_timestamps": (_I, [_P, _I]),

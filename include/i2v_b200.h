@@ -118,6 +118,10 @@ int i2v_op_conv(const float* dev_x, const float* dev_w, const float* dev_bias, c
                 int B, int Ti, int Hi, int Wi, int Cin, int Cout, int kt, int kh, int kw, int st, int sh, int sw,
                 int pt, int ph, int pw, int res_ut, int res_uh, int res_uw, int act, int out_mode, int engine,
                 void* stream);
+/* SPADE's Conv2d(3 -> 128, k3, p1) + act (normalization_layer.py:13,21) on img [B,H,W,3], weights [9,128,3]; result as the
+ * fp16 split hi = fp16(s*v), lo = fp16(s*v - hi), each [B,H,W,128] */
+int i2v_op_spade_conv3(const float* dev_img, const float* dev_w, const float* dev_bias, void* dev_y_hi, void* dev_y_lo,
+                       float split_scale, int B, int H, int W, int act, void* stream);
 /* tensor-core conv on fp32 inputs: splits x (scale_a) and w (scale_w; [taps,cout_pad,Cin], rows >= Cout zero) into
  * fp16 (hi, lo) inside the workspace (>= 4*(|x|+|w|)+2048 bytes), then runs the tcgen05 engine; terms 3 or 1;
  * variant 0 = auto, 1 = per-tap box kernel, 2 = 256-row H-halo kernel without kw stacking, 3 = H-halo kernel with the three

@@ -48,6 +48,16 @@ def conv(x_cl, w_taps, bias, res_cl, k, stride, pad, res_up=(1, 1, 1), act=0, ou
     return y
 
 
+def spade_conv3(img_cl, w_taps, bias, scale, act=2):
+    """img_cl [B,H,W,3], w_taps [9,128,3] -> (hi, lo) fp16 [B,H,W,128]"""
+    L = _lib.load()
+    B, H, W, _ = img_cl.shape
+    hi = torch.empty(B, H, W, 128, dtype=torch.float16, device="cuda")
+    lo = torch.empty_like(hi)
+    _lib.check(L.i2v_op_spade_conv3(P(img_cl), P(w_taps), P(bias), P(hi), P(lo), float(scale), B, H, W, act, S()), "op_spade_conv3")
+    return hi, lo
+
+
 def channel_stats(x_cl):
     L = _lib.load()
     B, C = x_cl.shape[0], x_cl.shape[-1]

@@ -131,6 +131,11 @@ def test_linear_resize_maxpool():
     assert rel_inf(ou.linear(x.cuda(), w.cuda(), b.cuda()).cpu(), F.linear(x, w, b)) < 1e-5
     x, w = torch.randn(19, 8192, generator=g), torch.randn(128, 8192, generator=g) * 0.01
     assert rel_inf(ou.linear(x.cuda(), w.cuda(), None).cpu(), F.linear(x, w)) < 1e-5
+    # the shapes launch_linear meets on the path: the flow's conditioning GEMM, AdaIN / fc widths, the control=True embedding
+    # width (160), ragged batch and feature counts, the embedder fc and conv_mu|var (deep K, few features)
+    for B_, K_, N_ in ((64, 64, 40960), (7, 128, 1000), (3, 160, 513), (200, 64, 256), (64, 2048, 64), (1, 8192, 128)):
+        x, w, b = torch.randn(B_, K_, generator=g), torch.randn(N_, K_, generator=g) * 0.05, torch.randn(N_, generator=g)
+        assert rel_inf(ou.linear(x.cuda(), w.cuda(), b.cuda()).cpu(), F.linear(x.double(), w.double(), b.double())) < 1e-5
     img = torch.rand(3, 3, 64, 64, generator=g) * 2 - 1
     for s in (4, 8, 16, 32, 64):
         want = F.interpolate(img, size=(s, s), mode="bilinear", align_corners=True)
@@ -173,3 +178,21 @@ def test_modulate_split_second_result_shares_the_read():
     assert torch.equal(hi, w16.half()) and torch.equal(lo, (w16 - w16.half().float()).half())
     b16 = ou.modulate(x, coef_b, (T, H, W), act=0) * 16.0
     assert torch.equal(hb, b16.half()) and torch.equal(lb, (b16 - b16.half().float()).half())
+
+
+@pytest.mark.parametrize("B,H,W", [(3, 4, 4), (2, 8, 8), (2, 16, 16), (2, 32, 32), (2, 64, 64), (1, 128, 128)])
+def test_spade_conv3_equals_simt_engine(B, H, W):
+    """The dedicated 3->128 SPADE conv (misc.cu) keeps the SIMT engine's summation order: same bits after the split."""
+    g = G(60 + H)
+    img = torch.rand(B, H, W, 3, generator=g) * 2 - 1
+    w = torch.randn(9, 128, 3, generator=g) * 0.2
+    b = torch.randn(128, generator=g) * 0.1
+    scale = 64.0
+    hi, lo = ou.spade_conv3(img.cuda(), w.cuda(), b.cuda(), scale, act=2)
+    y = ou.conv(img.cuda().view(B, 1, H, W, 3), w.cuda(), b.cuda(), None, (1, 3, 3), (1, 1, 1), (0, 1, 1), act=2).view(B, H, W, 128)
+    f = y * scale
+    want_hi = f.half()
+    want_lo = (f - want_hi.float()).half()
+    assert torch.equal(hi, want_hi) and torch.equal(lo, want_lo)
+    ref = F.leaky_relu(F.conv2d(img.permute(0, 3, 1, 2).double(), w.view(3, 3, 128, 3).permute(2, 3, 0, 1).double(), b.double(), padding=1), 0.2)
+    assert rel_inf(((hi.double() + lo.double()) / scale).permute(0, 3, 1, 2).cpu(), ref) < 1e-5
