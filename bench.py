@@ -18,7 +18,8 @@ One JSON line is printed by rank 0:
              / their summed CUDA-event time over K more steps run with events around every launch
              (same sampler window as the value), against the measured peak in MEASURED_PEAKS.json
   cpu_baseline  the oracle port (oracle/oracle_torch.py, = the reference's PyTorch arithmetic) timed on
-             the host cores on a bounded sample (rank 0, N=1 only)
+             the host cores on a bounded sample (3 calls on 8 start frames of the batch; rank 0, N=1 only) at the
+             fastest of a few tuned thread counts (`cores`)
 """
 from __future__ import annotations
 
@@ -126,25 +127,61 @@ def conv_flops_per_sample(dataset):
     return {"bair": 384.8e9, "iper": 384.8e9}.get(dataset, 137.4e9)
 
 
-def cpu_reference_rate(args, mp, n_calls=3, warm=1):
-    """The reference's arithmetic (oracle port) on the host cores: B=1 calls, bounded sample."""
+def _host_cpus():
+    """CPUs this process may really use: affinity mask, capped by the cgroup CPU quota when there is one."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(-(-int(quota) // int(period)))))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
+def cpu_reference_rate(args, mp, n_calls=3, warm=1, sample_batch=8):
+    """The reference's arithmetic (oracle port) on the host cores, bounded sample of the benchmark batch.
+
+    The thread count is tuned first on B=1 calls (ascending candidates, stop once it gets slower): all logical CPUs is
+    not the fastest setting for this model -- 128 threads on the GPU box ran a B=1 call in 31 s against 1.5 s on 8 --
+    and the baseline should be the CPU's best.  `cores` in the result is the thread count used."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_torch as ot     # CPU baseline leg only
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    avail = _host_cpus()
     om = ot.OracleModel(mp, args.seq_length, transfer=False)
     img = om.opt["Data"]["img_size"]
-    x0, residual = make_inputs(1, img, om.z_dim)
+    x1, r1 = make_inputs(1, img, om.z_dim)
+
+    def timed(x, r):
+        t0 = time.perf_counter()
+        out = om.forward(x, r, batch_slice=False)
+        return time.perf_counter() - t0, out
+
+    best_t, best_n, worse = None, None, 0
+    for n in sorted({c for c in (4, 8, 16, 32, 64, 128, avail) if c <= avail} | {min(avail, 4)}):
+        torch.set_num_threads(n)
+        timed(x1, r1)                       # first call at a thread count pays primitive creation
+        dt, _ = timed(x1, r1)
+        if best_t is None or dt < best_t:
+            best_t, best_n, worse = dt, n, 0
+        else:
+            worse += 1
+            if worse >= 2 or dt > 3 * best_t:
+                break
+    torch.set_num_threads(best_n)
+    xb, rb = make_inputs(sample_batch, img, om.z_dim)
     times = []
     for i in range(warm + n_calls):
-        t0 = time.perf_counter()
-        out = om.forward(x0, residual, batch_slice=False)
-        dt = time.perf_counter() - t0
+        dt, out = timed(xb, rb)
         if i >= warm:
             times.append(dt)
     frames = out.shape[0] * out.shape[1]
     med = sorted(times)[len(times) // 2]
-    return frames / med, cores, f"{n_calls} x Model.forward(B=1, {args.dataset} {img}x{img}, seq {args.seq_length}) after {warm} warm-up, median"
+    return frames / med, best_n, (f"{n_calls} x Model.forward(B={sample_batch} of the benchmark batch, {args.dataset} {img}x{img}, seq {args.seq_length}) "
+                                  f"after {warm} warm-up, median; {best_n} threads = fastest of the tuned counts on {avail} usable CPUs")
 
 
 # ------------------------------------------------------------------------------------------ reference arm
@@ -159,9 +196,9 @@ def run_reference(args):
     img = DATASETS[args.dataset]["img_size"]
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1000.0 * 16 / fps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1000.0 * 8 * 16 / fps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic start frames, random-init weights (reference checkpoint format)",
-        "config": {"workload": f"{args.dataset.upper()} {img}x{img} seq_length={args.seq_length}, batch=1 per call on host cores "
+        "config": {"workload": f"{args.dataset.upper()} {img}x{img} seq_length={args.seq_length}, batch=8 per call (a slice of the benchmark batch) on host cores "
                                "(reference PyTorch arithmetic = oracle port; the Python reference tree cannot travel to the GPU box)"},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
