@@ -86,7 +86,7 @@ class Model:
         x_0 = x_0.to(self.device, torch.float32)
         if residual is None:
             residual = torch.randn(x_0.size(0), self.z_dim)                                   # CPU RNG (Q5)
-        z = self.flow(residual.to(self.device), [x_0, cond], reverse=True).view(x_0.size(0), -1)
+        z = self.flow(residual.to(self.device), [x_0, cond], reverse=True).view(x_0.size(0), self.z_dim)
         seq = self._render(x_0, z)
         return (seq, z) if return_latent else seq
 
@@ -106,6 +106,6 @@ class Model:
         _, z, _ = self.encoder(seq_query[:, 1:].transpose(1, 2))                              # get_model.py:87
         res, logdet = self.flow(z, [seq_query[:, 0]])                                         # get_model.py:90
         res = res.view(z.size(0), -1).repeat(x_0.size(0), 1)
-        z_ref = self.flow(res, [x_0], reverse=True).view(x_0.size(0), -1)                     # get_model.py:93
+        z_ref = self.flow(res, [x_0], reverse=True).view(x_0.size(0), self.z_dim)                     # get_model.py:93
         seq = self._render(x_0, z_ref)
         return (seq, z_ref, z, res, logdet) if return_latent else seq

@@ -221,7 +221,7 @@ class Generator(_Native):
 
     def forward(self, img, motion, out=None):
         img = _f32c(img, self.device)
-        z = _f32c(motion.reshape(motion.shape[0], -1), self.device)
+        z = _f32c(motion.reshape(motion.shape[0], self.z_dim), self.device)
         B, _, H, W = img.shape
         if H != self.size or W != self.size:
             raise ValueError(f"decoder geometry renders {self.size}x{self.size} frames, start frame is {H}x{W}")
@@ -319,7 +319,7 @@ class SupervisedTransformer:
         return out.to(self.flow.device)
 
     def embed(self, cond):
-        e = self.embedder.encode(cond[0]).mode().reshape(cond[0].size(0), -1)
+        e = self.embedder.encode(cond[0]).mode().reshape(cond[0].size(0), self.embedder.z_dim)   # INN.py:62 (B, -1)
         if self.control:
             e = torch.cat((e, self.embed_pos(cond[1])), dim=1)
         return e

@@ -123,3 +123,24 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(lib, "LIB_PATH", "/nonexistent/libi2v_b200.so")
     with pytest.raises(RuntimeError, match="no CPU"):
         lib.load()
+
+
+def test_empty_and_ragged_batches(ckpt_cache):
+    """Edge cases of the batch dimension: no start frames, one start frame, a ragged last micro-batch."""
+    mp = ckpt_cache(dataset="bair", seed=4, nf=16, n_flows=2, with_encoder=False)
+    m = _model(mp, 16, False, micro_batch=2)
+    g = torch.Generator().manual_seed(12)
+    x0 = torch.rand(5, 3, 64, 64, generator=g) * 2 - 1
+    z = torch.randn(5, 64, generator=g)
+    out = m.sample(x0[:0])
+    assert out.shape == (0, 16, 3, 64, 64)
+    assert m.flow.embedder.encode(x0[:0].cuda()).mode().shape == (0, 64)
+    full = m.decoder(x0.cuda(), z.cuda())               # micro-batches of 2, 2, 1
+    assert full.shape == (5, 16, 3, 64, 64) and torch.isfinite(full).all()
+    for i in (0, 4):
+        # samples never mix (per-sample norms only): the batch a sample is rendered in must not matter beyond the
+        # summation order of the double-precision statistics atomics
+        one = m.decoder(x0[i:i + 1].cuda(), z[i:i + 1].cuda())
+        assert rel_inf(one[0].cpu(), full[i].cpu()) < 1e-6
+    big = _model(mp, 16, False, micro_batch=64)
+    assert rel_inf(big.decoder(x0.cuda(), z.cuda()).cpu(), full.cpu()) < 1e-6
