@@ -18,10 +18,12 @@
 // hi*hi + hi*lo + lo*hi in fp32 TMEM: 22 significand bits per operand at 3 kind::f16 MMAs, i.e. 1.5x the
 // cost of one TF32 pass and half the cost of 3xTF32.  (`terms`=1 keeps only hi*hi: fp16-grade fast mode.)
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
-// warps 2..5 = epilogue (tcgen05.ld -> scale, bias, residual through the nearest-upsample map,
-// activation -> global).  smem full/empty mbarrier ring between producer and MMA, one tmem_full barrier
-// between MMA and epilogue.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
+// warps 2..9 = epilogue, two per TMEM lane quarter (tcgen05.ld -> transpose through shared memory -> scale, bias,
+// residual through the nearest-upsample map, activation, per-(sample, channel) statistics -> global).  smem full/empty
+// mbarrier ring between producer and MMA, a tmem_full barrier between MMA and epilogue; the halo kernel
+// (conv_tc_halo_kernel, the one that carries the decoder) walks its tiles persistently and adds an epi_done barrier
+// that hands TMEM and the transpose tiles back to the MMA issuer and the producer.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
