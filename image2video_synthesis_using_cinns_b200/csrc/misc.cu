@@ -1,6 +1,8 @@
 // Small ops of the path: nn.Linear, bilinear start-frame resize, max-pool.
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "prof.h"
@@ -17,7 +19,7 @@ namespace {
 // the batch in shared memory was measured slower for the shallow-K shapes: 91 us vs 27 for AdaIN's Linear.)
 __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                      const float* __restrict__ bias, float* __restrict__ y, int B,
-                                                     int K, int N, int act) {
+                                                     int K, int N, int act, int bfly) {
     pdl_launch_dependents();
     pdl_wait();
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -40,6 +42,28 @@ __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x
                 acc[r] = fmaf(wv.z, xv.z, acc[r]); acc[r] = fmaf(wv.w, xv.w, acc[r]);
             }
         }
+    }
+    if (bfly) {
+        // transpose-reduce: 9 shuffles instead of 8 x 5.  After the three exchange steps a lane holds ONE row's partial sum
+        // (row = bits 4,3,2 of the lane index), the last two steps fold the lanes that share a row.
+        const bool u16 = (lane & 16) != 0, u8 = (lane & 8) != 0, u4 = (lane & 4) != 0;
+        float t[4], u[2];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const float recv = __shfl_xor_sync(0xffffffffu, u16 ? acc[r] : acc[r + 4], 16);
+            t[r] = (u16 ? acc[r + 4] : acc[r]) + recv;
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const float recv = __shfl_xor_sync(0xffffffffu, u8 ? t[r] : t[r + 2], 8);
+            u[r] = (u8 ? t[r + 2] : t[r]) + recv;
+        }
+        float v = (u4 ? u[1] : u[0]) + __shfl_xor_sync(0xffffffffu, u4 ? u[0] : u[1], 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        const int r = (u16 ? 4 : 0) + (u8 ? 2 : 0) + (u4 ? 1 : 0);
+        if ((lane & 3) == 0 && b0 + r < B) y[(long long)(b0 + r) * N + n] = apply_act(v + bn, act);
+        return;
     }
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
@@ -169,7 +193,8 @@ int launch_linear(const float* x, const float* w, const float* bias, float* y, i
     I2V_REQUIRE(K % 4 == 0, "linear: K=%d must be a multiple of 4", K);
     ProfScope ps(PROF_OTHER, 2.0 * (double)B * K * N, 4.0 * ((double)K * N + (double)B * (K + N)), stream);
     const long long warps = (long long)N * ((B + 7) / 8);
-    I2V_CHECK_CUDA(launch_k(linear_kernel, dim3(ceil_div(warps * 32, 256)), dim3(256), 0, stream, x, w, bias, y, B, K, N, act));
+    static const int bfly = getenv("I2V_LINEAR_BFLY") != nullptr ? atoi(getenv("I2V_LINEAR_BFLY")) : 1;   // A/B switch (0: 8 x warp_sum)
+    I2V_CHECK_CUDA(launch_k(linear_kernel, dim3(ceil_div(warps * 32, 256)), dim3(256), 0, stream, x, w, bias, y, B, K, N, act, bfly));
     return 0;
 }
 
