@@ -3,7 +3,6 @@
 // it never allocates device memory and never synchronises.
 #include <algorithm>
 #include <cstdarg>
-#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -32,9 +31,14 @@ struct ProfState {
         return pool[pool_used++];
     }
 };
-ProfState g_prof;
+// per host thread: handles are "one per host thread / stream" (include/i2v_b200.h), and events belong to the device
+// that was current when they were created -- a thread profiles the one device it drives
+thread_local ProfState g_prof;
 std::string g_prof_dump_path;
+TuneOptions g_tune;
 }  // namespace
+
+TuneOptions& tune() { return g_tune; }
 
 ProfScope::ProfScope(int cat, double flops, double bytes, cudaStream_t stream) : idx_(-1), stream_(stream) {
     g_prof.launches[cat]++;
@@ -48,14 +52,7 @@ ProfScope::~ProfScope() {
     if (idx_ >= 0) cudaEventRecord(g_prof.recs[idx_].b, stream_);
 }
 
-bool pdl_enabled() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("I2V_PDL");
-        v = (e != nullptr && e[0] == '0') ? 0 : 1;
-    }
-    return v != 0;
-}
+bool pdl_enabled() { return g_tune.pdl != 0; }
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -174,6 +171,7 @@ long long i2v_launch_count(void) {
     for (int c = 0; c < PROF_NCAT; ++c) n += g_prof.launches[c];
     return n;
 }
+int i2v_prof_is_enabled(void) { return g_prof.on ? 1 : 0; }
 void i2v_prof_enable(int on) {
     g_prof.on = on != 0;
     g_prof.recs.clear();
@@ -197,6 +195,22 @@ int i2v_prof_collect(double* ms, double* flops, double* bytes, long long* launch
     return 0;
 }
 void i2v_prof_dump_path(const char* path) { g_prof_dump_path = path ? path : ""; }
+
+int i2v_set_option(const char* name, double value) {
+    I2V_REQUIRE(name != nullptr, "set_option: null name");
+    const std::string k(name);
+    const int v = (int)value;
+    TuneOptions& t = tune();
+    if (k == "pdl") t.pdl = v != 0;
+    else if (k == "tc_flags") t.tc_flags = v;
+    else if (k == "tc_persist") t.tc_persist = v != 0;
+    else if (k == "tc_min_stages") t.tc_min_stages = v < 2 ? 2 : (v > 6 ? 6 : v);
+    else if (k == "tc_pair") t.tc_pair = v != 0;
+    else if (k == "linear_bfly") t.linear_bfly = v != 0;
+    else if (k == "flow_cluster") t.flow_cluster = v != 0;
+    else I2V_REQUIRE(false, "set_option: unknown option '%s'", name);
+    return 0;
+}
 
 i2v_flow* i2v_flow_create(int n_flows, int d, int zc, int hidden, int depth, const unsigned char* cond_mode) {
     if (n_flows <= 0 || n_flows > 64 || d <= 0 || d % 2 || zc <= 0 || zc % 4 || hidden <= 0 || hidden % 4 || hidden > 512 ||
@@ -628,8 +642,8 @@ static int decoder_run(const i2v_decoder* m, const float* img, const float* z, f
             ca.kt = 1; ca.kh = 3; ca.kw = 3; ca.st = ca.sh = ca.sw = 1; ca.pt = 0; ca.ph = ca.pw = 1;
             ca.res_ut = ca.res_uh = ca.res_uw = 1; ca.act = ACT_LRELU02; ca.out_mode = 0;
             ca.y_hi = reinterpret_cast<__half*>(sh); ca.y_lo = ca.y_hi + nsh; ca.split_scale = (float)it->second;
-            // dedicated K = 27 kernel (same bits as the SIMT engine); I2V_SPADE_SIMT=1 keeps the implicit-GEMM path (A/B switch)
-            static const bool spade_simt = getenv("I2V_SPADE_SIMT") != nullptr;
+            // dedicated K = 27 kernel (same bits as the SIMT engine); scalar "opt.spade_simt" keeps the implicit-GEMM path (A/B switch)
+            const bool spade_simt = m->scalars.count("opt.spade_simt") && m->scalars.at("opt.spade_simt") != 0;
             const int hw = Hc * Wc, tv = hw < 64 ? hw : 64;
             const bool tiles = hw % tv == 0 && (Wc >= tv ? Wc % tv == 0 : tv % Wc == 0);
             if (!spade_simt && tiles) I2V_TRY(launch_spade_conv3(imgr, scw, scb, ca.y_hi, ca.y_lo, ca.split_scale, B, Hc, Wc, ACT_LRELU02, s));
@@ -645,7 +659,7 @@ static int decoder_run(const i2v_decoder* m, const float* img, const float* z, f
         const int Ta = phase ? T / 2 : T;                       // stored planes of a0
         const size_t n_a0 = (size_t)B * Ta * Hc * Wc * cin;
         // a block that keeps the resolution runs its learned shortcut inside conv_1 (side input through the centre tap)
-        static const bool no_fuse_s = getenv("I2V_NO_FUSE_S") != nullptr;      // A/B switch (tuning aid)
+        const bool no_fuse_s = m->scalars.count("opt.no_fuse_s") && m->scalars.at("opt.no_fuse_s") != 0;   // A/B switch
         const bool fuse_s = !no_fuse_s && tc && cin != cout && k.ut == 1 && k.uh == 1 && k.uw == 1 && m->tt.has(nm + ".conv_1x.wh") &&
                             conv_tc_side_eligible(Hc, Wc, cmid, cin, (cout + 15) / 16 * 16, eng == 1 ? 3 : 1);
         // ... and its GroupNorm-affine input comes out of the same read of x as a0 (8-channel split path only)
@@ -902,6 +916,27 @@ int i2v_op_conv_tc(const float* x, const float* w, const float* bias, const floa
     a.res_ut = rut; a.res_uh = ruh; a.res_uw = ruw; a.act = act; a.out_mode = out_mode; a.terms = terms; a.variant = variant;
     return launch_conv_tc(a, s);
 }
+int i2v_op_conv_tc_phase(const float* x, const float* w, const float* bias, float* y, int B, int T, int H, int W, int Cin, int Cout,
+                         int cout_pad, int terms, int variant, float scale_a, float scale_w, void* ws, size_t ws_bytes, void* stream) {
+    I2V_REQUIRE(x && w && y && ws, "op_conv_tc_phase: null argument");
+    I2V_REQUIRE(T % 2 == 0, "op_conv_tc_phase: T must be even (x holds T/2 planes)");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t nx = (size_t)B * (T / 2) * H * W * Cin, nw = (size_t)4 * 9 * cout_pad * Cin;
+    Arena ar(ws, ws_bytes, false);
+    __half* xh = ar.take<__half>(nx); __half* xl = ar.take<__half>(nx);
+    __half* wh = ar.take<__half>(nw); __half* wl = ar.take<__half>(nw);
+    float* sc = ar.take<float>(1);
+    I2V_REQUIRE(ar.ok(), "op_conv_tc_phase: workspace too small (%zu needed)", ar.peak);
+    I2V_TRY(launch_split_fp16(x, xh, xl, scale_a, (long long)nx, s));
+    I2V_TRY(launch_split_fp16(w, wh, wl, scale_w, (long long)nw, s));
+    const float inv = 1.f / (scale_a * scale_w);
+    I2V_CHECK_CUDA(cudaMemcpyAsync(sc, &inv, sizeof(float), cudaMemcpyHostToDevice, s));
+    ConvTcArgs a;
+    a.x_hi = xh; a.x_lo = xl; a.w_hi = wh; a.w_lo = wl; a.scale_ptr = sc; a.bias = bias; a.res = nullptr; a.y = y;
+    a.B = B; a.T = T; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.cout_pad = cout_pad; a.kt = 3; a.kh = 3; a.kw = 3;
+    a.res_ut = a.res_uh = a.res_uw = 1; a.act = ACT_NONE; a.out_mode = 0; a.terms = terms; a.variant = variant; a.t_phase = 1;
+    return launch_conv_tc(a, s);
+}
 int i2v_op_conv_tc_side(const float* x, const float* w, const float* x2, const float* w2, const float* bias, float* y, int B, int T,
                         int H, int W, int Cin, int Cin2, int Cout, int cout_pad, int act, int out_mode, int terms, int variant,
                         float scale_a, float scale_w, void* ws, size_t ws_bytes, void* stream) {
@@ -958,6 +993,19 @@ int i2v_op_linear(const float* x, const float* w, const float* bias, float* y, i
 }
 int i2v_op_resize_bilinear(const float* img, float* out, int B, int C, int H0, int W0, int H, int W, void* stream) {
     return launch_resize_bilinear_nchw_to_nhwc(img, out, B, C, H0, W0, H, W, static_cast<cudaStream_t>(stream));
+}
+int i2v_op_preprocess_u8(const unsigned char* img, float* out, int H0, int W0, int H, int W, int bgr, void* stream) {
+    I2V_REQUIRE(img && out, "op_preprocess_u8: null argument");
+    return launch_preprocess_u8(img, out, H0, W0, H, W, bgr, static_cast<cudaStream_t>(stream));
+}
+int i2v_op_frames_max(const float* frames, float* mx, int64_t n, void* stream) {
+    I2V_REQUIRE(frames && mx && n > 0, "op_frames_max: null argument or empty clip");
+    return launch_frames_max(frames, mx, n, static_cast<cudaStream_t>(stream));
+}
+int i2v_op_frames_to_u8(const float* frames, const float* mx, unsigned char* out, int N, int T, int H, int W, int64_t sn, int64_t st,
+                        int64_t sh, void* stream) {
+    I2V_REQUIRE(frames && mx && out && N > 0 && T > 0 && H > 0 && W > 0, "op_frames_to_u8: null argument or empty clip");
+    return launch_frames_to_u8(frames, mx, out, N, T, H, W, sn, st, sh, static_cast<cudaStream_t>(stream));
 }
 int i2v_op_maxpool3x3s2(const float* x, float* y, int B, int H, int W, int C, void* stream) {
     return launch_maxpool3x3s2(x, y, B, H, W, C, static_cast<cudaStream_t>(stream));

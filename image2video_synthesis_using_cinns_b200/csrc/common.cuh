@@ -1,5 +1,6 @@
 // Shared device/host helpers for the sm_100a kernels of the image->video sampling path.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -19,6 +20,16 @@ __device__ __forceinline__ float apply_act(float v, int act) {
         case ACT_TANH: return tanhf(v);                      // decoder.py:118
         default: return v;
     }
+}
+
+// fp16 saturation of the tensor-core engine's operand split: values beyond +-65504 (|x| > 4094 at the activation
+// scale of 16) clip instead of turning into inf and then NaN frames; NaN stays NaN (comparisons are false).
+__device__ __forceinline__ float sat_f16(float f) { return f > 65504.f ? 65504.f : (f < -65504.f ? -65504.f : f); }
+// hi = fp16(f), lo = fp16(f - hi): the error-compensated operand pair (f already carries the split scale)
+__device__ __forceinline__ void split_f16(float f, __half& hi, __half& lo) {
+    f = sat_f16(f);
+    hi = __float2half_rn(f);
+    lo = __float2half_rn(f - __half2float(hi));
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -48,6 +59,19 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device function attribute: set it once per device the
+// process launches on (`done_mask`: one bit per device ordinal, a static at the call site).
+template <class K>
+inline cudaError_t ensure_max_dyn_smem(K kernel, int bytes, unsigned long long& done_mask) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 64 && ((done_mask >> dev) & 1ull)) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && dev < 64) done_mask |= 1ull << dev;
+    return e;
 }
 
 // thread-local error slot surfaced through i2v_last_error()

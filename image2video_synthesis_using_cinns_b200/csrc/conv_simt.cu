@@ -227,10 +227,10 @@ __global__ void __launch_bounds__(NT, 2) conv_simt_kernel(const ConvArgs a) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 if (nbase + j < a.Cout) {
-                    const float f = v[j] * a.split_scale;
-                    const __half hh = __float2half_rn(f);
+                    __half hh, ll;
+                    split_f16(v[j] * a.split_scale, hh, ll);
                     a.y_hi[m * a.Cout + nbase + j] = hh;
-                    a.y_lo[m * a.Cout + nbase + j] = __float2half_rn(f - __half2float(hh));
+                    a.y_lo[m * a.Cout + nbase + j] = ll;
                 }
         } else if (a.out_mode == 0) {
             float* dst = a.y + m * a.Cout + nbase;

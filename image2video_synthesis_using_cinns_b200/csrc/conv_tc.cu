@@ -27,8 +27,6 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
-#include <cstdlib>
-
 #include "common.cuh"
 #include "kernels.h"
 #include "prof.h"
@@ -1020,10 +1018,10 @@ __global__ void split_fp16_kernel(const float* __restrict__ x, __half* __restric
     pdl_launch_dependents();
     pdl_wait();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const float v = x[i] * scale;
-        const __half h = __float2half_rn(v);
+        __half h, l;
+        split_f16(x[i] * scale, h, l);
         hi[i] = h;
-        lo[i] = __float2half_rn(v - __half2float(h));
+        lo[i] = l;
     }
 }
 
@@ -1058,37 +1056,10 @@ int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dim
 
 bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
-// tuning switches of the halo kernel (I2V_TC_FLAGS overrides; bit 0 = residual L2 prefetch)
-int tc_flags() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("I2V_TC_FLAGS");
-        v = e ? atoi(e) : 1;
-    }
-    return v;
-}
-
-// persistent tile loop of the halo kernel (I2V_TC_PERSIST=0 turns it off: A/B switch)
-int tc_persist() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("I2V_TC_PERSIST");
-        v = e ? atoi(e) : 1;
-    }
-    return v;
-}
-
-// pipeline depth the halo kernel aims for when it picks its channel chunk (I2V_TC_MIN_STAGES overrides: tuning aid)
-int tc_min_stages() {
-    static int v = 0;
-    if (v == 0) {
-        const char* e = getenv("I2V_TC_MIN_STAGES");
-        v = e ? atoi(e) : 2;
-        if (v < 2) v = 2;
-        if (v > 6) v = 6;
-    }
-    return v;
-}
+// tuning switches of the halo kernel (i2v_set_option): residual L2 prefetch, persistent tile loop, pipeline depth
+int tc_flags() { return tune().tc_flags; }
+int tc_persist() { return tune().tc_persist; }
+int tc_min_stages() { return tune().tc_min_stages; }
 
 }  // namespace
 
@@ -1283,11 +1254,8 @@ static int launch_conv_tc_halo(const ConvTcArgs& h, cudaStream_t stream) {
         if (int rc = encode_map(&mB2h, h.w2_hi, 5, wd, ws_, wbox, rb)) return rc;
         if (int rc = encode_map(&mB2l, h.terms > 1 ? h.w2_lo : h.w2_hi, 5, wd, ws_, wbox, rb)) return rc;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        I2V_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
-    }
+    static unsigned long long attr_devs = 0;
+    I2V_CHECK_CUDA(ensure_max_dyn_smem(conv_tc_halo_kernel, 227 * 1024, attr_devs));
     // ring + alignment slack + barriers + (stacked form) 2 slots x 4 quarters x 2 edge rows of n_tile floats
     const size_t smem = (size_t)stages * stage_bytes + 1024 + 256 + (wstack ? 16 * (size_t)a.n_tile * sizeof(float) : 0);
     I2V_REQUIRE(smem <= 227 * 1024, "conv_tc: halo kernel shared memory (%zu bytes) over the 227 KB limit", smem);
@@ -1424,11 +1392,8 @@ int launch_conv_tc(const ConvTcArgs& h, cudaStream_t stream) {
         if (int rc = encode_map(&mBh, h.w_hi, 3, dims, st, box, rb)) return rc;
         if (int rc = encode_map(&mBl, h.terms > 1 ? h.w_lo : h.w_hi, 3, dims, st, box, rb)) return rc;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        I2V_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
-    }
+    static unsigned long long attr_devs = 0;
+    I2V_CHECK_CUDA(ensure_max_dyn_smem(conv_tc_kernel, 227 * 1024, attr_devs));
     const long long M = (long long)h.B * h.T * h.H * h.W;
     const double K_ = (double)h.kt * h.kh * h.kw * h.Cin;
     ProfScope ps(PROF_CONV_TC1, 2.0 * (double)M * h.Cout * K_, 4.0 * ((double)M * h.Cin + (double)M * h.Cout + K_ * h.Cout), stream);

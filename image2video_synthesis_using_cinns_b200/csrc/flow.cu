@@ -445,12 +445,9 @@ int launch_flow(const FlowWeights& fw, const float* in, const float* cond, float
     const int n1 = fw.n_flows * 2 * 2 * H;
     if (int rc = launch_linear(cond, fw.w1c, fw.b1, c1, B, fw.zc, n1, ACT_NONE, stream)) return rc;
 
-    static int max_smem_set = 0;
+    static unsigned long long attr_devs = 0;
     const size_t smem_max = 200 * 1024;
-    if (!max_smem_set) {
-        I2V_CHECK_CUDA(cudaFuncSetAttribute(flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-        max_smem_set = 1;
-    }
+    I2V_CHECK_CUDA(ensure_max_dyn_smem(flow_kernel, (int)smem_max, attr_devs));
     int dev = 0, sms = 0;
     I2V_CHECK_CUDA(cudaGetDevice(&dev));
     I2V_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

@@ -6,6 +6,19 @@
 
 namespace i2v {
 
+// Process-wide tuning switches (i2v_set_option; defaults are the measured optima, profiles/*_bench_ab*.txt).  They
+// exist for A/B measurements and never change results beyond summation order.
+struct TuneOptions {
+    int pdl = 1;             // programmatic dependent launch attribute on every kernel
+    int tc_flags = 1;        // halo conv kernel: bit 0 = residual L2 prefetch from the idle epilogue warps
+    int tc_persist = 1;      // halo conv kernel: persistent tile loop (0: one CTA per tile)
+    int tc_min_stages = 2;   // halo conv kernel: pipeline depth aimed for when picking the channel chunk (2..6)
+    int tc_pair = 1;         // halo conv kernel: 2-CTA (cta_group::2) tiles where the layer is eligible
+    int linear_bfly = 1;     // linear kernel: 9-shuffle transpose-reduce (0: 8 x warp_sum)
+    int flow_cluster = 1;    // flow: cluster-resident kernel where eligible (0: cooperative grid-barrier kernel)
+};
+TuneOptions& tune();
+
 // ----------------------------------------------------------------------------- convolution
 struct ConvArgs {
     const float* x;      // [B, Ti, Hi, Wi, Cin]
@@ -103,6 +116,11 @@ int launch_resize_bilinear_nchw_to_nhwc(const float* img, float* out, int B, int
 // (y_hi / y_lo [B,H,W,128]); same bits as launch_conv_simt with y_hi set.  H*W must tile into 64-voxel patches.
 int launch_spade_conv3(const float* img, const float* w, const float* bias, __half* y_hi, __half* y_lo, float split_scale, int B,
                        int H, int W, int act, cudaStream_t stream);
+// CLI pre/post-processing on the device (generate_samples.py:36-41,57-62; utils/auxiliaries.py:15-22,53-55)
+int launch_preprocess_u8(const unsigned char* img_hwc, float* out_chw, int H0, int W0, int H, int W, int bgr, cudaStream_t stream);
+int launch_frames_max(const float* frames, float* mx, long long n, cudaStream_t stream);
+int launch_frames_to_u8(const float* frames, const float* mx, unsigned char* out, int N, int T, int H, int W, long long sn,
+                        long long st, long long sh, cudaStream_t stream);
 // 3x3 stride-2 pad-1 max pool, channels-last [B,H,W,C] -> [B,Ho,Wo,C]
 int launch_maxpool3x3s2(const float* x, float* y, int B, int H, int W, int C, cudaStream_t stream);
 // mean over V from channel sums: y[b,c] = sums[b,c,0] / V

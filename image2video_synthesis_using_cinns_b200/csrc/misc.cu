@@ -1,8 +1,6 @@
 // Small ops of the path: nn.Linear, bilinear start-frame resize, max-pool.
 #include <cuda_fp16.h>
 
-#include <cstdlib>
-
 #include "common.cuh"
 #include "kernels.h"
 #include "prof.h"
@@ -128,7 +126,7 @@ __global__ void __launch_bounds__(256) spade_conv3_kernel(const float* __restric
                             apply_act(acc[2] + b4.z, act) * scale, apply_act(acc[3] + b4.w, act) * scale};
         __half hh[4], ll[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { hh[q] = __float2half_rn(f[q]); ll[q] = __float2half_rn(f[q] - __half2float(hh[q])); }
+        for (int q = 0; q < 4; ++q) split_f16(f[q], hh[q], ll[q]);
         const long long o = ((long long)b * HW + v0 + j) * 128 + n;
         *reinterpret_cast<uint2*>(y_hi + o) = *reinterpret_cast<const uint2*>(hh);
         *reinterpret_cast<uint2*>(y_lo + o) = *reinterpret_cast<const uint2*>(ll);
@@ -186,14 +184,111 @@ __global__ void maxpool3x3s2_kernel(const float* __restrict__ x, float* __restri
     }
 }
 
+// ---- CLI pre/post-processing on the device --------------------------------------------------------------
+// Start frame: cv2.imread's uint8 HWC image -> RGB -> /255 -> Normalize(0.5, 0.5) -> Resize((S, S)) (bilinear,
+// align_corners=False, no antialias: kornia 0.5's Resize is F.interpolate) -> one fp32 CHW slot of the batch tensor
+// (generate_samples.py:36-41).  Source index and weights follow ATen's area_pixel_compute_source_index.
+__global__ void preprocess_u8_kernel(const unsigned char* __restrict__ img, float* __restrict__ out, int H0, int W0, int H, int W,
+                                     float sh, float sw, int bgr) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int n = 3 * H * W;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int w = i % W, h = (i / W) % H, c = i / (W * H);
+        const int cs = bgr ? 2 - c : c;
+        float fy = sh * ((float)h + 0.5f) - 0.5f, fx = sw * ((float)w + 0.5f) - 0.5f;
+        fy = fy < 0.f ? 0.f : fy; fx = fx < 0.f ? 0.f : fx;
+        int y0 = (int)fy, x0 = (int)fx;
+        y0 = min(y0, H0 - 1); x0 = min(x0, W0 - 1);
+        const int y1 = y0 + (y0 < H0 - 1 ? 1 : 0), x1 = x0 + (x0 < W0 - 1 ? 1 : 0);
+        const float ly = fy - (float)y0, lx = fx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
+        auto px = [&](int y, int x) {
+            const float t = __fdiv_rn((float)img[((long long)y * W0 + x) * 3 + cs], 255.f);
+            return __fdiv_rn(__fsub_rn(t, 0.5f), 0.5f);
+        };
+        out[i] = hy * (hx * px(y0, x0) + lx * px(y0, x1)) + ly * (hx * px(y1, x0) + lx * px(y1, x1));
+    }
+}
+
+// max over the clip of denorm(x) = clamp((x + 1) / 2, 0, 1) (utils/auxiliaries.py:53-55): the normaliser of
+// convert_seq2gif (utils/auxiliaries.py:21).  Values are >= 0, so their float bits order like ints.
+__global__ void __launch_bounds__(256) frames_max_kernel(const float* __restrict__ x, float* __restrict__ mx, long long n) {
+    pdl_launch_dependents();
+    pdl_wait();
+    float m = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = __fadd_rn(__ldg(x + i), 1.f) * 0.5f;
+        m = fmaxf(m, fminf(v, 1.f));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(mx), __float_as_int(m));
+}
+
+// frames [N,T,3,H,W] in [-1,1] -> uint8 RGB pixels at out[n*sn + t*st + h*sh + w*3 + c] = trunc(255 * denorm(x) / max)
+// (utils/auxiliaries.py:15-22 + the .astype(np.uint8) of generate_samples.py:61; same fp32 operation order as numpy).
+// Strides select the layout: the GIF canvas [T, H, N*W, 3] (videos side by side) or per-video [N, T, H, W, 3].
+__global__ void __launch_bounds__(256) frames_to_u8_kernel(const float* __restrict__ x, const float* __restrict__ mx,
+                                                           unsigned char* __restrict__ out, int N, int T, int H, int W, long long sn,
+                                                           long long st, long long sh) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const float m = __ldg(mx);
+    const long long HW = (long long)H * W, n_px = (long long)N * T * HW;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_px; i += (long long)gridDim.x * blockDim.x) {
+        const int w = (int)(i % W);
+        long long p = i / W;
+        const int h = (int)(p % H); p /= H;
+        const int t = (int)(p % T);
+        const int n = (int)(p / T);
+        const float* src = x + (((long long)n * T + t) * 3) * HW + (long long)h * W + w;
+        unsigned char* dst = out + n * sn + t * st + h * sh + (long long)w * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float v = __fadd_rn(__ldg(src + c * HW), 1.f) * 0.5f;
+            v = fminf(fmaxf(v, 0.f), 1.f);
+            dst[c] = (unsigned char)(int)__fdiv_rn(__fmul_rn(255.f, v), m);
+        }
+    }
+}
+
 }  // namespace
+
+int launch_preprocess_u8(const unsigned char* img, float* out, int H0, int W0, int H, int W, int bgr, cudaStream_t stream) {
+    I2V_REQUIRE(H0 > 0 && W0 > 0 && H > 0 && W > 0, "preprocess_u8: empty image");
+    // ATen area_pixel_compute_scale (align_corners=False, no explicit scale factor): in / out
+    const float sh = (float)H0 / (float)H, sw = (float)W0 / (float)W;
+    const int n = 3 * H * W;
+    ProfScope ps(PROF_OTHER, 0, 0, stream);
+    I2V_CHECK_CUDA(launch_k(preprocess_u8_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, stream, img, out, H0, W0, H, W, sh, sw, bgr));
+    return 0;
+}
+
+int launch_frames_max(const float* frames, float* mx, long long n, cudaStream_t stream) {
+    I2V_CHECK_CUDA(cudaMemsetAsync(mx, 0, sizeof(float), stream));
+    long long blocks = (n + 255) / 256;
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    ProfScope ps(PROF_OTHER, 0, 4.0 * (double)n, stream);
+    I2V_CHECK_CUDA(launch_k(frames_max_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, frames, mx, n));
+    return 0;
+}
+
+int launch_frames_to_u8(const float* frames, const float* mx, unsigned char* out, int N, int T, int H, int W, long long sn,
+                        long long st, long long sh, cudaStream_t stream) {
+    const long long n_px = (long long)N * T * H * W;
+    long long blocks = (n_px + 255) / 256;
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    ProfScope ps(PROF_OTHER, 0, 15.0 * (double)n_px, stream);
+    I2V_CHECK_CUDA(launch_k(frames_to_u8_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, frames, mx, out, N, T, H, W, sn, st, sh));
+    return 0;
+}
 
 int launch_linear(const float* x, const float* w, const float* bias, float* y, int B, int K, int N, int act,
                   cudaStream_t stream) {
     I2V_REQUIRE(K % 4 == 0, "linear: K=%d must be a multiple of 4", K);
     ProfScope ps(PROF_OTHER, 2.0 * (double)B * K * N, 4.0 * ((double)K * N + (double)B * (K + N)), stream);
     const long long warps = (long long)N * ((B + 7) / 8);
-    static const int bfly = getenv("I2V_LINEAR_BFLY") != nullptr ? atoi(getenv("I2V_LINEAR_BFLY")) : 1;   // A/B switch (0: 8 x warp_sum)
+    const int bfly = tune().linear_bfly;   // A/B switch (0: 8 x warp_sum)
     I2V_CHECK_CUDA(launch_k(linear_kernel, dim3(ceil_div(warps * 32, 256)), dim3(256), 0, stream, x, w, bias, y, B, K, N, act, bfly));
     return 0;
 }

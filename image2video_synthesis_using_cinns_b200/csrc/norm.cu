@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(256) modulate_kernel(const ModArgs a, long lon
             const float f[4] = {o.x * s, o.y * s, o.z * s, o.w * s};
             __half hh[4], ll[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { hh[j] = __float2half_rn(f[j]); ll[j] = __float2half_rn(f[j] - __half2float(hh[j])); }
+            for (int j = 0; j < 4; ++j) split_f16(f[j], hh[j], ll[j]);
             reinterpret_cast<uint2*>(a.out_hi)[i] = *reinterpret_cast<const uint2*>(hh);
             reinterpret_cast<uint2*>(a.out_lo)[i] = *reinterpret_cast<const uint2*>(ll);
             if (a.out_f32 != nullptr) reinterpret_cast<float4*>(a.out_f32)[i] = o;
@@ -219,9 +219,10 @@ __global__ void __launch_bounds__(256) modulate8_split_kernel(const ModArgs a, i
                 if (cf != nullptr) { f0 = fmaf(ca[2 * j], f0, cb[2 * j]); f1 = fmaf(ca[2 * j + 1], f1, cb[2 * j + 1]); }
                 if (gbp != nullptr) { f0 = fmaf(f0, ga[2 * j], gbv[2 * j]); f1 = fmaf(f1, ga[2 * j + 1], gbv[2 * j + 1]); }
                 f0 = apply_act(f0, a.act) * s; f1 = apply_act(f1, a.act) * s;
-                const __half h0 = __float2half_rn(f0), h1 = __float2half_rn(f1);
+                __half h0, h1, l0, l1;
+                split_f16(f0, h0, l0); split_f16(f1, h1, l1);
                 hh[j] = __halves2half2(h0, h1);
-                ll[j] = __halves2half2(__float2half_rn(f0 - __half2float(h0)), __float2half_rn(f1 - __half2float(h1)));
+                ll[j] = __halves2half2(l0, l1);
             }
             for (int r = 0; r < a.ut; ++r) {
                 const long long o = (long long)(ts * a.ut + r) * per_plane + i;
@@ -232,9 +233,10 @@ __global__ void __launch_bounds__(256) modulate8_split_kernel(const ModArgs a, i
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const float f0 = fmaf(c2a[2 * j], v[2 * j], c2b[2 * j]) * s, f1 = fmaf(c2a[2 * j + 1], v[2 * j + 1], c2b[2 * j + 1]) * s;
-                    const __half h0 = __float2half_rn(f0), h1 = __float2half_rn(f1);
+                    __half h0, h1, l0, l1;
+                    split_f16(f0, h0, l0); split_f16(f1, h1, l1);
                     hh[j] = __halves2half2(h0, h1);
-                    ll[j] = __halves2half2(__float2half_rn(f0 - __half2float(h0)), __float2half_rn(f1 - __half2float(h1)));
+                    ll[j] = __halves2half2(l0, l1);
                 }
                 const long long o = (long long)ts * per_plane + i;
                 o2h[o] = *reinterpret_cast<const uint4*>(hh);
@@ -284,9 +286,10 @@ __global__ void __launch_bounds__(256) modulate8_split_plane_kernel(const ModArg
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float f0 = apply_act(v[2 * j], a.act) * s, f1 = apply_act(v[2 * j + 1], a.act) * s;
-            const __half h0 = __float2half_rn(f0), h1 = __float2half_rn(f1);
+            __half h0, h1, l0, l1;
+            split_f16(f0, h0, l0); split_f16(f1, h1, l1);
             hh[j] = __halves2half2(h0, h1);
-            ll[j] = __halves2half2(__float2half_rn(f0 - __half2float(h0)), __float2half_rn(f1 - __half2float(h1)));
+            ll[j] = __halves2half2(l0, l1);
         }
         oh[i] = *reinterpret_cast<const uint4*>(hh);
         ol[i] = *reinterpret_cast<const uint4*>(ll);

@@ -31,9 +31,11 @@ def _load_state(path):
 class Model:
     """``Model(model_path, vid_length, transfer=False)`` as in the reference; extra keyword-only knobs
     select the device, the decoder micro-batch and the decoder's conv engine (1 = tcgen05 tensor cores with
-    the error-compensated fp16 split, fp32-grade parity, default; 0 = fp32 SIMT; 2 = single fp16 product)."""
+    the error-compensated fp16 split, fp32-grade parity, default; 0 = fp32 SIMT; 2 = single fp16 product);
+    ``graph=True`` replays the embedder and each decoder micro-batch from CUDA graphs (small, launch-bound batches)."""
 
-    def __init__(self, model_path, vid_length, transfer=False, *, device="cuda", micro_batch=32, conv_engine=1, streams=1):
+    def __init__(self, model_path, vid_length, transfer=False, *, device="cuda", micro_batch=32, conv_engine=1, streams=1,
+                 graph=False):
         opt = load_yaml(model_path + "config_stage2.yaml")                                   # get_model.py:15
         fs = opt.First_stage_model
         path_stage1 = fs["model_path"] + fs["model_name"] + "/"                              # get_model.py:16
@@ -42,7 +44,7 @@ class Model:
 
         self.decoder = modules.Generator(_load_state(path_stage1 + fs["checkpoint_decoder"] + ".pth"),
                                          config.Decoder, device=device, conv_engine=conv_engine,
-                                         micro_batch=micro_batch, streams=streams)                             # get_model.py:22-24
+                                         micro_batch=micro_batch, streams=streams, graph=graph)                # get_model.py:22-24
         if transfer:
             self.encoder = modules.Encoder(_load_state(path_stage1 + fs["checkpoint_encoder"] + ".pth.tar"),
                                            config.Encoder, device=device)                     # get_model.py:27-31
@@ -54,7 +56,7 @@ class Model:
         ae_path = cm["model_path"] + cm["model_name"] + "/"                                   # INN.py:37
         ae_cfg = load_yaml(ae_path + "config_stage2_AE.yaml")
         embedder = modules.ResnetEncoder(_load_state(ae_path + cm["checkpoint_name"] + ".pth"), ae_cfg.AE,
-                                         device=device)                                       # INN.py:39-41
+                                         device=device, graph=graph)                          # INN.py:39-41
         flow = modules.ConditionalFlow(_load_state(model_path + "cINN.pth"), in_channels=z_dim,
                                        embedding_dim=cm["z_dim"] + (30 if control else 0), hidden_dim=hidden,
                                        hidden_depth=opt.Flow["flow_hidden_depth"], n_flows=opt.Flow["n_flows"],

@@ -81,8 +81,10 @@ SIGNATURES = {
     "i2v_last_error": (_c.c_char_p, []),
     "i2v_launch_count": (_c.c_longlong, []),
     "i2v_prof_enable": (None, [_I]),
+    "i2v_prof_is_enabled": (_I, []),
     "i2v_prof_collect": (_I, [_P, _P, _P, _P]),
     "i2v_prof_dump_path": (None, [_c.c_char_p]),
+    "i2v_set_option": (_I, [_c.c_char_p, _c.c_double]),
     "i2v_flow_create": (_P, [_I, _I, _I, _I, _I, _P]),
     "i2v_flow_set_tensor": (_I, [_P, _c.c_char_p, _P, _SZ]),
     "i2v_flow_workspace_bytes": (_SZ, [_P, _I]),
@@ -109,6 +111,7 @@ SIGNATURES = {
     "i2v_op_conv": (_I, [_P] * 5 + [_I] * 21 + [_P]),
     "i2v_op_spade_conv3": (_I, [_P] * 5 + [_F, _I, _I, _I, _I, _P]),
     "i2v_op_conv_tc": (_I, [_P] * 5 + [_I] * 17 + [_F, _F, _P, _SZ, _P]),
+    "i2v_op_conv_tc_phase": (_I, [_P] * 4 + [_I] * 9 + [_F, _F, _P, _SZ, _P]),
     "i2v_op_conv_tc_side": (_I, [_P] * 6 + [_I] * 12 + [_F, _F, _P, _SZ, _P]),
     "i2v_debug_conv_tc_timestamps": (_I, [_P, _I]),
     "i2v_debug_flow_timestamps": (_I, [_P]),
@@ -119,6 +122,9 @@ SIGNATURES = {
     "i2v_op_linear": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "i2v_op_resize_bilinear": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "i2v_op_maxpool3x3s2": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "i2v_op_preprocess_u8": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "i2v_op_frames_max": (_I, [_P, _P, _I64, _P]),
+    "i2v_op_frames_to_u8": (_I, [_P, _P, _P, _I, _I, _I, _I, _I64, _I64, _I64, _P]),
 }
 
 
@@ -139,6 +145,11 @@ def load():
         raise RuntimeError("libi2v_b200.so ABI version mismatch")
     _lib = lib
     return lib
+
+
+def set_option(name: str, value: float):
+    """Process-wide tuning switch (i2v_set_option): A/B measurements only."""
+    check(load().i2v_set_option(name.encode(), float(value)), f"set_option({name})")
 
 
 def check(rc: int, what: str = "i2v"):

@@ -16,7 +16,6 @@ CUDA device or without the built library raises.
 from __future__ import annotations
 
 import ctypes
-import os
 
 import numpy as np
 import torch
@@ -29,8 +28,9 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
-def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None):
+    """The caller's current stream ON `device` (not on whatever device happens to be current)."""
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def _f32c(t, device):
@@ -55,6 +55,14 @@ class _Native:
         self._tensors = {}
         self._ws = None
 
+    def _guard(self):
+        """Every native call runs with this handle's device current: the library reads cudaGetDevice() for its
+        per-device function attributes, and the stream handed over must belong to the same device as the pointers."""
+        return torch.cuda.device(self.device)
+
+    def _stream(self):
+        return _stream(self.device)
+
     def _register(self, set_fn, tensors):
         for name, t in tensors.items():
             t = t.to(self.device).contiguous()
@@ -68,6 +76,35 @@ class _Native:
             self._ws = None
             self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
         return self._ws
+
+    # ---- CUDA-graph replay of one native call (launch-bound small batches: the scripts' -bs 6 and B = 1) -------------
+    # The path is ~280 kernel launches per pass, each with host-side argument checks and TMA descriptor encoding; at
+    # B = 64 the device hides that, at B <= 6 the host does not keep up.  `_graphed` captures the launches of one call
+    # on fixed-address buffers once per shape and replays them; inputs are copied in, the result copied out.
+    graph = False
+    graph_replays = 0          # replays so far
+    graph_kernels = 0          # kernels replayed so far (they bypass i2v_launch_count)
+
+    def _graphed(self, key, shapes_in, shape_out, call):
+        """`call(*static_inputs, static_out, workspace_bytes_fn -> ws, stream)` is captured once per `key`."""
+        if not hasattr(self, "_graphs"):
+            self._graphs = {}
+        ent = self._graphs.get(key)
+        if ent is None:
+            ins = [torch.empty(sh, dtype=torch.float32, device=self.device) for sh in shapes_in]
+            for t in ins:
+                t.zero_()
+            out = torch.empty(shape_out, dtype=torch.float32, device=self.device)
+            holder = {}
+            call(*ins, out, holder, self._stream())                  # eager warm-up: lazy initialisation happens here
+            torch.cuda.current_stream(self.device).synchronize()
+            g = torch.cuda.CUDAGraph()
+            n0 = self.L.i2v_launch_count()
+            with torch.cuda.graph(g):
+                call(*ins, out, holder, self._stream())
+            ent = (g, ins, out, holder, self.L.i2v_launch_count() - n0)
+            self._graphs[key] = ent
+        return ent
 
     def weight_bytes(self):
         return sum(t.numel() * t.element_size() for t in self._tensors.values())
@@ -117,15 +154,16 @@ class ConditionalFlow(_Native):
             out = x2.new_zeros(0, self.in_channels, 1, 1)
             return out if reverse else (out, x2.new_zeros(0))
         cond = self._cond(embedding)
-        ws = self._workspace(self.L.i2v_flow_workspace_bytes(self.h, B))
-        out = torch.empty_like(x2)
-        if reverse:
-            _lib.check(self.L.i2v_flow_reverse(self.h, _ptr(x2), _ptr(cond), _ptr(out), B, _ptr(ws), ws.numel(),
-                                               _stream()), "flow_reverse")
-            return out[:, :, None, None]
-        logdet = torch.empty(B, dtype=torch.float32, device=self.device)
-        _lib.check(self.L.i2v_flow_forward(self.h, _ptr(x2), _ptr(cond), _ptr(out), _ptr(logdet), B, _ptr(ws),
-                                           ws.numel(), _stream()), "flow_forward")
+        with self._guard():
+            ws = self._workspace(self.L.i2v_flow_workspace_bytes(self.h, B))
+            out = torch.empty_like(x2)
+            if reverse:
+                _lib.check(self.L.i2v_flow_reverse(self.h, _ptr(x2), _ptr(cond), _ptr(out), B, _ptr(ws), ws.numel(),
+                                                   self._stream()), "flow_reverse")
+                return out[:, :, None, None]
+            logdet = torch.empty(B, dtype=torch.float32, device=self.device)
+            _lib.check(self.L.i2v_flow_forward(self.h, _ptr(x2), _ptr(cond), _ptr(out), _ptr(logdet), B, _ptr(ws),
+                                               ws.numel(), self._stream()), "flow_forward")
         return out[:, :, None, None], logdet
 
     __call__ = forward
@@ -149,10 +187,12 @@ class ResnetEncoder(_Native):
 
     _destroy = "i2v_embedder_destroy"
 
-    def __init__(self, state_dict, config, device="cuda", tc_mode=1):
+    def __init__(self, state_dict, config, device="cuda", tc_mode=1, tc_min_ctas=None, graph=False):
         """``tc_mode``: 0 = fp32 SIMT convs only, 1 = tensor-core convs (fp32-grade fp16 split) where the GEMM fills
-        the machine (InstanceNorm variant), 2 = wherever the shape is supported."""
+        the machine (InstanceNorm variant), 2 = wherever the shape is supported.  ``tc_min_ctas``: fewest 128x128
+        output tiles for which mode 1 picks the tensor-core engine (library default 8)."""
         super().__init__(device)
+        self.graph = bool(graph)
         self.config = config
         self.z_dim = config["z_dim"]
         norm = config["norm"]
@@ -165,8 +205,8 @@ class ResnetEncoder(_Native):
             raise RuntimeError(self.L.i2v_last_error().decode())
         self._register(self.L.i2v_embedder_set_tensor, loader.pack_embedder(state_dict, self.z_dim, norm, tensor_core=tc_mode != 0))
         self.set_tc_mode(tc_mode)
-        if os.environ.get("I2V_EMB_TC_MIN_CTAS"):          # tuning aid
-            _lib.check(self.L.i2v_embedder_set_scalar(self.h, b"tc_min_ctas", float(os.environ["I2V_EMB_TC_MIN_CTAS"])),
+        if tc_min_ctas is not None:
+            _lib.check(self.L.i2v_embedder_set_scalar(self.h, b"tc_min_ctas", float(tc_min_ctas)),
                        "embedder_set_scalar(tc_min_ctas)")
 
     def set_tc_mode(self, tc_mode):
@@ -181,9 +221,25 @@ class ResnetEncoder(_Native):
         out = torch.empty(B, self.z_dim, dtype=torch.float32, device=self.device)
         if B == 0:
             return out
-        ws = self._workspace(self.L.i2v_embedder_workspace_bytes(self.h, B, H, W))
-        _lib.check(self.L.i2v_embedder_forward(self.h, _ptr(x), _ptr(out), B, H, W, _ptr(ws), ws.numel(), _stream()),
-                   "embedder_forward")
+        with self._guard():
+            if self.graph and not self.L.i2v_prof_is_enabled():
+                def call(s_x, s_out, holder, stream):
+                    if "ws" not in holder:
+                        holder["ws"] = torch.empty(int(self.L.i2v_embedder_workspace_bytes(self.h, B, H, W)), dtype=torch.uint8,
+                                                   device=self.device)
+                    ws = holder["ws"]
+                    _lib.check(self.L.i2v_embedder_forward(self.h, _ptr(s_x), _ptr(s_out), B, H, W, _ptr(ws), ws.numel(), stream),
+                               "embedder_forward")
+                g, (s_x,), s_out, _, nk = self._graphed(("emb", B, H, W, self.tc_mode), [(B, 3, H, W)], (B, self.z_dim), call)
+                s_x.copy_(x)
+                g.replay()
+                out.copy_(s_out)
+                self.graph_replays += 1
+                self.graph_kernels += nk
+                return out
+            ws = self._workspace(self.L.i2v_embedder_workspace_bytes(self.h, B, H, W))
+            _lib.check(self.L.i2v_embedder_forward(self.h, _ptr(x), _ptr(out), B, H, W, _ptr(ws), ws.numel(), self._stream()),
+                       "embedder_forward")
         return out
 
     def encode(self, x):
@@ -195,8 +251,9 @@ class Generator(_Native):
 
     _destroy = "i2v_decoder_destroy"
 
-    def __init__(self, state_dict, dic, device="cuda", conv_engine=1, micro_batch=16, streams=1):
+    def __init__(self, state_dict, dic, device="cuda", conv_engine=1, micro_batch=16, streams=1, graph=False):
         super().__init__(device)
+        self.graph = bool(graph)
         self.nf, self.z_dim = dic["channel_factor"], dic["z_dim"]
         self.upsample_s, self.upsample_t = list(dic["upsample_s"]), list(dic["upsample_t"])
         self.micro_batch = micro_batch
@@ -204,6 +261,9 @@ class Generator(_Native):
         # micro-batch's HBM-bound passes and kernel tails overlap the other's tensor-bound convs
         self.n_streams = max(1, int(streams))
         self._side = None
+        # optional hook ``f(row_lo, row_hi, out)`` called after each micro-batch has been enqueued on the caller's stream
+        # (dist.py overlaps the all-gather of finished rows with the next micro-batch through it)
+        self.on_micro_batch = None
         if conv_engine >= 1 and self.nf % 16 != 0:
             conv_engine = 0      # tensor-core tiles need channel counts that are multiples of 16
         us = (ctypes.c_int * 2)(*self.upsample_s)
@@ -230,6 +290,38 @@ class Generator(_Native):
         mb = max(1, min(self.micro_batch, B))
         if B == 0:
             return out
+        with self._guard():
+            if self.graph and self.n_streams <= 1 and not self.L.i2v_prof_is_enabled():
+                return self._forward_graphed(img, z, out, B, H, W, mb)
+            return self._forward_batches(img, z, out, B, H, W, mb)
+
+    def _forward_graphed(self, img, z, out, B, H, W, mb):
+        for b0 in range(0, B, mb):
+            n = min(mb, B - b0)
+
+            def call(s_img, s_z, s_out, holder, stream, n=n):
+                if "ws" not in holder:
+                    nbytes = self.L.i2v_decoder_workspace_bytes(self.h, n, H, W)
+                    if nbytes == 0:
+                        raise RuntimeError(f"workspace query failed: {self.L.i2v_last_error().decode()}")
+                    holder["ws"] = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+                ws = holder["ws"]
+                _lib.check(self.L.i2v_decoder_forward(self.h, _ptr(s_img), _ptr(s_z), _ptr(s_out), n, H, W, _ptr(ws), ws.numel(),
+                                                      stream), "decoder_forward")
+
+            g, (s_img, s_z), s_out, _, nk = self._graphed(("dec", n, H, W), [(n, 3, H, W), (n, self.z_dim)],
+                                                         (n, self.frames, 3, H, W), call)
+            s_img.copy_(img[b0:b0 + n])
+            s_z.copy_(z[b0:b0 + n])
+            g.replay()
+            out[b0:b0 + n].copy_(s_out)
+            self.graph_replays += 1
+            self.graph_kernels += nk
+            if self.on_micro_batch is not None:
+                self.on_micro_batch(b0, b0 + n, out)
+        return out
+
+    def _forward_batches(self, img, z, out, B, H, W, mb):
         nbytes = self.L.i2v_decoder_workspace_bytes(self.h, mb, H, W)
         ns = min(self.n_streams, (B + mb - 1) // mb)
         if ns <= 1:
@@ -237,7 +329,9 @@ class Generator(_Native):
             for b0 in range(0, B, mb):
                 n = min(mb, B - b0)
                 _lib.check(self.L.i2v_decoder_forward(self.h, _ptr(img[b0:b0 + n]), _ptr(z[b0:b0 + n]), _ptr(out[b0:b0 + n]),
-                                                      n, H, W, _ptr(ws), ws.numel(), _stream()), "decoder_forward")
+                                                      n, H, W, _ptr(ws), ws.numel(), self._stream()), "decoder_forward")
+                if self.on_micro_batch is not None:
+                    self.on_micro_batch(b0, b0 + n, out)
             return out
         if nbytes == 0:
             raise RuntimeError(f"workspace query failed: {self.L.i2v_last_error().decode()}")
@@ -287,9 +381,10 @@ class Encoder(_Native):
         if C != 3:
             raise ValueError("encoder expects RGB clips")
         out = torch.empty(B, 2 * self.z_dim, dtype=torch.float32, device=self.device)
-        ws = self._workspace(self.L.i2v_encoder3d_workspace_bytes(self.h, B, T, H, W))
-        _lib.check(self.L.i2v_encoder3d_forward(self.h, _ptr(seq), _ptr(out), B, T, H, W, _ptr(ws), ws.numel(),
-                                                _stream()), "encoder3d_forward")
+        with self._guard():
+            ws = self._workspace(self.L.i2v_encoder3d_workspace_bytes(self.h, B, T, H, W))
+            _lib.check(self.L.i2v_encoder3d_forward(self.h, _ptr(seq), _ptr(out), B, T, H, W, _ptr(ws), ws.numel(),
+                                                    self._stream()), "encoder3d_forward")
         return out[:, : self.z_dim], out[:, self.z_dim:]
 
     def forward(self, x):
@@ -310,13 +405,17 @@ class SupervisedTransformer:
 
     def embed_pos(self, pos):
         # INN.py:49-57: three 10-way one-hots of floor(pos*10 - 1e-4), built on the host
+        # Three separate (B, 10) one-hots like the reference, so a negative bin (pos <= -0.1: .long() truncates towards
+        # zero) wraps INSIDE its own block exactly as the reference's negative indexing does, never into a neighbour's.
         pos = pos.detach().cpu() * self.cond_size - 1e-4
-        out = torch.zeros(pos.size(0), 3 * self.cond_size)
         idx = pos.long()
         rows = np.arange(pos.size(0))
+        blocks = []
         for k in range(3):
-            out[rows, k * self.cond_size + idx[:, k]] = 1
-        return out.to(self.flow.device)
+            one_hot = torch.zeros(pos.size(0), self.cond_size)
+            one_hot[rows, idx[:, k]] = 1
+            blocks.append(one_hot)
+        return torch.cat(blocks, dim=1).to(self.flow.device)
 
     def embed(self, cond):
         e = self.embedder.encode(cond[0]).mode().reshape(cond[0].size(0), self.embedder.z_dim)   # INN.py:62 (B, -1)

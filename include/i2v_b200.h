@@ -48,9 +48,14 @@ const char* i2v_last_error(void);
  * device time [ms], algorithmic FLOPs, algorithmic bytes and launch counts since the last collect. */
 long long i2v_launch_count(void);
 void i2v_prof_enable(int on);
+int i2v_prof_is_enabled(void);
 int i2v_prof_collect(double* ms, double* flops, double* bytes, long long* launches);
 /* when set (non-NULL, non-empty) i2v_prof_collect also writes one CSV row per launch to this path */
 void i2v_prof_dump_path(const char* path);
+/* Process-wide tuning switches for A/B measurements (defaults = the measured optima): "pdl" (programmatic dependent
+ * launch), "tc_flags", "tc_persist", "tc_min_stages", "tc_pair" (2-CTA conv tiles), "linear_bfly", "flow_cluster".
+ * None changes a result beyond summation order.  Returns -2 for an unknown name. */
+int i2v_set_option(const char* name, double value);
 
 /* ---------------------------------------------------------------- conditional INN (stage 2) */
 typedef struct i2v_flow i2v_flow;
@@ -130,6 +135,12 @@ int i2v_op_conv_tc(const float* dev_x, const float* dev_w, const float* dev_bias
                    int B, int T, int H, int W, int Cin, int Cout, int cout_pad, int kt, int kh, int kw, int res_ut,
                    int res_uh, int res_uw, int act, int out_mode, int terms, int variant, float scale_a, float scale_w,
                    void* dev_ws, size_t ws_bytes, void* stream);
+/* Temporal phase form (conv_0 of a GeneratorBlock behind a x2 temporal nearest upsample, decoder.py:102-111): x is the
+ * PRE-upsample tensor [B,T/2,H,W,Cin], w the phase-combined 3x3x3 weights [2 phases][2 taps][3][3][cout_pad][Cin]
+ * (loader.phase_weights); y [B,T,H,W,Cout] equals conv3d(repeat_interleave(x, 2, dim=T), w_original) + bias. */
+int i2v_op_conv_tc_phase(const float* dev_x, const float* dev_w, const float* dev_bias, float* dev_y, int B, int T, int H, int W,
+                         int Cin, int Cout, int cout_pad, int terms, int variant, float scale_a, float scale_w, void* dev_ws,
+                         size_t ws_bytes, void* stream);
 /* 3x3x3 tensor-core conv with a side input: y = conv3x3x3(x, w) + conv1x1x1(x2, w2) + bias as ONE implicit GEMM (the
  * GeneratorBlock's learned shortcut fused into conv_1, decoder.py:44-50).  w2 is [3 (kw)][cout_pad][Cin2] with only
  * the kw = 1 slab non-zero. */
@@ -161,6 +172,18 @@ int i2v_op_linear(const float* dev_x, const float* dev_w, const float* dev_bias,
 int i2v_op_resize_bilinear(const float* dev_img, float* dev_out, int B, int C, int H0, int W0, int H, int W,
                            void* stream);
 int i2v_op_maxpool3x3s2(const float* dev_x, float* dev_y, int B, int H, int W, int C, void* stream);
+
+/* ---------------------------------------------------------------- CLI pre/post-processing */
+/* Start frame as generate_samples.py:36-41 prepares it: uint8 HWC image (bgr != 0: cv2.imread channel order) -> RGB ->
+ * /255 -> Normalize(0.5, 0.5) -> bilinear resize to HxW (align_corners=False) -> fp32 [3,H,W] (one slot of x_0). */
+int i2v_op_preprocess_u8(const unsigned char* dev_img_hwc, float* dev_out_chw, int H0, int W0, int H, int W, int bgr, void* stream);
+/* *dev_max = max over the n floats of denorm(x) = clamp((x+1)/2, 0, 1)   (utils/auxiliaries.py:21,53-55) */
+int i2v_op_frames_max(const float* dev_frames, float* dev_max, int64_t n, void* stream);
+/* frames [N,T,3,H,W] -> uint8 RGB at out[n*stride_n + t*stride_t + h*stride_h + w*3 + c] = trunc(255*denorm(x) / *dev_max)
+ * (utils/auxiliaries.py:15-22 + .astype(uint8), generate_samples.py:61).  GIF canvas [T,H,N*W,3]: stride_n = 3W,
+ * stride_h = 3NW, stride_t = 3HNW; per-video [N,T,H,W,3]: stride_n = 3THW, stride_t = 3HW, stride_h = 3W. */
+int i2v_op_frames_to_u8(const float* dev_frames, const float* dev_max, unsigned char* dev_out, int N, int T, int H, int W,
+                        int64_t stride_n, int64_t stride_t, int64_t stride_h, void* stream);
 
 #ifdef __cplusplus
 }

@@ -72,7 +72,7 @@ def flow_forward(sd, x, cond, n_flows, control=False, depth=2):
     modes = flow_block_modes(n_flows, control)
     x = x.reshape(x.shape[0], -1)
     half = x.shape[1] // 2
-    logdet = torch.zeros(x.shape[0], dtype=x.dtype)
+    logdet = torch.zeros(x.shape[0], dtype=x.dtype, device=x.device)
     for fl in range(n_flows):
         p = f"sub_layers.{fl}."
         scale = sd[p + "norm_layer.scale"].reshape(1, -1)
@@ -93,13 +93,16 @@ def flow_forward(sd, x, cond, n_flows, control=False, depth=2):
 
 
 def embed_pos(pos, cond_size=10):
-    """SupervisedTransformer.embed_pos (INN.py:49-57): three 10-way one-hots of pos*10-1e-4."""
-    pos = pos * cond_size - 1e-4
-    out = torch.zeros(pos.shape[0], 3 * cond_size)
+    """SupervisedTransformer.embed_pos (INN.py:49-57): three separate 10-way one-hots of (pos*10-1e-4).long(),
+    concatenated (a negative bin wraps inside its own block, as the reference's indexing does)."""
+    pos = pos.detach().cpu() * cond_size - 1e-4
     idx = pos.long()
+    blocks = []
     for k in range(3):
-        out[torch.arange(pos.shape[0]), k * cond_size + idx[:, k]] = 1
-    return out
+        one_hot = torch.zeros(pos.shape[0], cond_size)
+        one_hot[torch.arange(pos.shape[0]), idx[:, k]] = 1
+        blocks.append(one_hot)
+    return torch.cat(blocks, dim=1)
 
 
 # ------------------------------------------------------------------------------------ embedder
@@ -236,7 +239,7 @@ def encoder3d_posterior(sd, x, stride_s, stride_t, layers=(2, 2, 2, 2)):
     h = _encoder3d_trunk(sd, x, stride_s, stride_t, layers)
     mu = F.conv2d(h, sd["conv_mu.weight"], sd["conv_mu.bias"]).reshape(h.shape[0], -1)
     logvar = F.conv2d(h, sd["conv_var.weight"], sd["conv_var.bias"]).reshape(h.shape[0], -1)
-    eps = torch.FloatTensor(logvar.size()).normal_()
+    eps = torch.FloatTensor(logvar.size()).normal_().to(logvar)
     return eps.mul(logvar.mul(0.5).exp()).add(mu), mu, logvar
 
 
@@ -276,10 +279,21 @@ class OracleModel:
         self.z_dim = c1["Decoder"]["z_dim"]
         self.vid_length = vid_length
 
+    def to(self, device=None, dtype=None):
+        """Move (and/or cast) every floating-point state-dict tensor: ``to(dtype=torch.float64)`` gives the fp64
+        evaluation of the same algorithm (the "truth" the fp32 reference and the CUDA path are both measured against in
+        tests/test_parity_truth_gpu.py), ``to('cuda')`` the eager PyTorch-on-GPU leg of bench.py."""
+        def mv(sd):
+            if sd is None:
+                return None
+            return {k: (v.to(device=device, dtype=dtype if v.is_floating_point() else None)) for k, v in sd.items()}
+        self.dec, self.enc, self.flow, self.emb = mv(self.dec), mv(self.enc), mv(self.flow), mv(self.emb)
+        return self
+
     def embed(self, x_0, cond=None):
         e = embedder_mean(self.emb, x_0, self.cae["AE"]["norm"])
         if self.control:
-            e = torch.cat((e, embed_pos(cond)), dim=1)
+            e = torch.cat((e, embed_pos(cond).to(e)), dim=1)
         return e
 
     def decode(self, x_0, z, trace=None):

@@ -66,3 +66,28 @@ def report(name, **vals):
             f.write(json.dumps(dict(test=name, **vals)) + "\n")
     except OSError:
         pass
+
+
+def truth_model(model_path, vid_length, transfer=False):
+    """The oracle evaluated in float64 on the same checkpoint: the exact result of the reference's algorithm, up to
+    fp64 rounding.  Both the fp32 reference and the CUDA path are measured against it."""
+    import oracle_torch as ot
+    return ot.OracleModel(model_path, vid_length, transfer=transfer).to(dtype=torch.float64)
+
+
+def assert_parity(name, got, want32, truth, flat=1e-4, factor=1.5, **extra):
+    """The parity bar of BASELINE.md section 5, stated without a derived tolerance:
+
+        rel_inf(got, fp32 reference) < 1e-4                                     (the flat bar), or
+        rel_inf(got, fp64 truth) <= factor * rel_inf(fp32 reference, fp64 truth)
+
+    The second line holds exactly where the reference's own fp32 arithmetic is less stable than 1e-4 (the 64x64
+    InstanceNorm embedder amplifies rounding ~4000x; random-init flows push |z| to ~75): there the CUDA path is
+    required to be as close to the exact result as the reference itself is, which is all any fp32 implementation
+    can be.  Both sides of that inequality are measured here, on the same inputs."""
+    e_ref = rel_inf(got, want32)
+    e_truth = rel_inf(got, truth)
+    e_ref_truth = rel_inf(want32, truth)
+    report(name, vs_reference=e_ref, vs_fp64_truth=e_truth, reference_vs_fp64_truth=e_ref_truth, **extra)
+    assert e_ref < flat or e_truth <= factor * e_ref_truth, (name, e_ref, e_truth, e_ref_truth)
+    return e_ref, e_truth, e_ref_truth

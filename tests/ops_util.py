@@ -161,3 +161,22 @@ def conv_tc_side(x_cl, w_taps, x2_cl, w2, bias, act=0, terms=3, scale_a=16.0, va
     _lib.check(L.i2v_op_conv_tc_side(P(x_cl), P(wp), P(x2_cl), P(w2p), P(bias), P(y), B, T, H, W, Cin, Cin2, Cout, cpad, act, 0,
                                      terms, variant, scale_a, scale_w, P(ws), ws.numel(), S()), "op_conv_tc_side")
     return y
+
+
+def conv_tc_phase(x_half_cl, w_taps, bias, terms=3, scale_a=16.0, variant=0):
+    """Temporal phase form: x_half_cl [B,T/2,H,W,Cin] is the PRE-upsample tensor, w_taps [27,Cout,Cin] the original
+    3x3x3 kernel (phase-combined here with the product's own loader.phase_weights); returns [B,T,H,W,Cout]."""
+    import math
+    from image2video_synthesis_using_cinns_b200 import loader
+    L = _lib.load()
+    B, Th, H, W, Cin = x_half_cl.shape
+    Cout = w_taps.shape[1]
+    cpad = (Cout + 15) // 16 * 16
+    wp = torch.zeros(36, cpad, Cin, device="cuda")
+    wp[:, :Cout] = loader.phase_weights(w_taps.cpu()).float().cuda()
+    scale_w = 2.0 ** math.floor(math.log2(2.0 ** 14 / float(wp.abs().max())))
+    y = torch.empty(B, 2 * Th, H, W, Cout, dtype=torch.float32, device="cuda")
+    ws = torch.empty(4 * (x_half_cl.numel() + wp.numel()) + 4096, dtype=torch.uint8, device="cuda")
+    _lib.check(L.i2v_op_conv_tc_phase(P(x_half_cl), P(wp), P(bias), P(y), B, 2 * Th, H, W, Cin, Cout, cpad, terms, variant,
+                                      scale_a, scale_w, P(ws), ws.numel(), S()), "op_conv_tc_phase")
+    return y

@@ -147,3 +147,47 @@ def test_conv_tc_side_input_is_fused_shortcut(name, xs, cin2, cout, variant):
     e = rel_inf(got, want)
     report("conv_tc_side:" + name, err=e)
     assert e < (1e-3 if terms == 1 else 1e-5)
+
+
+PHASE_CASES = [
+    # name, (B, Cin, T/2, H, W), Cout, variant
+    ("g3_conv0_like", (1, 128, 4, 16, 32), 64, 0),      # N = 64 at W = 32: kw-stacked halo form
+    ("g2_conv0_like", (2, 64, 2, 16, 16), 128, 0),      # N = 128: plain halo form
+    ("t_half_1", (2, 32, 1, 16, 16), 32, 0),            # T = 2: both temporal edges in one tile pair
+    ("plain_forced", (1, 64, 2, 8, 64), 64, 2),         # stacked form switched off
+]
+
+
+@pytest.mark.parametrize("name,xs,cout,variant", PHASE_CASES, ids=[c[0] for c in PHASE_CASES])
+def test_conv_tc_temporal_phase_form(name, xs, cout, variant):
+    """conv_tc(t_phase=1) on the T/2 tensor == F.conv3d on the repeat_interleave'd one (decoder.py:102-111; the phase
+    weights are loader.phase_weights, the form csrc/conv_tc.cu::halo_tile documents)."""
+    g = G(sum(map(ord, name)))
+    x = torch.randn(xs, generator=g)
+    w = torch.randn(cout, xs[1], 3, 3, 3, generator=g) / (27 * xs[1]) ** 0.5
+    b = torch.randn(cout, generator=g)
+    want = F.conv3d(x.double().repeat_interleave(2, dim=2), w.double(), b.double(), 1, 1)
+    got = ou.from_cl(ou.conv_tc_phase(ou.to_cl(x), ou.taps(w), b.cuda(), variant=variant))
+    e = rel_inf(got, want)
+    e1 = rel_inf(ou.from_cl(ou.conv_tc_phase(ou.to_cl(x), ou.taps(w), b.cuda(), terms=1, variant=variant)), want)
+    report("conv_tc_phase:" + name, split3=e, fp16_single=e1)
+    assert got.shape == want.shape
+    assert e < 1e-5 and e1 < 1e-3
+
+
+def test_split_saturates_instead_of_overflowing():
+    """|x| beyond the fp16 range of the operand split (16 * x > 65504) must clip, not turn into inf / NaN."""
+    g = G(5)
+    x = torch.randn(1, 64, 2, 16, 16, generator=g)
+    x[0, 3, 1, 5, 7] = 1.0e5          # 16 * 1e5 overflows fp16
+    x[0, 9, 0, 2, 2] = -3.0e6
+    w = torch.randn(32, 64, 3, 3, 3, generator=g) * 0.03
+    got = ou.conv_tc(ou.to_cl(x), ou.taps(w), None, None, (3, 3, 3))
+    assert torch.isfinite(got).all()
+    hi, lo = ou.modulate_split(ou.to_cl(x), None, (2, 16, 16), act=2)
+    assert torch.isfinite(hi.float()).all() and torch.isfinite(lo.float()).all()
+    assert hi.float().abs().max() <= 65504
+    # in-range values are untouched by the clamp
+    xs = torch.randn(1, 64, 2, 16, 16, generator=g)
+    a = ou.conv_tc(ou.to_cl(xs), ou.taps(w), None, None, (3, 3, 3))
+    assert rel_inf(ou.from_cl(a), F.conv3d(xs.double(), w.double(), None, 1, 1)) < 1e-5

@@ -61,3 +61,50 @@ def test_sharded_sample_matches_single_process(n):
     r = torch.randn(n, 8, generator=g)
     c = torch.rand(n, 3, generator=g)
     assert torch.equal(got, _fake_sample(x, r, c))
+
+
+class _FakeModel:
+    z_dim, vid_length, device = 8, 16, None
+
+    def sample(self, x, cond=None, residual=None):
+        return _fake_sample(x, residual, cond)
+
+
+def _worker_residual(rank, world, port, n, q):
+    from image2video_synthesis_using_cinns_b200.dist import ShardedModel, global_residual
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(100 + rank)                      # the usual seed + rank: ranks disagree on their own RNG
+    res = global_residual(n, 8)
+    torch.manual_seed(100 + rank)
+    x = torch.randn(n, 3, 4, 4, generator=torch.Generator().manual_seed(0))
+    out = ShardedModel(_FakeModel()).sample(x)
+    q.put((rank, res, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_global_residual_is_rank0s_draw_on_every_rank():
+    """with seed + rank seeding the shards must still render ONE consistent global batch."""
+    n = 5
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_residual, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict()
+    for _ in range(2):
+        rank, res, out = q.get(timeout=120)
+        got[rank] = (res, out)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    torch.manual_seed(100)
+    want_res = torch.randn(n, 8)                       # rank 0's CPU draw (quirk Q5)
+    assert torch.equal(got[0][0], want_res) and torch.equal(got[1][0], want_res)
+    x = torch.randn(n, 3, 4, 4, generator=torch.Generator().manual_seed(0))
+    want = _fake_sample(x, want_res, None)
+    assert torch.equal(got[0][1], want) and torch.equal(got[1][1], want)

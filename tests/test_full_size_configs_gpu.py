@@ -15,7 +15,7 @@ import pytest
 import torch
 
 import oracle_torch as ot
-from golden_util import rel_inf, report
+from golden_util import assert_parity, rel_inf, report, truth_model
 
 pytestmark = pytest.mark.gpu
 G = lambda s: torch.Generator().manual_seed(s)
@@ -57,7 +57,9 @@ def test_config3_landscape_full_size(ckpts):
     e_fast = rel_inf(m2.decoder(x0.cuda(), z.cuda()).cpu(), m0.decoder(x0.cuda(), z.cuda()).cpu())
     report("full_size:landscape", z=e_z, frames=e_f, decoder=e_dec, tc_vs_simt=e_eng, fast_mode=e_fast)
     assert e_z < 1e-4 and e_dec < 1e-4 and e_eng < 1e-4
-    assert e_f < 2e-4           # frames at the flow's own (large) latents, see test_full_size_gpu.py
+    tm = truth_model(mp, 16)
+    tf = tm.forward(x0[:1].double(), res[:1].double(), batch_slice=False)
+    assert_parity("oracle:landscape:frames", gf[:1].cpu(), wf, tf)
     assert e_fast < FAST_MODE_TOL
     assert gf.shape == (4, 16, 3, 128, 128) and gf.abs().max() <= 1.0
 
@@ -120,3 +122,64 @@ def test_config5_iper128_transfer_full_size(ckpts):
     report("full_size:iper128_transfer", roundtrip_z=e_rt, roundtrip_frames=e_frames, repeat=e_rep, tc_vs_simt=e_eng)
     assert e_rt < 1e-4 and e_frames < 2e-4 and e_rep < 1e-5
     assert e_eng < 2e-4
+
+
+def test_config4_dtdb_fire_seq24_sample_matches_oracle(ckpts):
+    """one oracle-compared sample of config 4 at full size (seq_length 24 -> two decoder passes,
+    the second conditioned on the first pass's last frame: 32 frames)."""
+    from image2video_synthesis_using_cinns_b200.get_model import Model
+    mp = ckpts("dtdb_fire", False)
+    m = Model(mp, 24, micro_batch=2)
+    om, tm = ot.OracleModel(mp, 24), truth_model(mp, 24)
+    g = G(41)
+    x0 = torch.rand(1, 3, 128, 128, generator=g) * 2 - 1
+    res = torch.randn(1, 64, generator=g)
+    gf, gz = m.sample(x0, residual=res, return_latent=True)
+    wf, wz = om.forward(x0, res, return_latent=True, batch_slice=False)
+    tf, tz = tm.forward(x0.double(), res.double(), return_latent=True, batch_slice=False)
+    assert gf.shape == wf.shape == (1, 32, 3, 128, 128)
+    assert_parity("oracle:dtdb_fire_seq24:z", gz.cpu(), wz, tz)
+    assert_parity("oracle:dtdb_fire_seq24:frames_pass1", gf[:, :16].cpu(), wf[:, :16], tf[:, :16])
+    assert_parity("oracle:dtdb_fire_seq24:frames", gf.cpu(), wf, tf)
+
+
+def test_config5_iper128_transfer_sample_matches_oracle(ckpts):
+    """one oracle-compared transfer of config 5 at full size (3-D encoder at channels
+    [64,128,256,512,512] on 128x128 clips -> forward cINN -> inverse cINN on a new start frame -> nf = 64 decoder)."""
+    from image2video_synthesis_using_cinns_b200.get_model import Model
+    mp = ckpts("iper128", True)
+    m = Model(mp, 16, transfer=True, micro_batch=2)
+    om, tm = ot.OracleModel(mp, 16, transfer=True), truth_model(mp, 16, transfer=True)
+    g = G(42)
+    q = torch.rand(1, 16, 3, 128, 128, generator=g) * 2 - 1
+    x0 = torch.rand(1, 3, 128, 128, generator=g) * 2 - 1
+    gs, gz, gmu, gres, gld = m.transfer(q, x0, return_latent=True)
+    ws_, wz, wmu, wres, wld = om.transfer(q, x0, return_latent=True)
+    ts, tz, tmu, tres, tld = tm.transfer(q.double(), x0.double(), return_latent=True)
+    assert_parity("oracle:iper128_transfer:mu", gmu.view(1, -1).cpu(), wmu, tmu)
+    assert_parity("oracle:iper128_transfer:residual", gres.cpu(), wres, tres)
+    assert_parity("oracle:iper128_transfer:logdet", gld.cpu(), wld, tld)
+    assert_parity("oracle:iper128_transfer:z", gz.cpu(), wz, tz)
+    assert_parity("oracle:iper128_transfer:frames", gs.cpu(), ws_, ts)
+
+
+@pytest.mark.parametrize("dataset", ["bair", "landscape", "dtdb_fire", "iper128"])
+def test_encoder3d_full_size_matches_oracle(dataset):
+    """the 3-D encoder at its FULL-size channels (resnet3D.py:138-219) against the oracle's mu,
+    for the 64x64 geometry and the three 128x128 ones (flat 1e-4)."""
+    from image2video_synthesis_using_cinns_b200 import modules, synthetic
+    from image2video_synthesis_using_cinns_b200.config import DATASETS
+    cfg = DATASETS[dataset]
+    e = cfg["enc"]
+    sd = synthetic.encoder3d_state_dict(G(50), e["channels"], e["stride_s"])
+    dic = dict(res_type_encoder="resnet18", deterministic=False, use_max_pool=False, z_dim=64, **e)
+    enc = modules.Encoder(sd, dic)
+    img = cfg["img_size"]
+    clip = torch.rand(2, 15, 3, img, img, generator=G(51)) * 2 - 1          # the query minus its first frame (get_model.py:87)
+    mu, logvar = enc.mu_logvar(clip.cuda().transpose(1, 2))
+    want = ot.encoder3d_mu(sd, clip.transpose(1, 2), e["stride_s"], e["stride_t"])
+    truth = ot.encoder3d_mu({k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}, clip.double().transpose(1, 2),
+                            e["stride_s"], e["stride_t"])
+    e_ref, _, _ = assert_parity(f"oracle:encoder3d_full:{dataset}", mu.cpu(), want, truth)
+    assert e_ref < 1e-4
+    assert torch.isfinite(logvar).all()

@@ -138,3 +138,22 @@ def test_pack_embedder_in_adds_tensor_core_split():
     assert ((hi.double() + lo.double()) / s - w.double()).abs().max() / w.abs().max() < 2 ** -21
     assert not any(k.endswith(".wh") for k in loader.pack_embedder(sd, 64, "in", tensor_core=False))
     assert not any(k.endswith(".wh") for k in loader.pack_embedder(synthetic.embedder_state_dict(gen, 64, "bn"), 64, "bn"))
+
+
+def test_embed_pos_wraps_inside_its_block_like_the_reference():
+    """three separate 10-wide one-hots (INN.py:49-57): a negative bin wraps inside its own block."""
+    import oracle_torch as ot
+    from image2video_synthesis_using_cinns_b200.modules import SupervisedTransformer
+
+    class _Flow:
+        device = torch.device("cpu")
+
+    st = SupervisedTransformer(_Flow(), None, control=True)
+    pos = torch.tensor([[0.05, 0.55, 0.999], [-0.25, 0.0, 1.0], [0.31, -0.95, 0.1]])
+    got = st.embed_pos(pos)
+    assert got.shape == (3, 30) and torch.equal(got.sum(1), torch.full((3,), 3.0))
+    idx = (pos * 10 - 1e-4).long()
+    for b in range(3):
+        for k in range(3):
+            assert got[b, k * 10 + (idx[b, k].item() % 10)] == 1        # python's % = the reference's negative indexing
+    assert torch.equal(got, ot.embed_pos(pos))

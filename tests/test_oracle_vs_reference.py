@@ -76,3 +76,14 @@ def test_synthetic_layout_matches_reference_constructors(ckpt_cache):
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             same(synthetic.embedder_state_dict(gen, 64, norm), ns.AE.ResnetEncoder(acfg).state_dict())
+
+
+def test_embed_pos_matches_reference_including_negative_bins():
+    ns = rh.import_reference()
+
+    class _Self:
+        cond_size = 10
+    pos = torch.tensor([[0.05, 0.55, 0.999], [-0.25, 0.0, 1.0], [0.31, -0.95, 0.1]])
+    with rh.cpu_cuda_identity():
+        want = ns.INN.SupervisedTransformer.embed_pos(_Self(), pos.clone())
+    assert torch.equal(ot.embed_pos(pos), want)
