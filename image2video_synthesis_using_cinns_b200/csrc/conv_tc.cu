@@ -654,7 +654,8 @@ struct ConvTcHArgs {
 
 // Tile coordinates + the temporal tap range of one output tile of the halo kernel.
 struct HaloTile { int t, b, w0, h0, ct_base, wt_base, dt_lo, dt_hi, n_main, n_total; };
-__device__ __forceinline__ HaloTile halo_tile(const ConvTcHArgs& a, int tile, int cchunks) {
+template <class Args>
+__device__ __forceinline__ HaloTile halo_tile(const Args& a, int tile, int cchunks) {
     HaloTile c;
     const int tw = tile % a.tiles_w; tile /= a.tiles_w;
     const int th = tile % a.tiles_h; tile /= a.tiles_h;
@@ -1013,6 +1014,298 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
     if (warp == 1) ptx::tmem_dealloc(tmem_base, ncols);
 }
 
+// ------------------------------------------------------------------------------------------------------
+// v3: CTA-pair tiles.  The halo kernel above fills TMEM with ONE tile (2 sub-tiles x (main + cross-term) x 128
+// columns), so its epilogue (6.6-12 us of a 14-79 us tile) cannot run under the next tile's MMAs, and its 90 KB
+// stages leave room for a 2-deep ring only.  Here the two 128-voxel sub-tiles of the same 256-voxel patch go to the
+// two CTAs of a cluster on one TPC, and every MMA is ONE tcgen05.mma.cta_group::2 of M = 256 issued by the leader:
+//   * each CTA stages its own sub-tile with its 1-row halo (box bw x (bh_sub + 2)) and HALF of the weight tile (n_tile / 2
+//     output rows x 3 kh taps): 44-57 KB per stage instead of 90 -> 4-5 ring buffers in the same shared memory, and the
+//     weight tile crosses L2 -> SM once per PAIR;
+//   * a CTA's TMEM holds 128 rows x (main + cross) x n_tile columns = half of it: TWO accumulator sets, so the epilogue of
+//     tile i drains set i & 1 while the MMAs of tile i + 1 fill the other one (tmem_full / tmem_empty barriers per set);
+//   * the epilogue therefore no longer borrows the ring buffers: every thread finishes its own output row straight from
+//     registers (128 contiguous bytes per 32-column chunk, 16-byte accesses), and the per-(sample, channel) statistics
+//     come out of a 31-shuffle transpose-reduce of each chunk;
+//   * stage release (empty) and accumulator-ready (tmem_full) signals are multicast commits onto the same-offset barriers
+//     of both CTAs; both CTAs' TMA loads report their bytes to the LEADER's full barrier; the 8 + 8 epilogue warps of the
+//     pair arrive on the leader's tmem_empty barrier (remote mbarrier.arrive for the peer).
+struct ConvTcPArgs {
+    const float* bias; const float* res; const float* scale_ptr; float* y; double* stats;
+    int B, T, H, W, Cin, Cout;
+    int kt, kw;                   // kh == 3
+    int t_phase;
+    int wstack;                   // always 0 (halo_tile reads it)
+    int bw, bh2;                  // the PAIR's patch: bw x bh2 voxels (= 256); each CTA owns bh2 / 2 of its rows
+    int tiles_w, tiles_h;
+    int n_tile, kc, stages, terms;
+    int res_ut, res_uh, res_uw, act;
+    int cc_lo, cc_hi;
+    int cc2;
+    int n_tiles;
+};
+
+// sum over the warp's 32 rows of each of 32 columns: v[j] of lane r = element (row r, column j); returns to lane c the
+// sum of column c.  Each step halves the columns a lane still carries: 16 + 8 + 4 + 2 + 1 shuffles.
+__device__ __forceinline__ float column_sums32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int j = 0; j < n; ++j) {
+            const float send = up ? v[j] : v[j + n];
+            const float keep = up ? v[j + n] : v[j];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
+                    const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl,
+                    const __grid_constant__ CUtensorMap mA2h, const __grid_constant__ CUtensorMap mA2l,
+                    const __grid_constant__ CUtensorMap mB2h, const __grid_constant__ CUtensorMap mB2l, const ConvTcPArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t rb = (uint32_t)a.kc * 2;
+    const int bh_sub = a.bh2 / 2;
+    const uint32_t a_rows = (uint32_t)(a.bw * (bh_sub + 2));
+    const uint32_t a_bytes = (a_rows * rb + 1023u) & ~1023u;
+    const int nh = a.n_tile / 2;                                    // weight rows this CTA stages (its half of N)
+    const uint32_t b_tap = (uint32_t)nh * rb;                       // one kh tap; multiple of 1024 (host-checked)
+    const uint32_t b_bytes = 3 * b_tap;
+    const uint32_t mult = a.terms > 1 ? 2u : 1u;
+    const uint32_t off_alo = a_bytes, off_bhi = mult * a_bytes, off_blo = mult * a_bytes + b_bytes;
+    const uint32_t stage_bytes = mult * (a_bytes + b_bytes);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)a.stages * stage_bytes);   // used in the leader only
+    uint64_t* empty = full + a.stages;
+    uint64_t* tmem_full = empty + a.stages;       // [2] one per accumulator set
+    uint64_t* tmem_empty = tmem_full + 2;         // [2] leader only: 16 arrivals (8 epilogue warps of each CTA)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const bool leader = rank == 0;
+    const int n0 = blockIdx.y * a.n_tile;
+    const int cchunks = a.cc_hi - a.cc_lo;
+    const int set_cols = (int)mult * a.n_tile;                      // TMEM columns of one accumulator set
+    uint32_t ncols = 32;
+    while (ncols < (uint32_t)(2 * set_cols)) ncols <<= 1;
+    if (threadIdx.x == 0 && leader) dbg_stamp(0, blockIdx.x >> 1);
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&mAh); ptx::prefetch_tensormap(&mBh);
+        if (a.terms > 1) { ptx::prefetch_tensormap(&mAl); ptx::prefetch_tensormap(&mBl); }
+        if (a.cc2 > 0) {
+            ptx::prefetch_tensormap(&mA2h); ptx::prefetch_tensormap(&mB2h);
+            if (a.terms > 1) { ptx::prefetch_tensormap(&mA2l); ptx::prefetch_tensormap(&mB2l); }
+        }
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < a.stages; ++s) { ptx::mbar_init(full + s, 1); ptx::mbar_init(empty + s, 1); }
+            ptx::mbar_init(tmem_full, 1); ptx::mbar_init(tmem_full + 1, 1);
+            ptx::mbar_init(tmem_empty, 16); ptx::mbar_init(tmem_empty + 1, 16);
+            ptx::fence_barrier_init();
+        }
+        __syncwarp();
+        ptx::tmem_alloc_2cta(tmem_slot, ncols);
+        ptx::tmem_relinquish_2cta();
+    }
+    ptx::tc_fence_before();
+    ptx::cluster_sync();          // both CTAs' barriers exist before any remote arrive / TMA signal
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    pdl_launch_dependents();
+    pdl_wait();      // nothing above touched global memory
+    const int kw_iter = a.kw;
+    const int tile0 = blockIdx.x >> 1, tstep = gridDim.x >> 1;      // the pair walks tiles tile0, tile0 + tstep, ...
+
+    if (warp == 0) {
+        // ================================ TMA producer (both CTAs; bytes of both land on the leader's full barrier)
+        const uint32_t full0 = ptx::mapa_u32(ptx::smem_u32(full), 0);
+        const uint32_t tx = 2u * mult * (a_rows * rb + b_bytes);
+        const uint32_t tx2 = 2u * mult * (a_rows * rb + b_tap);
+        const int hsub = (int)rank * bh_sub, nsub = n0 + (int)rank * nh;
+        int s = 0;
+        uint32_t ph = 0;
+        for (int tile = tile0; tile < a.n_tiles; tile += tstep) {
+            const HaloTile c = halo_tile(a, tile, cchunks);
+            for (int dt = c.dt_lo; dt <= c.dt_hi; ++dt)
+            for (int dw = 0; dw < kw_iter; ++dw)
+            for (int cc = a.cc_lo; cc < a.cc_hi; ++cc) {
+                const int ct = c.ct_base + dt, wt = c.wt_base + dt, c0 = cc * a.kc;
+                ptx::mbar_wait(empty + s, ph ^ 1u);
+                uint8_t* st = smem + (size_t)s * stage_bytes;
+                const int cw = c.w0 + dw - a.kw / 2, ch = c.h0 + hsub - 1;
+                const uint32_t fb = full0 + 8u * (uint32_t)s;
+                if (ptx::elect_one()) {
+                    if (leader) ptx::mbar_expect_tx(full + s, tx);
+                    ptx::tma_load_5d_2cta(st, &mAh, fb, c0, cw, ch, ct, c.b);
+                    ptx::tma_load_5d_2cta(st + off_bhi, &mBh, fb, c0, nsub, dw, 0, wt);
+                    if (a.terms > 1) {
+                        ptx::tma_load_5d_2cta(st + off_alo, &mAl, fb, c0, cw, ch, ct, c.b);
+                        ptx::tma_load_5d_2cta(st + off_blo, &mBl, fb, c0, nsub, dw, 0, wt);
+                    }
+                }
+                __syncwarp();
+                if (++s == a.stages) { s = 0; ph ^= 1u; }
+            }
+            for (int cc = 0; cc < a.cc2; ++cc) {
+                const int c0 = cc * a.kc;
+                ptx::mbar_wait(empty + s, ph ^ 1u);
+                uint8_t* st = smem + (size_t)s * stage_bytes;
+                const uint32_t fb = full0 + 8u * (uint32_t)s;
+                if (ptx::elect_one()) {
+                    if (leader) ptx::mbar_expect_tx(full + s, tx2);
+                    ptx::tma_load_5d_2cta(st, &mA2h, fb, c0, c.w0, c.h0 + hsub - 1, c.t, c.b);
+                    ptx::tma_load_5d_2cta(st + off_bhi, &mB2h, fb, c0, nsub, 1, 0, 0);
+                    if (a.terms > 1) {
+                        ptx::tma_load_5d_2cta(st + off_alo, &mA2l, fb, c0, c.w0, c.h0 + hsub - 1, c.t, c.b);
+                        ptx::tma_load_5d_2cta(st + off_blo, &mB2l, fb, c0, nsub, 1, 0, 0);
+                    }
+                }
+                __syncwarp();
+                if (++s == a.stages) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader) {
+            // ================================ MMA issuer (leader only): M = 256 across the pair
+            const uint32_t idesc = ptx::make_idesc_f16(2 * TILE_M, a.n_tile);
+            const int ksteps = a.kc / 16;
+            const uint64_t dproto = ptx::make_kmajor_desc(0, rb);
+            const uint32_t dlo = (uint32_t)dproto, dhi = (uint32_t)(dproto >> 32);
+            const uint32_t kh_step = (uint32_t)a.bw * rb >> 4;
+            int s = 0, it = 0;
+            uint32_t ph = 0;
+            for (int tile = tile0; tile < a.n_tiles; tile += tstep, ++it) {
+                const HaloTile c = halo_tile(a, tile, cchunks);
+                const int set = it & 1;
+                if (it >= 2) {
+                    // the epilogues of BOTH CTAs must have drained this set (tile it - 2) before it is overwritten
+                    ptx::mbar_wait(tmem_empty + set, (uint32_t)(((it - 2) >> 1) & 1));
+                    ptx::tc_fence_after();
+                }
+                const uint32_t tmain = tmem_base + (uint32_t)(set * set_cols), tcross = tmain + (uint32_t)a.n_tile;
+                uint32_t acc_flag = 0u, sm_flag = 0u;       // first MMA into each accumulator of this tile overwrites
+                for (int n = 0; n < c.n_total; ++n) {
+                    ptx::mbar_wait(full + s, ph);
+                    if (n == 0 && lane == 0) dbg_stamp(2, tile);
+                    ptx::tc_fence_after();
+                    const uint32_t sa = ptx::smem_u32(smem + (size_t)s * stage_bytes);
+                    const uint32_t lah = dlo + (sa >> 4), lal = lah + (off_alo >> 4);
+                    const uint32_t lbh = lah + (off_bhi >> 4), lbl = lah + (off_blo >> 4);
+                    const bool ext = n >= c.n_main;                  // side-input stage: centre row only, weight slab 0
+                    if (ptx::elect_one()) {
+#pragma unroll
+                        for (int kh = 0; kh < 3; ++kh) {
+                            if (ext && kh != 1) continue;
+                            const uint32_t ao = (uint32_t)kh * kh_step, bo = ext ? 0u : (uint32_t)kh * (b_tap >> 4);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                if (k < ksteps) {
+                                    const uint32_t o = (uint32_t)k * 2u;
+                                    const uint64_t dAh = ptx::desc64(lah + ao + o, dhi), dBh = ptx::desc64(lbh + bo + o, dhi);
+                                    ptx::mma_f16_ss_2cta(tmain, dAh, dBh, idesc, acc_flag);
+                                    acc_flag = 1u;
+                                    if (a.terms > 1) {
+                                        ptx::mma_f16_ss_2cta(tcross, dAh, ptx::desc64(lbl + bo + o, dhi), idesc, sm_flag);
+                                        sm_flag = 1u;
+                                        ptx::mma_f16_ss_2cta(tcross, ptx::desc64(lal + ao + o, dhi), dBh, idesc, 1u);
+                                    }
+                                }
+                            }
+                        }
+                        ptx::mma_commit_2cta_mc(empty + s, 3);       // frees this ring buffer in BOTH CTAs
+                    }
+                    __syncwarp();
+                    if (++s == a.stages) { s = 0; ph ^= 1u; }
+                }
+                if (ptx::elect_one()) ptx::mma_commit_2cta_mc(tmem_full + set, 3);
+                __syncwarp();
+                if (lane == 0) dbg_stamp(3, tile);
+            }
+        }
+    } else {
+        // ================================ epilogue (8 warps per CTA, two per TMEM lane quarter), one output row per thread
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        const int m = q * 32 + lane;
+        const int wi = m % a.bw, hi = m / a.bw;
+        const int ncw = a.n_tile / 2, col0 = half * ncw;                // this warp's columns of the tile
+        const int Tr = a.T / a.res_ut, Hr = a.H / a.res_uh, Wr = a.W / a.res_uw;
+        const uint32_t te0 = ptx::mapa_u32(ptx::smem_u32(tmem_empty), 0);
+        const bool want_stats = a.stats != nullptr;
+        float scale = 0.f;
+        int it = 0;
+        for (int tile = tile0; tile < a.n_tiles; tile += tstep, ++it) {
+            const HaloTile c = halo_tile(a, tile, cchunks);
+            const int set = it & 1;
+            const int hh = c.h0 + (int)rank * bh_sub + hi, ww = c.w0 + wi;
+            const long long vox = (((long long)c.b * a.T + c.t) * a.H + hh) * a.W + ww;
+            float* yrow = a.y + vox * a.Cout;
+            const float* rrow = nullptr;
+            if (a.res != nullptr)
+                rrow = a.res + ((((long long)c.b * Tr + c.t / a.res_ut) * Hr + hh / a.res_uh) * Wr + ww / a.res_uw) * a.Cout;
+            if (it == 0) scale = __ldg(a.scale_ptr);
+            ptx::mbar_wait_backoff(tmem_full + set, (uint32_t)((it >> 1) & 1));
+            if (threadIdx.x == 64 && leader) dbg_stamp(4, tile);
+            ptx::tc_fence_after();
+            const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * set_cols + col0);
+            for (int c0 = 0; c0 < ncw; c0 += 32) {
+                uint32_t ra[32], rc[32];
+                float v[32];
+                ptx::tmem_ld_32x32b_x32(tb + (uint32_t)c0, ra);
+                if (a.terms > 1) ptx::tmem_ld_32x32b_x32(tb + (uint32_t)(a.n_tile + c0), rc);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = (__uint_as_float(ra[j]) + (a.terms > 1 ? __uint_as_float(rc[j]) : 0.f)) * scale;
+                const int n = n0 + col0 + c0;                           // first output channel of this chunk
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    if (n + 4 * g < a.Cout) {                           // Cout % 4 == 0 (host-checked): whole float4 groups
+                        if (a.bias != nullptr) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + n) + g);
+                            v[4 * g] += b4.x; v[4 * g + 1] += b4.y; v[4 * g + 2] += b4.z; v[4 * g + 3] += b4.w;
+                        }
+                        if (rrow != nullptr) {
+                            const float4 r4 = __ldg(reinterpret_cast<const float4*>(rrow + n) + g);
+                            v[4 * g] += r4.x; v[4 * g + 1] += r4.y; v[4 * g + 2] += r4.z; v[4 * g + 3] += r4.w;
+                        }
+                        const float4 o4 = make_float4(apply_act(v[4 * g], a.act), apply_act(v[4 * g + 1], a.act),
+                                                      apply_act(v[4 * g + 2], a.act), apply_act(v[4 * g + 3], a.act));
+                        reinterpret_cast<float4*>(yrow + n)[g] = o4;
+                        v[4 * g] = o4.x; v[4 * g + 1] = o4.y; v[4 * g + 2] = o4.z; v[4 * g + 3] = o4.w;
+                    } else {
+                        v[4 * g] = 0.f; v[4 * g + 1] = 0.f; v[4 * g + 2] = 0.f; v[4 * g + 3] = 0.f;
+                    }
+                }
+                if (want_stats) {
+                    // per-(sample, channel) sum / sum of squares of the STORED values (the next normalisation's statistics)
+                    float sq[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
+                    const float s1 = column_sums32(v, lane), s2 = column_sums32(sq, lane);
+                    if (n + lane < a.Cout) {
+                        double* sp = a.stats + ((size_t)c.b * a.Cout + n + lane) * 2;
+                        atomicAdd(sp, (double)s1);
+                        atomicAdd(sp + 1, (double)s2);
+                    }
+                }
+            }
+            // this warp is done with its TMEM columns of the set: tell the leader's MMA issuer (remote arrive for the peer)
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(te0 + 8u * (uint32_t)set);
+            if (threadIdx.x == 64 && leader) dbg_stamp(6, tile);
+        }
+    }
+    ptx::tc_fence_before();
+    ptx::cluster_sync();          // no CTA of the pair leaves (or frees TMEM) while its peer may still signal it
+    if (warp == 1) ptx::tmem_dealloc_2cta(tmem_base, ncols);
+}
+
 __global__ void split_fp16_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, float scale,
                                   long long n) {
     pdl_launch_dependents();
@@ -1144,6 +1437,126 @@ static bool halo_config(int H, int W, int Cin, int cout_pad, int kh, int kw, int
 bool conv_tc_side_eligible(int H, int W, int Cin, int Cin2, int cout_pad, int terms) {
     HaloCfg c;
     return halo_config(H, W, Cin, cout_pad, 3, 3, terms, 0, c) && Cin2 > 0 && Cin2 % c.kc == 0;
+}
+
+// Tile / pipeline configuration of the CTA-pair kernel; false when the layer is not eligible.
+struct PairCfg { int bw, bh2, n_tile, kc, stages; size_t stage_bytes; };
+static bool pair_config(int H, int W, int Cin, int Cout, int cout_pad, int kh, int kw, int terms, int out_mode, bool allow_narrow,
+                        PairCfg& c) {
+    if (kh != 3 || W < 16 || H * W < 256 || out_mode != 0 || Cout % 4 != 0) return false;
+    c.bw = W < 128 ? W : 128;
+    c.bh2 = 256 / c.bw;
+    if (c.bh2 < 2 || H % c.bh2 != 0) return false;
+    c.n_tile = cout_pad < 128 ? cout_pad : 128;
+    if (c.n_tile % 64 != 0) return false;                  // two column halves per lane quarter, 32-column epilogue chunks
+    // narrow layers (Cout <= 64 on whole w-rows) are better served by the halo kernel's kw-stacked form (N = 3 Cout)
+    if (!allow_narrow && kw == 3 && cout_pad <= 64 && W == c.bw) return false;
+    const int mult = terms > 1 ? 2 : 1;
+    const int bh_sub = c.bh2 / 2;
+    c.kc = 0;
+    // the widest channel chunk that still leaves `want` ring buffers (64-byte rows at 4 stages beat 128-byte rows at 2)
+    for (int want : {4, 3, 2}) {
+        for (int cand : {64, 32, 16}) {
+            if (Cin % cand) continue;
+            const size_t rb = (size_t)cand * 2;
+            if (((size_t)(c.n_tile / 2) * rb) % 1024 != 0) continue;
+            const size_t a_bytes = ((size_t)c.bw * (bh_sub + 2) * rb + 1023) & ~(size_t)1023;
+            const size_t sb = mult * (a_bytes + 3 * (size_t)(c.n_tile / 2) * rb);
+            const int st = (int)((227 * 1024 - 1024 - 512) / sb);
+            if (st >= want) { c.kc = cand; c.stages = st > 8 ? 8 : st; c.stage_bytes = sb; break; }
+        }
+        if (c.kc != 0) break;
+    }
+    return c.kc != 0;
+}
+
+// v3 eligibility + launch.  Returns 1 if the layer is not eligible (caller falls through to the halo kernel).
+static int launch_conv_tc_pair(const ConvTcArgs& h, cudaStream_t stream) {
+    PairCfg cfg{};
+    if (!pair_config(h.H, h.W, h.Cin, h.Cout, h.cout_pad, h.kh, h.kw, h.terms, h.out_mode, h.variant == 4, cfg)) return 1;
+    if (h.t_phase && !(h.kt == 3 && h.T % 2 == 0)) return 1;
+    const int kt_eff = h.t_phase ? 2 : h.kt;
+    const int Tin = h.t_phase ? h.T / 2 : h.T;
+    const int kc = cfg.kc, cch = h.Cin / kc;
+    if (h.Cin2 != 0 && !(h.x2_hi && h.w2_hi && h.Cin2 % kc == 0 && !h.t_phase && h.kt == 3 && h.kw == 3)) return 1;
+    const int cc2 = h.Cin2 / kc;
+    // K split across launches: one main accumulator per set, chains of <= kMaxChain truncating MMAs (see launch_conv_tc_halo)
+    int parts = 1;
+    if (h.terms > 1) {
+        const long long chain = (long long)kt_eff * h.kw * cch * 3 * (kc / 16) + (long long)cc2 * (kc / 16);
+        parts = (int)((chain + kMaxChain - 1) / kMaxChain);
+        if (parts > cch) parts = cch;
+        if (parts < 1) parts = 1;
+    }
+    if (parts > 1 && (h.act != ACT_NONE || cc2 != 0)) return 1;
+    const int cper = (cch + parts - 1) / parts;
+    ConvTcPArgs a;
+    a.bias = h.bias; a.res = h.res; a.scale_ptr = h.scale_ptr; a.y = h.y; a.stats = h.stats;
+    a.B = h.B; a.T = h.T; a.H = h.H; a.W = h.W; a.Cin = h.Cin; a.Cout = h.Cout; a.kt = kt_eff; a.kw = h.kw;
+    a.t_phase = h.t_phase ? 1 : 0; a.wstack = 0;
+    a.bw = cfg.bw; a.bh2 = cfg.bh2; a.tiles_w = h.W / a.bw; a.tiles_h = h.H / a.bh2;
+    a.n_tile = cfg.n_tile; a.kc = kc; a.stages = cfg.stages; a.terms = h.terms;
+    a.res_ut = h.res_ut; a.res_uh = h.res_uh; a.res_uw = h.res_uw; a.act = h.act;
+    a.cc2 = cc2;
+    const int rb = kc * 2, bh_sub = a.bh2 / 2;
+
+    CUtensorMap mAh, mAl, mBh, mBl;
+    {
+        const cuuint64_t dims[5] = {(cuuint64_t)h.Cin, (cuuint64_t)h.W, (cuuint64_t)h.H, (cuuint64_t)Tin, (cuuint64_t)h.B};
+        const cuuint64_t st[4] = {(cuuint64_t)h.Cin * 2, (cuuint64_t)h.W * h.Cin * 2, (cuuint64_t)h.H * h.W * h.Cin * 2,
+                                  (cuuint64_t)Tin * h.H * h.W * h.Cin * 2};
+        const cuuint32_t box[5] = {(cuuint32_t)kc, (cuuint32_t)a.bw, (cuuint32_t)(bh_sub + 2), 1, 1};
+        if (int rc = encode_map(&mAh, h.x_hi, 5, dims, st, box, rb)) return rc;
+        if (int rc = encode_map(&mAl, h.terms > 1 ? h.x_lo : h.x_hi, 5, dims, st, box, rb)) return rc;
+    }
+    {
+        const cuuint64_t row = (cuuint64_t)h.cout_pad * h.Cin * 2;
+        const cuuint64_t dims[5] = {(cuuint64_t)h.Cin, (cuuint64_t)h.cout_pad, (cuuint64_t)h.kw, 3, (cuuint64_t)(h.t_phase ? 4 : h.kt)};
+        const cuuint64_t st[4] = {(cuuint64_t)h.Cin * 2, row, row * h.kw, row * h.kw * 3};
+        const cuuint32_t box[5] = {(cuuint32_t)kc, (cuuint32_t)(a.n_tile / 2), 1, 3, 1};    // this CTA's half of the N tile
+        if (int rc = encode_map(&mBh, h.w_hi, 5, dims, st, box, rb)) return rc;
+        if (int rc = encode_map(&mBl, h.terms > 1 ? h.w_lo : h.w_hi, 5, dims, st, box, rb)) return rc;
+    }
+    CUtensorMap mA2h = mAh, mA2l = mAl, mB2h = mBh, mB2l = mBl;
+    if (cc2 > 0) {
+        const cuuint64_t dims[5] = {(cuuint64_t)h.Cin2, (cuuint64_t)h.W, (cuuint64_t)h.H, (cuuint64_t)h.T, (cuuint64_t)h.B};
+        const cuuint64_t st[4] = {(cuuint64_t)h.Cin2 * 2, (cuuint64_t)h.W * h.Cin2 * 2, (cuuint64_t)h.H * h.W * h.Cin2 * 2,
+                                  (cuuint64_t)h.T * h.H * h.W * h.Cin2 * 2};
+        const cuuint32_t box[5] = {(cuuint32_t)kc, (cuuint32_t)a.bw, (cuuint32_t)(bh_sub + 2), 1, 1};
+        if (int rc = encode_map(&mA2h, h.x2_hi, 5, dims, st, box, rb)) return rc;
+        if (int rc = encode_map(&mA2l, h.terms > 1 ? h.x2_lo : h.x2_hi, 5, dims, st, box, rb)) return rc;
+        const cuuint64_t row = (cuuint64_t)h.cout_pad * h.Cin2 * 2;
+        const cuuint64_t wd[5] = {(cuuint64_t)h.Cin2, (cuuint64_t)h.cout_pad, 3, 1, 1};
+        const cuuint64_t ws_[4] = {(cuuint64_t)h.Cin2 * 2, row, row * 3, row * 3};
+        const cuuint32_t wbox[5] = {(cuuint32_t)kc, (cuuint32_t)(a.n_tile / 2), 1, 1, 1};
+        if (int rc = encode_map(&mB2h, h.w2_hi, 5, wd, ws_, wbox, rb)) return rc;
+        if (int rc = encode_map(&mB2l, h.terms > 1 ? h.w2_lo : h.w2_hi, 5, wd, ws_, wbox, rb)) return rc;
+    }
+    static unsigned long long attr_devs = 0;
+    I2V_CHECK_CUDA(ensure_max_dyn_smem(conv_tc_pair_kernel, 227 * 1024, attr_devs));
+    const size_t smem = (size_t)cfg.stages * cfg.stage_bytes + 1024 + 512;
+    I2V_REQUIRE(smem <= 227 * 1024, "conv_tc: pair kernel shared memory (%zu bytes) over the 227 KB limit", smem);
+    const long long M = (long long)h.B * h.T * h.H * h.W;
+    const double K_ = (double)h.kt * h.kh * h.kw * h.Cin + (double)h.Cin2;
+    ProfScope ps(PROF_CONV, 2.0 * (double)M * h.Cout * K_,
+                 4.0 * ((double)M * (h.Cin + h.Cin2) + (double)M * h.Cout + K_ * h.Cout), stream);
+    // persistent pairs: one per TPC over all N tiles, each walking its share of the 256-voxel output tiles
+    const long long n_tiles = (long long)a.tiles_w * a.tiles_h * h.T * h.B;
+    const unsigned ny = (unsigned)((h.cout_pad + a.n_tile - 1) / a.n_tile);
+    long long pairs = (kNumSMs / 2) / ny > 0 ? (kNumSMs / 2) / ny : 1;
+    if (pairs > n_tiles) pairs = n_tiles;
+    a.n_tiles = (int)n_tiles;
+    dim3 grid((unsigned)(2 * pairs), ny);
+    for (int p = 0; p < parts; ++p) {
+        a.cc_lo = p * cper;
+        a.cc_hi = (p + 1) * cper < cch ? (p + 1) * cper : cch;
+        if (a.cc_lo >= a.cc_hi) break;
+        const bool last = a.cc_hi == cch;
+        if (p > 0) { a.bias = nullptr; a.res = h.y; a.res_ut = a.res_uh = a.res_uw = 1; }
+        a.stats = last ? h.stats : nullptr;
+        I2V_CHECK_CUDA(launch_k(conv_tc_pair_kernel, grid, dim3(TC_THREADS), smem, stream, mAh, mAl, mBh, mBl, mA2h, mA2l, mB2h, mB2l, a));
+    }
+    return 0;
 }
 
 // v2 eligibility + launch.  Returns 1 if the shape is not eligible (caller falls through to v1).
@@ -1307,6 +1720,11 @@ int launch_conv_tc(const ConvTcArgs& h, cudaStream_t stream) {
     I2V_REQUIRE(h.cout_pad % 16 == 0 && h.cout_pad >= h.Cout, "conv_tc: weights must be padded to a multiple of 16 output rows");
     I2V_REQUIRE(h.res == nullptr || (h.T % h.res_ut == 0 && h.H % h.res_uh == 0 && h.W % h.res_uw == 0),
                 "conv_tc: residual upsample factors must divide the output size");
+    if ((h.variant == 0 && tune().tc_pair) || h.variant == 4) {
+        const int rc = launch_conv_tc_pair(h, stream);
+        if (rc <= 0) return rc;     // launched (0) or failed (<0); 1 = not eligible -> the single-CTA kernels below
+        I2V_REQUIRE(h.variant != 4, "conv_tc: shape not eligible for the CTA-pair kernel");
+    }
     if (h.variant != 1) {
         const int rc = launch_conv_tc_halo(h, stream);
         if (rc <= 0) return rc;     // launched (0) or failed (<0); 1 = shape not eligible -> v1 below

@@ -130,7 +130,8 @@ int i2v_op_spade_conv3(const float* dev_img, const float* dev_w, const float* de
 /* tensor-core conv on fp32 inputs: splits x (scale_a) and w (scale_w; [taps,cout_pad,Cin], rows >= Cout zero) into
  * fp16 (hi, lo) inside the workspace (>= 4*(|x|+|w|)+2048 bytes), then runs the tcgen05 engine; terms 3 or 1;
  * variant 0 = auto, 1 = per-tap box kernel, 2 = 256-row H-halo kernel without kw stacking, 3 = H-halo kernel with the three
- * kw taps stacked along N (Cout <= 64); 2 and 3 fail if the shape is not eligible */
+ * kw taps stacked along N (Cout <= 64), 4 = CTA-pair kernel (cta_group::2 tiles, two TMEM accumulator sets); 2, 3 and 4 fail
+ * if the shape is not eligible */
 int i2v_op_conv_tc(const float* dev_x, const float* dev_w, const float* dev_bias, const float* dev_res, float* dev_y,
                    int B, int T, int H, int W, int Cin, int Cout, int cout_pad, int kt, int kh, int kw, int res_ut,
                    int res_uh, int res_uw, int act, int out_mode, int terms, int variant, float scale_a, float scale_w,

@@ -33,6 +33,8 @@ CASES = [
 ]
 HALO_OK = {"g3_like_w64", "w32_kc64_n128", "w16_n256", "kc32", "spade_gb_2d", "w128_row", "long_k_halo",
            "halo_n64_t4", "halo_cout3", "g4_conv0_like", "wstack_w32_n32", "wstack_w16_n48", "wstack_2d"}
+# CTA-pair kernel (cta_group::2, two TMEM accumulator sets), forced with variant=4: N tiles of 64 / 128 columns
+PAIR_OK = {"g3_like_w64", "w32_kc64_n128", "w16_n256", "spade_gb_2d", "long_k_halo", "halo_n64_t4", "g4_conv0_like", "wstack_2d"}
 # narrow layers (Cout <= 64, whole w-rows per tile): the halo kernel's kw-stacked form, forced with variant=3
 WSTACK_OK = {"g3_like_w64", "kc32", "w128_row", "halo_n64_t4", "halo_cout3", "g4_conv0_like", "wstack_w32_n32",
              "wstack_w16_n48", "wstack_2d"}
@@ -54,7 +56,10 @@ def test_conv_tc_matches_fp32(name, xs, cout, k):
     ev1 = rel_inf(ou.from_cl(ou.conv_tc(ou.to_cl(x), ou.taps(w), b.cuda(), None, k, variant=1)), want)
     ev2 = rel_inf(ou.from_cl(ou.conv_tc(ou.to_cl(x), ou.taps(w), b.cuda(), None, k, variant=2)), want) if name in HALO_OK else None
     ev3 = rel_inf(ou.from_cl(ou.conv_tc(ou.to_cl(x), ou.taps(w), b.cuda(), None, k, variant=3)), want) if name in WSTACK_OK else None
-    report("conv_tc:" + name, split3=e3, fp16_single=e1, simt_fp32=simt, v1=ev1, v2_halo=ev2, v3_wstack=ev3)
+    ev4 = rel_inf(ou.from_cl(ou.conv_tc(ou.to_cl(x), ou.taps(w), b.cuda(), None, k, variant=4)), want) if name in PAIR_OK else None
+    ev4f = rel_inf(ou.from_cl(ou.conv_tc(ou.to_cl(x), ou.taps(w), b.cuda(), None, k, variant=4, terms=1)), want) if name in PAIR_OK else None
+    report("conv_tc:" + name, split3=e3, fp16_single=e1, simt_fp32=simt, v1=ev1, v2_halo=ev2, v3_wstack=ev3, v4_pair=ev4, v4_pair_fp16=ev4f)
+    assert ev4 is None or (ev4 < 1e-5 and ev4f < 1e-3)
     assert ev1 < 6e-6 and (ev2 is None or ev2 < 1e-5)   # halo kernel: 2 accumulators at N=128 instead of 4
     assert ev3 is None or ev3 < 1e-5
     assert got.shape == want.shape
@@ -79,6 +84,34 @@ def test_conv_tc_epilogue_residual_act_and_frames_layout():
     want = torch.tanh(F.conv3d(x, w3, b3, 1, 1)).transpose(1, 2)
     got = ou.conv_tc(ou.to_cl(x), ou.taps(w3), b3.cuda(), None, (3, 3, 3), act=3, out_mode=1)
     assert rel_inf(got.cpu(), want) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 4, 16, 32, 128), (1, 32, 2, 32, 64, 64), (3, 64, 2, 16, 16, 192), (1, 64, 2, 4, 128, 64)])
+def test_conv_tc_pair_epilogue_residual_act_many_tiles(shape):
+    """CTA-pair kernel: bias, residual through the x2x2x2 upsample map, activation, a partial last N tile (Cout = 192),
+    and more tiles than CTA pairs would hold at once for the accumulator-set alternation (odd and even tile counts)."""
+    B, C, T, H, W, cout = shape
+    g = G(B * 1000 + W + cout)
+    x = torch.randn(B, C, T, H, W, generator=g)
+    w = torch.randn(cout, C, 3, 3, 3, generator=g) * 0.03
+    b = torch.randn(cout, generator=g)
+    res = torch.randn(B, cout, T // 2, H // 2, W // 2, generator=g)
+    want = F.leaky_relu(F.conv3d(x.double(), w.double(), b.double(), 1, 1) + F.interpolate(res.double(), scale_factor=2.0), 0.2)
+    got = ou.conv_tc(ou.to_cl(x), ou.taps(w), b.cuda(), ou.to_cl(res), (3, 3, 3), res_up=(2, 2, 2), act=2, variant=4)
+    assert rel_inf(ou.from_cl(got), want) < 1e-5
+    # same launch twice: the barriers / accumulator sets leave no state behind
+    got2 = ou.conv_tc(ou.to_cl(x), ou.taps(w), b.cuda(), ou.to_cl(res), (3, 3, 3), res_up=(2, 2, 2), act=2, variant=4)
+    assert torch.equal(got, got2)
+
+
+def test_conv_tc_pair_many_tiles_per_pair():
+    """A batch large enough that every CTA pair walks > 4 tiles: ring and accumulator-set phases wrap several times."""
+    g = G(77)
+    x = torch.randn(8, 32, 8, 32, 32, generator=g)          # 8*8*4 = 256 tiles of 256 voxels... x 1 N tile over 74 pairs
+    w = torch.randn(64, 32, 3, 3, 3, generator=g) * 0.05
+    want = F.conv3d(x, w, None, 1, 1)
+    got = ou.conv_tc(ou.to_cl(x), ou.taps(w), None, None, (3, 3, 3), variant=4)
+    assert rel_inf(ou.from_cl(got), want) < 1e-5
 
 
 @pytest.mark.parametrize("hw", [(16, 16), (8, 64), (2, 128)])
@@ -128,6 +161,8 @@ SIDE_CASES = [
     ("small_nf32", (2, 32, 4, 16, 16), 64, 32, 0),           # narrow net: kc = 32 (64-byte rows), stacked N = 96
     ("stacked_forced_off", (1, 64, 2, 8, 64), 128, 64, 2),   # same layer through the plain halo form
     ("single_product", (1, 64, 2, 8, 64), 128, 64, 0),       # terms = 1 (conv_engine 2)
+    ("pair_bair_g4", (1, 64, 4, 8, 64), 128, 64, 4),         # CTA-pair kernel: side chunks through the centre row
+    ("pair_n128", (2, 32, 2, 16, 32), 64, 128, 4),           # (a side input excludes K-split launches: short reduction)
 ]
 
 
@@ -155,6 +190,9 @@ PHASE_CASES = [
     ("g2_conv0_like", (2, 64, 2, 16, 16), 128, 0),      # N = 128: plain halo form
     ("t_half_1", (2, 32, 1, 16, 16), 32, 0),            # T = 2: both temporal edges in one tile pair
     ("plain_forced", (1, 64, 2, 8, 64), 64, 2),         # stacked form switched off
+    ("pair_g3_conv0", (1, 128, 4, 16, 32), 64, 4),      # CTA-pair kernel
+    ("pair_n128", (2, 64, 2, 16, 16), 128, 4),
+    ("pair_t_half_1", (2, 64, 1, 8, 64), 64, 4),
 ]
 
 
