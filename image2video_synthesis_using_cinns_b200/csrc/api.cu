@@ -206,6 +206,8 @@ int i2v_set_option(const char* name, double value) {
     else if (k == "tc_persist") t.tc_persist = v != 0;
     else if (k == "tc_min_stages") t.tc_min_stages = v < 2 ? 2 : (v > 6 ? 6 : v);
     else if (k == "tc_pair") t.tc_pair = v != 0;
+    else if (k == "tc_pair_stack") t.tc_pair_stack = v < 0 ? 0 : (v > 2 ? 2 : v);
+    else if (k == "tc_pair_stages") t.tc_pair_stages = v < 0 ? 0 : v;
     else if (k == "linear_bfly") t.linear_bfly = v != 0;
     else if (k == "flow_cluster") t.flow_cluster = v != 0;
     else I2V_REQUIRE(false, "set_option: unknown option '%s'", name);

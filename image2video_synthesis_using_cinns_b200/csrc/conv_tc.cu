@@ -1035,7 +1035,9 @@ struct ConvTcPArgs {
     int B, T, H, W, Cin, Cout;
     int kt, kw;                   // kh == 3
     int t_phase;
-    int wstack;                   // always 0 (halo_tile reads it)
+    int wstack;                   // 1: the 3 kw taps are stacked along N (narrow layers; see wstack_gather above)
+    int nacc;                     // accumulators per set: 2 = main + cross terms, 1 = shared (terms == 1, or stacked N = 192)
+    int out_mode;                 // 1: (B,T,C,H,W) frame layout (conv_img), stacked form only
     int bw, bh2;                  // the PAIR's patch: bw x bh2 voxels (= 256); each CTA owns bh2 / 2 of its rows
     int tiles_w, tiles_h;
     int n_tile, kc, stages, terms;
@@ -1061,6 +1063,23 @@ __device__ __forceinline__ float column_sums32(float (&v)[32], int lane) {
     return v[0];
 }
 
+// 16-column variant: lanes L and L ^ 16 end up with the sum of column L & 15
+__device__ __forceinline__ float column_sums16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j], 16);
+#pragma unroll
+    for (int off = 8, n = 8; off >= 1; off >>= 1, n >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int j = 0; j < n; ++j) {
+            const float send = up ? v[j] : v[j + n];
+            const float keep = up ? v[j + n] : v[j];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ CUtensorMap mAl,
                     const __grid_constant__ CUtensorMap mBh, const __grid_constant__ CUtensorMap mBl,
@@ -1072,24 +1091,29 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
     const int bh_sub = a.bh2 / 2;
     const uint32_t a_rows = (uint32_t)(a.bw * (bh_sub + 2));
     const uint32_t a_bytes = (a_rows * rb + 1023u) & ~1023u;
-    const int nh = a.n_tile / 2;                                    // weight rows this CTA stages (its half of N)
-    const uint32_t b_tap = (uint32_t)nh * rb;                       // one kh tap; multiple of 1024 (host-checked)
+    const int nh = a.n_tile / 2;                                    // output channels this CTA stages weights for (its half of N)
+    const int nw = a.wstack ? 3 : 1;                                // kw taps per weight row block
+    // Stacked form: the MMA's N = 3 n_tile columns are ordered [half][kw][nh], so that each CTA of the pair stages the three
+    // kw slabs of ITS nh output channels (one TMA box) and its accumulator columns [kw][nh] sit side by side.
+    const uint32_t b_tap = (uint32_t)(nw * nh) * rb;                // one kh tap; multiple of 1024 (host-checked)
     const uint32_t b_bytes = 3 * b_tap;
     const uint32_t mult = a.terms > 1 ? 2u : 1u;
     const uint32_t off_alo = a_bytes, off_bhi = mult * a_bytes, off_blo = mult * a_bytes + b_bytes;
-    const uint32_t stage_bytes = mult * (a_bytes + b_bytes);
+    const uint32_t stage_bytes = (mult * (a_bytes + b_bytes) + 1023u) & ~1023u;   // as pair_config sizes it
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)a.stages * stage_bytes);   // used in the leader only
     uint64_t* empty = full + a.stages;
     uint64_t* tmem_full = empty + a.stages;       // [2] one per accumulator set
     uint64_t* tmem_empty = tmem_full + 2;         // [2] leader only: 16 arrivals (8 epilogue warps of each CTA)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* const xbuf = reinterpret_cast<float*>(tmem_slot + 4);    // stacked epilogue: [2 slots][4 quarters][2 halves][d0 | d2][16]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = ptx::cluster_ctarank();
     const bool leader = rank == 0;
     const int n0 = blockIdx.y * a.n_tile;
     const int cchunks = a.cc_hi - a.cc_lo;
-    const int set_cols = (int)mult * a.n_tile;                      // TMEM columns of one accumulator set
+    const int accw = nw * a.n_tile;                                 // TMEM columns of one accumulator = the MMA's N
+    const int set_cols = a.nacc * accw;                             // TMEM columns of one accumulator set
     uint32_t ncols = 32;
     while (ncols < (uint32_t)(2 * set_cols)) ncols <<= 1;
     if (threadIdx.x == 0 && leader) dbg_stamp(0, blockIdx.x >> 1);
@@ -1119,7 +1143,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     pdl_launch_dependents();
     pdl_wait();      // nothing above touched global memory
-    const int kw_iter = a.kw;
+    const int kw_iter = a.wstack ? 1 : a.kw;                        // stacked: one unshifted load covers all kw taps
     const int tile0 = blockIdx.x >> 1, tstep = gridDim.x >> 1;      // the pair walks tiles tile0, tile0 + tstep, ...
 
     if (warp == 0) {
@@ -1138,7 +1162,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
                 const int ct = c.ct_base + dt, wt = c.wt_base + dt, c0 = cc * a.kc;
                 ptx::mbar_wait(empty + s, ph ^ 1u);
                 uint8_t* st = smem + (size_t)s * stage_bytes;
-                const int cw = c.w0 + dw - a.kw / 2, ch = c.h0 + hsub - 1;
+                const int cw = a.wstack ? c.w0 : c.w0 + dw - a.kw / 2, ch = c.h0 + hsub - 1;
                 const uint32_t fb = full0 + 8u * (uint32_t)s;
                 if (ptx::elect_one()) {
                     if (leader) ptx::mbar_expect_tx(full + s, tx);
@@ -1160,10 +1184,10 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
                 if (ptx::elect_one()) {
                     if (leader) ptx::mbar_expect_tx(full + s, tx2);
                     ptx::tma_load_5d_2cta(st, &mA2h, fb, c0, c.w0, c.h0 + hsub - 1, c.t, c.b);
-                    ptx::tma_load_5d_2cta(st + off_bhi, &mB2h, fb, c0, nsub, 1, 0, 0);
+                    ptx::tma_load_5d_2cta(st + off_bhi, &mB2h, fb, c0, nsub, a.wstack ? 0 : 1, 0, 0);
                     if (a.terms > 1) {
                         ptx::tma_load_5d_2cta(st + off_alo, &mA2l, fb, c0, c.w0, c.h0 + hsub - 1, c.t, c.b);
-                        ptx::tma_load_5d_2cta(st + off_blo, &mB2l, fb, c0, nsub, 1, 0, 0);
+                        ptx::tma_load_5d_2cta(st + off_blo, &mB2l, fb, c0, nsub, a.wstack ? 0 : 1, 0, 0);
                     }
                 }
                 __syncwarp();
@@ -1173,7 +1197,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
     } else if (warp == 1) {
         if (leader) {
             // ================================ MMA issuer (leader only): M = 256 across the pair
-            const uint32_t idesc = ptx::make_idesc_f16(2 * TILE_M, a.n_tile);
+            const uint32_t idesc = ptx::make_idesc_f16(2 * TILE_M, accw);
             const int ksteps = a.kc / 16;
             const uint64_t dproto = ptx::make_kmajor_desc(0, rb);
             const uint32_t dlo = (uint32_t)dproto, dhi = (uint32_t)(dproto >> 32);
@@ -1188,8 +1212,9 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
                     ptx::mbar_wait(tmem_empty + set, (uint32_t)(((it - 2) >> 1) & 1));
                     ptx::tc_fence_after();
                 }
-                const uint32_t tmain = tmem_base + (uint32_t)(set * set_cols), tcross = tmain + (uint32_t)a.n_tile;
-                uint32_t acc_flag = 0u, sm_flag = 0u;       // first MMA into each accumulator of this tile overwrites
+                // cross terms hi*lo, lo*hi accumulate apart from hi*hi unless the set holds ONE accumulator (stacked N = 192)
+                const uint32_t tmain = tmem_base + (uint32_t)(set * set_cols), tcross = a.nacc > 1 ? tmain + (uint32_t)accw : tmain;
+                uint32_t acc_flag = 0u, sm_flag = a.nacc > 1 ? 0u : 1u;      // first MMA into each accumulator of this tile overwrites
                 for (int n = 0; n < c.n_total; ++n) {
                     ptx::mbar_wait(full + s, ph);
                     if (n == 0 && lane == 0) dbg_stamp(2, tile);
@@ -1252,15 +1277,120 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
             ptx::mbar_wait_backoff(tmem_full + set, (uint32_t)((it >> 1) & 1));
             if (threadIdx.x == 64 && leader) dbg_stamp(4, tile);
             ptx::tc_fence_after();
+            if (a.wstack) {
+                // ---- stacked kw taps: out[m] = D1[m] + D0[m-1] [w > 0] + D2[m+1] [w < W-1]  (see wstack_gather); rows m -+ 1 are
+                // the neighbouring lanes, the first / last lane of a 32-row slice gets them from the neighbouring warp through
+                // `xbuf` (two alternating slots, one named barrier of the 8 epilogue warps per 16-column chunk)
+                const bool left_ok = wi > 0, right_ok = wi < a.bw - 1;
+                const bool fix0 = q > 0 && ((q * 32) % a.bw) > 0, fix31 = q < 3 && ((q * 32 + 31) % a.bw) < a.bw - 1;
+                const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * set_cols + half * 3 * nh);
+                int slot = 0;
+                for (int c0 = 0; c0 < nh; c0 += 16) {
+                    const int cw16 = nh - c0 < 16 ? nh - c0 : 16;       // 8 when the tile is 16 channels wide (conv_img)
+                    uint32_t r0[16], r1[16], r2[16];
+                    float d0[16], d1[16], d2[16], v[16];
+                    if (cw16 == 16) {
+                        ptx::tmem_ld_32x32b_x16(tb + (uint32_t)c0, r0);
+                        ptx::tmem_ld_32x32b_x16(tb + (uint32_t)(nh + c0), r1);
+                        ptx::tmem_ld_32x32b_x16(tb + (uint32_t)(2 * nh + c0), r2);
+                    } else {
+                        ptx::tmem_ld_32x32b_x8(tb + (uint32_t)c0, r0);
+                        ptx::tmem_ld_32x32b_x8(tb + (uint32_t)(nh + c0), r1);
+                        ptx::tmem_ld_32x32b_x8(tb + (uint32_t)(2 * nh + c0), r2);
+#pragma unroll
+                        for (int j = 8; j < 16; ++j) { r0[j] = 0u; r1[j] = 0u; r2[j] = 0u; }
+                    }
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { d0[j] = __uint_as_float(r0[j]); d1[j] = __uint_as_float(r1[j]); d2[j] = __uint_as_float(r2[j]); }
+                    if (a.nacc > 1) {
+                        if (cw16 == 16) {
+                            ptx::tmem_ld_32x32b_x16(tb + (uint32_t)(accw + c0), r0);
+                            ptx::tmem_ld_32x32b_x16(tb + (uint32_t)(accw + nh + c0), r1);
+                            ptx::tmem_ld_32x32b_x16(tb + (uint32_t)(accw + 2 * nh + c0), r2);
+                        } else {
+                            ptx::tmem_ld_32x32b_x8(tb + (uint32_t)(accw + c0), r0);
+                            ptx::tmem_ld_32x32b_x8(tb + (uint32_t)(accw + nh + c0), r1);
+                            ptx::tmem_ld_32x32b_x8(tb + (uint32_t)(accw + 2 * nh + c0), r2);
+                        }
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) { d0[j] += __uint_as_float(r0[j]); d1[j] += __uint_as_float(r1[j]); d2[j] += __uint_as_float(r2[j]); }
+                    }
+                    wstack_combine(d0, d1, d2, lane, left_ok, right_ok, v);
+                    float* xs = xbuf + (size_t)slot * 256;                   // [quarter][half][d0 | d2][16]
+                    if (lane == 31) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) xs[((q * 2 + half) * 2) * 16 + j] = d0[j];
+                    }
+                    if (lane == 0) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) xs[((q * 2 + half) * 2 + 1) * 16 + j] = d2[j];
+                    }
+                    epi_bar();
+                    if (lane == 0 && fix0) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] += xs[(((q - 1) * 2 + half) * 2) * 16 + j];
+                    }
+                    if (lane == 31 && fix31) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] += xs[(((q + 1) * 2 + half) * 2 + 1) * 16 + j];
+                    }
+                    slot ^= 1;
+                    const int n = n0 + half * nh + c0;                        // first output channel of this chunk
+                    if (a.out_mode == 0) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            if (4 * g < cw16 && n + 4 * g < a.Cout) {         // Cout % 4 == 0 (host-checked)
+                                float o[4] = {v[4 * g] * scale, v[4 * g + 1] * scale, v[4 * g + 2] * scale, v[4 * g + 3] * scale};
+                                if (a.bias != nullptr) {
+                                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + n) + g);
+                                    o[0] += b4.x; o[1] += b4.y; o[2] += b4.z; o[3] += b4.w;
+                                }
+                                if (rrow != nullptr) {
+                                    const float4 r4 = __ldg(reinterpret_cast<const float4*>(rrow + n) + g);
+                                    o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
+                                }
+                                const float4 o4 = make_float4(apply_act(o[0], a.act), apply_act(o[1], a.act), apply_act(o[2], a.act),
+                                                              apply_act(o[3], a.act));
+                                reinterpret_cast<float4*>(yrow + n)[g] = o4;
+                                v[4 * g] = o4.x; v[4 * g + 1] = o4.y; v[4 * g + 2] = o4.z; v[4 * g + 3] = o4.w;
+                            } else {
+                                v[4 * g] = 0.f; v[4 * g + 1] = 0.f; v[4 * g + 2] = 0.f; v[4 * g + 3] = 0.f;
+                            }
+                        }
+                        if (want_stats) {
+                            float sq[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) sq[j] = v[j] * v[j];
+                            const float s1 = column_sums16(v, lane), s2 = column_sums16(sq, lane);
+                            if (lane < 16 && lane < cw16 && n + lane < a.Cout) {
+                                double* sp = a.stats + ((size_t)c.b * a.Cout + n + lane) * 2;
+                                atomicAdd(sp, (double)s1);
+                                atomicAdd(sp + 1, (double)s2);
+                            }
+                        }
+                    } else {
+                        // frame layout (B, T, C, H, W) of conv_img: consecutive lanes = consecutive w of one channel plane
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            if (j < cw16 && n + j < a.Cout) {
+                                float o = v[j] * scale;
+                                if (a.bias != nullptr) o += __ldg(a.bias + n + j);
+                                a.y[((((long long)c.b * a.T + c.t) * a.Cout + n + j) * a.H + hh) * a.W + ww] = apply_act(o, a.act);
+                            }
+                        }
+                    }
+                }
+            } else {
             const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * set_cols + col0);
-            for (int c0 = 0; c0 < ncw; c0 += 32) {
-                uint32_t ra[32], rc[32];
+            for (int c0 = 0; c0 < ncw; c0 += 32) {                uint32_t ra[32], rc[32];
                 float v[32];
                 ptx::tmem_ld_32x32b_x32(tb + (uint32_t)c0, ra);
-                if (a.terms > 1) ptx::tmem_ld_32x32b_x32(tb + (uint32_t)(a.n_tile + c0), rc);
+                if (a.nacc > 1) ptx::tmem_ld_32x32b_x32(tb + (uint32_t)(accw + c0), rc);
                 ptx::tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = (__uint_as_float(ra[j]) + (a.terms > 1 ? __uint_as_float(rc[j]) : 0.f)) * scale;
+                for (int j = 0; j < 32; ++j) v[j] = (__uint_as_float(ra[j]) + (a.nacc > 1 ? __uint_as_float(rc[j]) : 0.f)) * scale;
                 const int n = n0 + col0 + c0;                           // first output channel of this chunk
 #pragma unroll
                 for (int g = 0; g < 8; ++g) {
@@ -1293,6 +1423,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_consta
                         atomicAdd(sp + 1, (double)s2);
                     }
                 }
+            }
             }
             // this warp is done with its TMEM columns of the set: tell the leader's MMA issuer (remote arrive for the peer)
             ptx::tc_fence_before();
@@ -1440,17 +1571,27 @@ bool conv_tc_side_eligible(int H, int W, int Cin, int Cin2, int cout_pad, int te
 }
 
 // Tile / pipeline configuration of the CTA-pair kernel; false when the layer is not eligible.
-struct PairCfg { int bw, bh2, n_tile, kc, stages; size_t stage_bytes; };
-static bool pair_config(int H, int W, int Cin, int Cout, int cout_pad, int kh, int kw, int terms, int out_mode, bool allow_narrow,
-                        PairCfg& c) {
-    if (kh != 3 || W < 16 || H * W < 256 || out_mode != 0 || Cout % 4 != 0) return false;
+struct PairCfg { int bw, bh2, n_tile, kc, stages, nw, nacc; size_t stage_bytes; bool wstack; };
+constexpr size_t kPairSmemBase = 1024 + 256;               // alignment slack + barriers
+constexpr size_t kPairSmemStack = 2048;                    // stacked-epilogue edge rows
+static bool pair_config(int H, int W, int Cin, int Cout, int cout_pad, int kh, int kw, int terms, int out_mode, bool stack_ok, PairCfg& c) {
+    if (kh != 3 || W < 16 || H * W < 256) return false;
     c.bw = W < 128 ? W : 128;
     c.bh2 = 256 / c.bw;
     if (c.bh2 < 2 || H % c.bh2 != 0) return false;
-    c.n_tile = cout_pad < 128 ? cout_pad : 128;
-    if (c.n_tile % 64 != 0) return false;                  // two column halves per lane quarter, 32-column epilogue chunks
-    // narrow layers (Cout <= 64 on whole w-rows) are better served by the halo kernel's kw-stacked form (N = 3 Cout)
-    if (!allow_narrow && kw == 3 && cout_pad <= 64 && W == c.bw) return false;
+    // narrow layers (Cout <= 64 on whole w-rows): the three kw taps stacked along N (N = 3 Cout), see wstack_gather
+    c.wstack = stack_ok && kw == 3 && cout_pad <= 64 && W == c.bw;
+    c.nw = c.wstack ? 3 : 1;
+    if (c.wstack) {
+        c.n_tile = cout_pad;                               // multiple of 16 -> N = 3 n_tile is a multiple of 16 (cta_group::2)
+        if (out_mode == 0 && Cout % 4 != 0) return false;
+    } else {
+        if (out_mode != 0 || Cout % 4 != 0) return false;
+        c.n_tile = cout_pad < 128 ? cout_pad : 128;
+        if (c.n_tile % 64 != 0) return false;              // two column halves per lane quarter, 32-column epilogue chunks
+    }
+    const int accw = c.nw * c.n_tile;
+    c.nacc = (terms > 1 && 2 * 2 * accw <= 512) ? 2 : 1;   // two accumulator SETS must fit the 512 TMEM columns
     const int mult = terms > 1 ? 2 : 1;
     const int bh_sub = c.bh2 / 2;
     c.kc = 0;
@@ -1459,10 +1600,11 @@ static bool pair_config(int H, int W, int Cin, int Cout, int cout_pad, int kh, i
         for (int cand : {64, 32, 16}) {
             if (Cin % cand) continue;
             const size_t rb = (size_t)cand * 2;
-            if (((size_t)(c.n_tile / 2) * rb) % 1024 != 0) continue;
+            // every kh slab of the weight tile starts on a swizzle period (8 rows: 1024 / 512 / 256 bytes for 128 / 64 / 32-byte rows)
+            if ((c.nw * c.n_tile / 2) % 8 != 0) continue;
             const size_t a_bytes = ((size_t)c.bw * (bh_sub + 2) * rb + 1023) & ~(size_t)1023;
-            const size_t sb = mult * (a_bytes + 3 * (size_t)(c.n_tile / 2) * rb);
-            const int st = (int)((227 * 1024 - 1024 - 512) / sb);
+            const size_t sb = (mult * (a_bytes + 3 * (size_t)(c.nw * c.n_tile / 2) * rb) + 1023) & ~(size_t)1023;
+            const int st = (int)((227 * 1024 - kPairSmemBase - (c.wstack ? kPairSmemStack : 0)) / sb);
             if (st >= want) { c.kc = cand; c.stages = st > 8 ? 8 : st; c.stage_bytes = sb; break; }
         }
         if (c.kc != 0) break;
@@ -1471,19 +1613,29 @@ static bool pair_config(int H, int W, int Cin, int Cout, int cout_pad, int kh, i
 }
 
 // v3 eligibility + launch.  Returns 1 if the layer is not eligible (caller falls through to the halo kernel).
+// variant 0 / 4: kw-stacked form for narrow layers, plain form otherwise; 5: never stacked.
 static int launch_conv_tc_pair(const ConvTcArgs& h, cudaStream_t stream) {
     PairCfg cfg{};
-    if (!pair_config(h.H, h.W, h.Cin, h.Cout, h.cout_pad, h.kh, h.kw, h.terms, h.out_mode, h.variant == 4, cfg)) return 1;
+    if (!pair_config(h.H, h.W, h.Cin, h.Cout, h.cout_pad, h.kh, h.kw, h.terms, h.out_mode, h.variant != 5, cfg)) return 1;
+    // Narrow layers are bound by L2 -> SM operand traffic, and a pair's 128-voxel sub-tiles carry more halo rows per output
+    // row than the single-CTA kernel's 256-voxel tile: measured (profiles/r02_bench_ab.txt) the stacked pair form wins on
+    // conv_img (tiny K, epilogue-bound) and loses on g_4.conv_0 -- automatic selection takes it for the frame layout only.
+    if (h.variant == 0 && cfg.wstack && !(tune().tc_pair_stack == 2 || (tune().tc_pair_stack == 1 && h.out_mode == 1))) return 1;
+    if (tune().tc_pair_stages >= 2 && cfg.stages > tune().tc_pair_stages) cfg.stages = tune().tc_pair_stages;
     if (h.t_phase && !(h.kt == 3 && h.T % 2 == 0)) return 1;
+    if (h.stats != nullptr && h.out_mode != 0) return 1;
     const int kt_eff = h.t_phase ? 2 : h.kt;
     const int Tin = h.t_phase ? h.T / 2 : h.T;
     const int kc = cfg.kc, cch = h.Cin / kc;
     if (h.Cin2 != 0 && !(h.x2_hi && h.w2_hi && h.Cin2 % kc == 0 && !h.t_phase && h.kt == 3 && h.kw == 3)) return 1;
     const int cc2 = h.Cin2 / kc;
-    // K split across launches: one main accumulator per set, chains of <= kMaxChain truncating MMAs (see launch_conv_tc_halo)
+    // K split across launches: one main accumulator per set, chains of <= kMaxChain truncating MMAs (see launch_conv_tc_halo);
+    // a shared accumulator (stacked N = 192) also takes the two cross-term MMAs of every k-step
     int parts = 1;
     if (h.terms > 1) {
-        const long long chain = (long long)kt_eff * h.kw * cch * 3 * (kc / 16) + (long long)cc2 * (kc / 16);
+        const int kw_iter = cfg.wstack ? 1 : h.kw;
+        const int per_k = cfg.nacc > 1 ? 1 : 3;
+        const long long chain = (long long)kt_eff * kw_iter * cch * 3 * (kc / 16) * per_k + (long long)cc2 * (kc / 16) * per_k;
         parts = (int)((chain + kMaxChain - 1) / kMaxChain);
         if (parts > cch) parts = cch;
         if (parts < 1) parts = 1;
@@ -1493,7 +1645,7 @@ static int launch_conv_tc_pair(const ConvTcArgs& h, cudaStream_t stream) {
     ConvTcPArgs a;
     a.bias = h.bias; a.res = h.res; a.scale_ptr = h.scale_ptr; a.y = h.y; a.stats = h.stats;
     a.B = h.B; a.T = h.T; a.H = h.H; a.W = h.W; a.Cin = h.Cin; a.Cout = h.Cout; a.kt = kt_eff; a.kw = h.kw;
-    a.t_phase = h.t_phase ? 1 : 0; a.wstack = 0;
+    a.t_phase = h.t_phase ? 1 : 0; a.wstack = cfg.wstack ? 1 : 0; a.nacc = cfg.nacc; a.out_mode = h.out_mode;
     a.bw = cfg.bw; a.bh2 = cfg.bh2; a.tiles_w = h.W / a.bw; a.tiles_h = h.H / a.bh2;
     a.n_tile = cfg.n_tile; a.kc = kc; a.stages = cfg.stages; a.terms = h.terms;
     a.res_ut = h.res_ut; a.res_uh = h.res_uh; a.res_uw = h.res_uw; a.act = h.act;
@@ -1513,7 +1665,8 @@ static int launch_conv_tc_pair(const ConvTcArgs& h, cudaStream_t stream) {
         const cuuint64_t row = (cuuint64_t)h.cout_pad * h.Cin * 2;
         const cuuint64_t dims[5] = {(cuuint64_t)h.Cin, (cuuint64_t)h.cout_pad, (cuuint64_t)h.kw, 3, (cuuint64_t)(h.t_phase ? 4 : h.kt)};
         const cuuint64_t st[4] = {(cuuint64_t)h.Cin * 2, row, row * h.kw, row * h.kw * 3};
-        const cuuint32_t box[5] = {(cuuint32_t)kc, (cuuint32_t)(a.n_tile / 2), 1, 3, 1};    // this CTA's half of the N tile
+        // this CTA's half of the N tile; stacked form: its three kw slabs in one box -> smem [kh][kw][n_tile / 2][kc]
+        const cuuint32_t box[5] = {(cuuint32_t)kc, (cuuint32_t)(a.n_tile / 2), (cuuint32_t)cfg.nw, 3, 1};
         if (int rc = encode_map(&mBh, h.w_hi, 5, dims, st, box, rb)) return rc;
         if (int rc = encode_map(&mBl, h.terms > 1 ? h.w_lo : h.w_hi, 5, dims, st, box, rb)) return rc;
     }
@@ -1528,13 +1681,13 @@ static int launch_conv_tc_pair(const ConvTcArgs& h, cudaStream_t stream) {
         const cuuint64_t row = (cuuint64_t)h.cout_pad * h.Cin2 * 2;
         const cuuint64_t wd[5] = {(cuuint64_t)h.Cin2, (cuuint64_t)h.cout_pad, 3, 1, 1};
         const cuuint64_t ws_[4] = {(cuuint64_t)h.Cin2 * 2, row, row * 3, row * 3};
-        const cuuint32_t wbox[5] = {(cuuint32_t)kc, (cuuint32_t)(a.n_tile / 2), 1, 1, 1};
+        const cuuint32_t wbox[5] = {(cuuint32_t)kc, (cuuint32_t)(a.n_tile / 2), (cuuint32_t)cfg.nw, 1, 1};
         if (int rc = encode_map(&mB2h, h.w2_hi, 5, wd, ws_, wbox, rb)) return rc;
         if (int rc = encode_map(&mB2l, h.terms > 1 ? h.w2_lo : h.w2_hi, 5, wd, ws_, wbox, rb)) return rc;
     }
     static unsigned long long attr_devs = 0;
     I2V_CHECK_CUDA(ensure_max_dyn_smem(conv_tc_pair_kernel, 227 * 1024, attr_devs));
-    const size_t smem = (size_t)cfg.stages * cfg.stage_bytes + 1024 + 512;
+    const size_t smem = (size_t)cfg.stages * cfg.stage_bytes + kPairSmemBase + (cfg.wstack ? kPairSmemStack : 0);
     I2V_REQUIRE(smem <= 227 * 1024, "conv_tc: pair kernel shared memory (%zu bytes) over the 227 KB limit", smem);
     const long long M = (long long)h.B * h.T * h.H * h.W;
     const double K_ = (double)h.kt * h.kh * h.kw * h.Cin + (double)h.Cin2;
@@ -1720,10 +1873,10 @@ int launch_conv_tc(const ConvTcArgs& h, cudaStream_t stream) {
     I2V_REQUIRE(h.cout_pad % 16 == 0 && h.cout_pad >= h.Cout, "conv_tc: weights must be padded to a multiple of 16 output rows");
     I2V_REQUIRE(h.res == nullptr || (h.T % h.res_ut == 0 && h.H % h.res_uh == 0 && h.W % h.res_uw == 0),
                 "conv_tc: residual upsample factors must divide the output size");
-    if ((h.variant == 0 && tune().tc_pair) || h.variant == 4) {
+    if ((h.variant == 0 && tune().tc_pair) || h.variant == 4 || h.variant == 5) {
         const int rc = launch_conv_tc_pair(h, stream);
         if (rc <= 0) return rc;     // launched (0) or failed (<0); 1 = not eligible -> the single-CTA kernels below
-        I2V_REQUIRE(h.variant != 4, "conv_tc: shape not eligible for the CTA-pair kernel");
+        I2V_REQUIRE(h.variant != 4 && h.variant != 5, "conv_tc: shape not eligible for the CTA-pair kernel");
     }
     if (h.variant != 1) {
         const int rc = launch_conv_tc_halo(h, stream);

@@ -13,7 +13,9 @@ struct TuneOptions {
     int tc_flags = 1;        // halo conv kernel: bit 0 = residual L2 prefetch from the idle epilogue warps
     int tc_persist = 1;      // halo conv kernel: persistent tile loop (0: one CTA per tile)
     int tc_min_stages = 2;   // halo conv kernel: pipeline depth aimed for when picking the channel chunk (2..6)
-    int tc_pair = 1;         // halo conv kernel: 2-CTA (cta_group::2) tiles where the layer is eligible
+    int tc_pair = 1;         // conv engine: CTA-pair (cta_group::2) tiles where the layer is eligible
+    int tc_pair_stack = 1;   // kw-stacked narrow layers on the CTA-pair kernel: 0 never, 1 frame-layout output only (conv_img), 2 all
+    int tc_pair_stages = 0;  // CTA-pair kernel: cap on the ring depth (0 = as many as fit, up to 8)
     int linear_bfly = 1;     // linear kernel: 9-shuffle transpose-reduce (0: 8 x warp_sum)
     int flow_cluster = 1;    // flow: cluster-resident kernel where eligible (0: cooperative grid-barrier kernel)
 };

@@ -33,8 +33,10 @@ CASES = [
 ]
 HALO_OK = {"g3_like_w64", "w32_kc64_n128", "w16_n256", "kc32", "spade_gb_2d", "w128_row", "long_k_halo",
            "halo_n64_t4", "halo_cout3", "g4_conv0_like", "wstack_w32_n32", "wstack_w16_n48", "wstack_2d"}
-# CTA-pair kernel (cta_group::2, two TMEM accumulator sets), forced with variant=4: N tiles of 64 / 128 columns
-PAIR_OK = {"g3_like_w64", "w32_kc64_n128", "w16_n256", "spade_gb_2d", "long_k_halo", "halo_n64_t4", "g4_conv0_like", "wstack_2d"}
+# CTA-pair kernel (cta_group::2, two TMEM accumulator sets): variant=5 = plain form (N tiles of 64 / 128 columns),
+# variant=4 = kw-stacked form on narrow layers (N = 3 Cout), plain form otherwise
+PAIR5_OK = {"g3_like_w64", "w32_kc64_n128", "w16_n256", "spade_gb_2d", "long_k_halo", "halo_n64_t4", "g4_conv0_like", "wstack_2d"}
+PAIR_OK = PAIR5_OK | {"kc32", "w128_row", "wstack_w32_n32", "wstack_w16_n48"}
 # narrow layers (Cout <= 64, whole w-rows per tile): the halo kernel's kw-stacked form, forced with variant=3
 WSTACK_OK = {"g3_like_w64", "kc32", "w128_row", "halo_n64_t4", "halo_cout3", "g4_conv0_like", "wstack_w32_n32",
              "wstack_w16_n48", "wstack_2d"}
@@ -58,8 +60,11 @@ def test_conv_tc_matches_fp32(name, xs, cout, k):
     ev3 = rel_inf(ou.from_cl(ou.conv_tc(ou.to_cl(x), ou.taps(w), b.cuda(), None, k, variant=3)), want) if name in WSTACK_OK else None
     ev4 = rel_inf(ou.from_cl(ou.conv_tc(ou.to_cl(x), ou.taps(w), b.cuda(), None, k, variant=4)), want) if name in PAIR_OK else None
     ev4f = rel_inf(ou.from_cl(ou.conv_tc(ou.to_cl(x), ou.taps(w), b.cuda(), None, k, variant=4, terms=1)), want) if name in PAIR_OK else None
-    report("conv_tc:" + name, split3=e3, fp16_single=e1, simt_fp32=simt, v1=ev1, v2_halo=ev2, v3_wstack=ev3, v4_pair=ev4, v4_pair_fp16=ev4f)
+    ev5 = rel_inf(ou.from_cl(ou.conv_tc(ou.to_cl(x), ou.taps(w), b.cuda(), None, k, variant=5)), want) if name in PAIR5_OK else None
+    report("conv_tc:" + name, split3=e3, fp16_single=e1, simt_fp32=simt, v1=ev1, v2_halo=ev2, v3_wstack=ev3, v4_pair=ev4, v4_pair_fp16=ev4f,
+           v5_pair_plain=ev5)
     assert ev4 is None or (ev4 < 1e-5 and ev4f < 1e-3)
+    assert ev5 is None or ev5 < 1e-5
     assert ev1 < 6e-6 and (ev2 is None or ev2 < 1e-5)   # halo kernel: 2 accumulators at N=128 instead of 4
     assert ev3 is None or ev3 < 1e-5
     assert got.shape == want.shape
@@ -114,9 +119,11 @@ def test_conv_tc_pair_many_tiles_per_pair():
     assert rel_inf(ou.from_cl(got), want) < 1e-5
 
 
+@pytest.mark.parametrize("variant", [3, 4], ids=["halo", "pair"])
 @pytest.mark.parametrize("hw", [(16, 16), (8, 64), (2, 128)])
-def test_conv_tc_wstack_epilogue_residual_act_and_frames_layout(hw):
-    """kw-stacked halo kernel: shifted-sum epilogue with bias, upsampled residual, activation; frame layout + tanh."""
+def test_conv_tc_wstack_epilogue_residual_act_and_frames_layout(hw, variant):
+    """kw-stacked form (single-CTA halo kernel / CTA-pair kernel): shifted-sum epilogue with bias, upsampled residual,
+    activation; frame layout + tanh (conv_img)."""
     g = G(11)
     H, W = hw
     x = torch.randn(2, 64, 2, H, W, generator=g)
@@ -124,15 +131,15 @@ def test_conv_tc_wstack_epilogue_residual_act_and_frames_layout(hw):
     b = torch.randn(32, generator=g)
     res = torch.randn(2, 32, 1, H // 2, W // 2, generator=g)
     want = F.leaky_relu(F.conv3d(x, w, b, 1, 1) + F.interpolate(res, scale_factor=2.0), 0.2)
-    got = ou.conv_tc(ou.to_cl(x), ou.taps(w), b.cuda(), ou.to_cl(res), (3, 3, 3), res_up=(2, 2, 2), act=2, variant=3)
+    got = ou.conv_tc(ou.to_cl(x), ou.taps(w), b.cuda(), ou.to_cl(res), (3, 3, 3), res_up=(2, 2, 2), act=2, variant=variant)
     assert rel_inf(ou.from_cl(got), want) < 1e-5
     w3 = torch.randn(3, 64, 3, 3, 3, generator=g) * 0.03
     b3 = torch.randn(3, generator=g)
     want = torch.tanh(F.conv3d(x, w3, b3, 1, 1)).transpose(1, 2)
-    got = ou.conv_tc(ou.to_cl(x), ou.taps(w3), b3.cuda(), None, (3, 3, 3), act=3, out_mode=1, variant=3)
+    got = ou.conv_tc(ou.to_cl(x), ou.taps(w3), b3.cuda(), None, (3, 3, 3), act=3, out_mode=1, variant=variant)
     assert rel_inf(got.cpu(), want) < 1e-5
     # single fp16 product mode takes the same path with one accumulator
-    got = ou.conv_tc(ou.to_cl(x), ou.taps(w), b.cuda(), None, (3, 3, 3), terms=1, variant=3)
+    got = ou.conv_tc(ou.to_cl(x), ou.taps(w), b.cuda(), None, (3, 3, 3), terms=1, variant=variant)
     assert rel_inf(ou.from_cl(got), F.conv3d(x, w, b, 1, 1)) < 1e-3
 
 
