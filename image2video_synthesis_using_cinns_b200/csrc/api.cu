@@ -158,6 +158,11 @@ static int flow_weights(const i2v_flow* h, FlowWeights& fw) {
     I2V_PTR(scale, h->tt.get("scale", nf * h->d)); fw.scale = scale;
     I2V_PTR(pf, h->tt.get<int>("perm_fwd", nf * h->d)); fw.perm_fwd = pf;
     I2V_PTR(pb, h->tt.get<int>("perm_bwd", nf * h->d)); fw.perm_bwd = pb;
+    if (h->tt.has("wpack") && h->d == 64 && H % 8 == 0) {
+        // per coupling and CTA rank: 1 + depth * H/32 + 1 chunks of 32 * H/8 floats
+        const size_t chunks = 1 + (size_t)h->depth * (H / 32) + 1;
+        I2V_PTR(wp, h->tt.get("wpack", nf * 2 * 16 * chunks * 32 * (H / 8))); fw.wpack = wp;
+    }
     return 0;
 }
 

@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) flow_kernel(const FlowKernelA
 }  // namespace
 int flow_set_debug(unsigned long long* buf) {
     I2V_CHECK_CUDA(cudaMemcpyToSymbol(g_flow_dbg, &buf, sizeof(buf)));
-    return 0;
+    return flow_cluster_set_debug(buf);
 }
 namespace {
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -445,6 +445,11 @@ int launch_flow(const FlowWeights& fw, const float* in, const float* cond, float
     const int n1 = fw.n_flows * 2 * 2 * H;
     if (int rc = launch_linear(cond, fw.w1c, fw.b1, c1, B, fw.zc, n1, ACT_NONE, stream)) return rc;
 
+    if (flow_cluster_eligible(fw)) {
+        // cluster-resident nets: no grid barrier, no activation round trip through L2 (flow_cluster.cu)
+        const int rc = launch_flow_cluster(fw, in, c1, out, logdet, B, reverse, stream);
+        if (rc <= 0) return rc;        // launched or failed; 1 = clusters of 16 cannot be scheduled here -> cooperative kernel
+    }
     static unsigned long long attr_devs = 0;
     const size_t smem_max = 200 * 1024;
     I2V_CHECK_CUDA(ensure_max_dyn_smem(flow_kernel, (int)smem_max, attr_devs));

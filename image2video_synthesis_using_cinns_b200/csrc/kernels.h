@@ -144,7 +144,15 @@ struct FlowWeights {
     const float* scale;  // [n_flows, d]
     const int* perm_fwd; // [n_flows, d]
     const int* perm_bwd; // [n_flows, d]
+    // optional: the x-part of the first Linear, the hidden Linears and the last Linear once more, cut into the per-CTA,
+    // k-major chunks the cluster kernel streams (flow_cluster.cu; loader.pack_flow "wpack"); nullptr = cooperative kernel only
+    const float* wpack = nullptr;
 };
+bool flow_cluster_eligible(const FlowWeights& fw);
+int flow_cluster_set_debug(unsigned long long* buf);
+// cluster-resident kernel; c1 = hoisted conditioning GEMM output.  Returns 1 if the device cannot schedule the cluster.
+int launch_flow_cluster(const FlowWeights& fw, const float* in, const float* c1, float* out, float* logdet, int B, bool reverse,
+                        cudaStream_t stream);
 size_t flow_workspace_bytes(const FlowWeights& fw, int B);
 int flow_set_debug(unsigned long long* buf);   // phase timestamps of coupling #4 (profiling aid)
 // reverse: z = flow^-1(residual | cond);  forward: (out, logdet) = flow(z | cond)

@@ -91,7 +91,34 @@ def pack_flow(sd, n_flows, d, cond_channels, hidden, depth, control):
                 bo[fl, i, orow] = sd[f"{q}{2 * (depth + 1)}.bias"]
     t = dict(w1x=w1x, w1c=w1c.reshape(-1, zc_pad), b1=b1.reshape(-1), wh=wh, bh=bh, wo=wo, bo=bo, loc=loc,
              scale=scale, perm_fwd=pf, perm_bwd=pb)
+    if d == 64 and H in (256, 512):
+        t["wpack"] = pack_flow_chunks(w1x, wh, wo, depth)
     return {k: v.contiguous() for k, v in t.items()}, cond_mode, zc_pad
+
+
+def pack_flow_chunks(w1x, wh, wo, depth):
+    """Weight stream of the cluster-resident flow kernel (csrc/flow_cluster.cu).
+
+    A cluster of 16 CTAs carries 8 batch rows through every coupling: CTAs 0..7 hold the scale net, 8..15 the translation
+    net; CTA j of a net owns output columns [j*H/8, (j+1)*H/8) of the first and the hidden Linears and outputs [4j, 4j+4)
+    of the last one.  Per coupling and CTA the weights are laid out in the order they are consumed, k-major (column
+    fastest, so a warp's shared-memory reads are conflict-free), in chunks of 32 k-rows:
+        [first Linear, x part: 32 x H/8] [hidden l: H/32 chunks of 32 x H/8] ... [last Linear: H x 4]
+    -> [n_flows*2, 16, 1 + depth*H/32 + 1, 32*H/8] float32."""
+    n_flows, _, twoH, half = w1x.shape
+    H = twoH // 2
+    Cc = H // 8
+    assert half == 32 and H % 32 == 0
+    nc = n_flows * 2
+    w1 = w1x.reshape(nc, 2, 8, Cc, half)                                   # [c, net, j, col, k]
+    parts = [w1.permute(0, 1, 2, 4, 3).reshape(nc, 16, 1, half * Cc)]      # k-major: [k][col]
+    if depth > 0:
+        h = wh.reshape(nc, depth, 2, 8, Cc, H // 32, 32)                    # [c, l, net, j, col, chunk, k]
+        h = h.permute(0, 2, 3, 1, 5, 6, 4)                                  # [c, net, j, l, chunk, k, col]
+        parts.append(h.reshape(nc, 16, depth * (H // 32), 32 * Cc))
+    o = wo.reshape(nc, 2, 8, 4, H)                                          # [c, net, j, out, k]
+    parts.append(o.permute(0, 1, 2, 4, 3).reshape(nc, 16, 1, H * 4))        # [k][4]
+    return torch.cat(parts, dim=2).contiguous()
 
 
 # --------------------------------------------------------------------------------------- decoder

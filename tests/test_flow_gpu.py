@@ -1,4 +1,5 @@
-"""cINN parity: the persistent flow kernel against the oracle port (flow_blocks.py semantics)."""
+"""cINN parity: the flow kernels (cluster-resident nets, csrc/flow_cluster.cu; cooperative grid kernel, csrc/flow.cu) against
+the oracle port (flow_blocks.py semantics)."""
 import pytest
 import torch
 
@@ -18,7 +19,8 @@ def _mk(n_flows, zc, hidden, control, seed):
     return sd, ConditionalFlow(sd, 64, cc, hidden, 2, n_flows, control=control), cc, gen
 
 
-@pytest.mark.parametrize("B", [1, 3, 64, 70])
+# B <= 7: one row per cluster; 8..56: 8-row clusters; 57..70: 10-row clusters in one wave; 130: two waves of clusters
+@pytest.mark.parametrize("B", [1, 3, 20, 64, 70, 130])
 @pytest.mark.parametrize("n_flows,zc,hidden,control", [(20, 64, 512, False), (6, 128, 512, False), (8, 64, 256, True)])
 def test_flow_reverse_forward_match_oracle(B, n_flows, zc, hidden, control):
     sd, flow, cc, gen = _mk(n_flows, zc, hidden, control, seed=B + n_flows)
@@ -50,3 +52,22 @@ def test_flow_empty_batch():
     sd, flow, cc, gen = _mk(2, 64, 128, False, 1)
     out = flow(torch.zeros(0, 64).cuda(), torch.zeros(0, 64).cuda(), reverse=True)
     assert out.shape == (0, 64, 1, 1)
+
+
+@pytest.mark.parametrize("B", [5, 64])
+def test_flow_cooperative_kernel_still_matches(B):
+    """The grid-barrier kernel stays as the path for geometries the cluster kernel does not take (hidden not in {256, 512},
+    devices that cannot co-schedule 16-CTA clusters): same parity with the cluster kernel switched off."""
+    from image2video_synthesis_using_cinns_b200 import lib
+    sd, flow, cc, gen = _mk(6, 64, 512, False, seed=40 + B)
+    x = torch.randn(B, 64, generator=gen)
+    cond = torch.randn(B, cc, generator=gen) * 0.7
+    want = ot.flow_reverse(sd, x, cond, 6, False)
+    a = flow(x.cuda(), cond.cuda(), reverse=True).view(B, -1).cpu()
+    lib.set_option("flow_cluster", 0)
+    try:
+        b = flow(x.cuda(), cond.cuda(), reverse=True).view(B, -1).cpu()
+    finally:
+        lib.set_option("flow_cluster", 1)
+    assert rel_inf(a, want) < TOL and rel_inf(b, want) < TOL
+    assert rel_inf(a, b) < 1e-5
