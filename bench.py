@@ -17,7 +17,8 @@ One JSON line is printed by rank 0:
              N>1: per-GPU batch fixed = weak scaling, the all-gather of finished frames is inside: it is issued on a
              side stream behind the step that produced the frames and the timed region ends when it has completed)
   e2e        same metric through the public API call with HOST buffers: pinned H2D of start frames + residual and
-             D2H of the frames inside the timed region
+             D2H of the frames inside the timed region (the read-back of step i runs on a copy stream under the kernels
+             of step i + 1; the region ends when the last copy has landed)
   ab         the two timings repeated alternately (device, e2e, device, e2e): resolves the host-copy cost from the
              box's clock noise
   roofline   the dominant kernel family: algorithmic FLOPs of its launches / their summed CUDA-event time over K
@@ -339,7 +340,7 @@ def run_reference_gpu(args):
 def run_b200(args):
     import torch.distributed as dist
     from image2video_synthesis_using_cinns_b200 import cli, lib
-    from image2video_synthesis_using_cinns_b200.dist import FrameGather
+    from image2video_synthesis_using_cinns_b200.dist import FrameGather, HostFrameSink
     from image2video_synthesis_using_cinns_b200.get_model import Model
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -373,7 +374,8 @@ def run_b200(args):
     passes = -(-args.seq_length // 16)
     T = 16 * passes
     gather = FrameGather(dev) if world > 1 else None
-    out_h = torch.empty(B, T, 3, img, img).pin_memory()
+    sink = HostFrameSink(dev)           # pinned double buffer + copy stream: read-back of step i under the compute of step i + 1
+    out_numel = B * T * 3 * img * img
 
     def run_model(x, r, q):
         return model.transfer(q, x) if transfer else model.sample(x, residual=r)
@@ -401,7 +403,7 @@ def run_b200(args):
         q = q_h.to(dev, non_blocking=True) if transfer else None
         seq = run_model(x, r, q)
         finish(seq)
-        out_h.copy_(seq, non_blocking=True)
+        sink.put(seq)
         return seq
 
     def timed(fn, steps, profile=False):
@@ -418,6 +420,7 @@ def run_b200(args):
             fn()
         if gather is not None:
             gather.wait()          # the compute stream owns every gathered batch before the closing event
+        torch.cuda.current_stream(dev).wait_stream(sink.stream)     # ... and every read-back has landed in host memory
         e1.record()
         torch.cuda.synchronize()
         barrier()
@@ -508,7 +511,9 @@ def run_b200(args):
             "dtype": dtype, "data": "synthetic start frames U[-1,1], random-init weights in the reference checkpoint format",
             "config": cfg,
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": world * out_h.numel() * 4},
+                    "d2h_bytes_per_step": world * out_numel * 4,
+                    "note": "H2D of the step's inputs on the compute stream; D2H of its frames on a copy stream behind the next step's "
+                            "kernels (dist.HostFrameSink), all copies complete inside the timed region"},
             "ab": {"device_ms_per_step": [ms / args.steps, ms_b / args.steps], "e2e_ms_per_step": [ms_e2e / args.steps, ms_e2e_b / args.steps]},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
         }

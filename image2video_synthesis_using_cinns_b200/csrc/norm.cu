@@ -247,8 +247,13 @@ __global__ void __launch_bounds__(256) modulate8_split_kernel(const ModArgs a, i
 }
 
 // Map-free variant (AdaIN / GroupNorm-affine / plain activation passes): one (b, t) plane per blockIdx.y -- a pure
-// stream, which DRAM serves better than 16 interleaved plane streams (measured: 5.3 vs 4.5 TB/s).
-__global__ void __launch_bounds__(256) modulate8_split_plane_kernel(const ModArgs a, int c8_shift, int w_shift) {
+// stream, which DRAM serves better than 16 interleaved plane streams (measured: 5.3 vs 4.5 TB/s).  A thread's channel group
+// is fixed (the grid stride is a multiple of C/8), so its 8 coefficient pairs are loaded ONCE instead of once per element
+// (they cost 4 of the 6 load instructions of an iteration: 3.7 TB/s at C = 128 against 6.0 TB/s without coefficients), two
+// elements are in flight per thread.  (Streaming stores, st.global.cs, for the fp16 pair were measured slower: 1.25 -> 1.32 /
+// 1.51 -> 1.75 ms on the two big SPADE passes, profiles/r02_bench_ab.txt.)
+template <bool COEF>
+__global__ void __launch_bounds__(256, 4) modulate8_split_plane_kernel(const ModArgs a, int c8_shift, int w_shift) {
     pdl_launch_dependents();
     pdl_wait();
     const int C8 = a.C >> 3;
@@ -257,30 +262,31 @@ __global__ void __launch_bounds__(256) modulate8_split_plane_kernel(const ModArg
     const int Ts = a.T / a.ut, Hs = a.H / a.uh, Ws = a.W / a.uw;
     const int per_plane = a.H * a.W * C8;
     const float4* xp = reinterpret_cast<const float4*>(a.x) + ((long long)(b * Ts + t / a.ut) * Hs * Ws) * (C8 * 2);
-    const float4* cf = a.coef ? reinterpret_cast<const float4*>(a.coef + (long long)b * a.C * 2) : nullptr;
-    const float4* gbp = a.gb ? reinterpret_cast<const float4*>(a.gb + (long long)b * a.H * a.W * 2 * a.C) : nullptr;
     uint4* oh = reinterpret_cast<uint4*>(a.out_hi) + (long long)plane * per_plane;
     uint4* ol = reinterpret_cast<uint4*>(a.out_lo) + (long long)plane * per_plane;
     const float s = a.split_scale;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per_plane; i += gridDim.x * blockDim.x) {
-        const int c8 = i & (C8 - 1);
+    const int i0 = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;    // stride % C8 == 0 (host-checked)
+    const int c8 = i0 & (C8 - 1);
+    float ca[8], cb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ca[j] = 1.f; cb[j] = 0.f; }
+    constexpr bool has_coef = COEF;
+    if (has_coef) {
+        const float4* c = reinterpret_cast<const float4*>(a.coef + (long long)b * a.C * 2) + c8 * 4;
+        const float4 c0 = __ldg(c), c1 = __ldg(c + 1), c2 = __ldg(c + 2), c3 = __ldg(c + 3);
+        ca[0] = c0.x; cb[0] = c0.y; ca[1] = c0.z; cb[1] = c0.w; ca[2] = c1.x; cb[2] = c1.y; ca[3] = c1.z; cb[3] = c1.w;
+        ca[4] = c2.x; cb[4] = c2.y; ca[5] = c2.z; cb[5] = c2.w; ca[6] = c3.x; cb[6] = c3.y; ca[7] = c3.z; cb[7] = c3.w;
+    }
+    auto src_of = [&](int i) {
         const int hw = i >> c8_shift;
         const int w = hw & (a.W - 1), h = hw >> w_shift;
-        const int src = ((h / a.uh) * Ws + (w / a.uw)) * (C8 * 2) + c8 * 2;
-        const float4 x0 = __ldg(xp + src), x1 = __ldg(xp + src + 1);
+        return ((h / a.uh) * Ws + (w / a.uw)) * (C8 * 2) + c8 * 2;
+    };
+    auto finish = [&](int i, const float4& x0, const float4& x1) {
         float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-        if (cf != nullptr) {
-            const float4* c = cf + c8 * 4;
-            const float4 c0 = __ldg(c), c1 = __ldg(c + 1), c2 = __ldg(c + 2), c3 = __ldg(c + 3);
-            v[0] = fmaf(c0.x, v[0], c0.y); v[1] = fmaf(c0.z, v[1], c0.w); v[2] = fmaf(c1.x, v[2], c1.y); v[3] = fmaf(c1.z, v[3], c1.w);
-            v[4] = fmaf(c2.x, v[4], c2.y); v[5] = fmaf(c2.z, v[5], c2.w); v[6] = fmaf(c3.x, v[6], c3.y); v[7] = fmaf(c3.z, v[7], c3.w);
-        }
-        if (gbp != nullptr) {
-            const float4* g = gbp + (long long)hw * (C8 * 4) + c8 * 2;      // row of 2C floats = C8*4 float4: gamma | beta
-            const float4 g0 = __ldg(g), g1 = __ldg(g + 1), b0 = __ldg(g + C8 * 2), b1 = __ldg(g + C8 * 2 + 1);
-            v[0] = fmaf(v[0], 1.f + g0.x, b0.x); v[1] = fmaf(v[1], 1.f + g0.y, b0.y); v[2] = fmaf(v[2], 1.f + g0.z, b0.z);
-            v[3] = fmaf(v[3], 1.f + g0.w, b0.w); v[4] = fmaf(v[4], 1.f + g1.x, b1.x); v[5] = fmaf(v[5], 1.f + g1.y, b1.y);
-            v[6] = fmaf(v[6], 1.f + g1.z, b1.z); v[7] = fmaf(v[7], 1.f + g1.w, b1.w);
+        if (has_coef) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaf(ca[j], v[j], cb[j]);
         }
         __half2 hh[4], ll[4];
 #pragma unroll
@@ -293,6 +299,26 @@ __global__ void __launch_bounds__(256) modulate8_split_plane_kernel(const ModArg
         }
         oh[i] = *reinterpret_cast<const uint4*>(hh);
         ol[i] = *reinterpret_cast<const uint4*>(ll);
+    };
+    int i = i0;
+    if (!COEF) {          // plain activation pass: the one-element loop already streams at 6.0 TB/s
+        for (; i < per_plane; i += stride) {
+            const int sa = src_of(i);
+            const float4 xa0 = __ldg(xp + sa), xa1 = __ldg(xp + sa + 1);
+            finish(i, xa0, xa1);
+        }
+        return;
+    }
+    for (; i + stride < per_plane; i += 2 * stride) {
+        const int sa = src_of(i), sb = src_of(i + stride);
+        const float4 xa0 = __ldg(xp + sa), xa1 = __ldg(xp + sa + 1), xb0 = __ldg(xp + sb), xb1 = __ldg(xp + sb + 1);
+        finish(i, xa0, xa1);
+        finish(i + stride, xb0, xb1);
+    }
+    if (i < per_plane) {
+        const int sa = src_of(i);
+        const float4 xa0 = __ldg(xp + sa), xa1 = __ldg(xp + sa + 1);
+        finish(i, xa0, xa1);
     }
 }
 
@@ -336,7 +362,7 @@ int launch_modulate(const ModArgs& a, cudaStream_t stream) {
     I2V_REQUIRE(a.outb_hi == nullptr || (a.coef_b && a.outb_lo && a.out_hi && a.r == nullptr && a.ut == 1 && a.uh == 1 && a.uw == 1 &&
                                          a.C % 8 == 0 && pow2(a.C / 8) && pow2(a.W)),
                 "modulate: the second result needs the 8-channel split path without upsampling");
-    if (a.out_hi != nullptr && a.r == nullptr && a.out_f32 == nullptr && a.C % 8 == 0 && pow2(a.C / 8) && pow2(a.W) &&
+    if (a.out_hi != nullptr && a.r == nullptr && a.out_f32 == nullptr && a.C % 8 == 0 && pow2(a.C / 8) && a.C / 8 <= 256 && pow2(a.W) &&
         (long long)a.T * a.H * a.W * (a.C / 8) < (1ll << 31) && (long long)a.B * a.T < 65536) {
         const int per_plane = a.H * a.W * (a.C / 8);
         int bx = (per_plane + 255) / 256;
@@ -352,7 +378,10 @@ int launch_modulate(const ModArgs& a, cudaStream_t stream) {
             int bp = (per_plane + 255) / 256;
             const int capp = (kNumSMs * 16 + planes - 1) / planes;
             if (bp > capp) bp = capp < 1 ? 1 : capp;
-            I2V_CHECK_CUDA(launch_k(modulate8_split_plane_kernel, dim3(bp, planes), dim3(256), 0, stream, a, ilog2(a.C / 8), ilog2(a.W)));
+            if (a.coef != nullptr)
+                I2V_CHECK_CUDA(launch_k(modulate8_split_plane_kernel<true>, dim3(bp, planes), dim3(256), 0, stream, a, ilog2(a.C / 8), ilog2(a.W)));
+            else
+                I2V_CHECK_CUDA(launch_k(modulate8_split_plane_kernel<false>, dim3(bp, planes), dim3(256), 0, stream, a, ilog2(a.C / 8), ilog2(a.W)));
         }
         return 0;
     }

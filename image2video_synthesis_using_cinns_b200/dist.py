@@ -106,6 +106,41 @@ class FrameGather:
         return self._pending
 
 
+class HostFrameSink:
+    """Device -> pinned-host read-back of finished frames on a copy stream: ``put(frames)`` returns at once, the copy runs
+    behind the caller's next kernels (two pinned buffers alternate), ``wait()`` blocks the HOST until the last copy has
+    landed and returns that buffer.  This is how a serving loop keeps the PCIe read-back of batch i under the compute of
+    batch i + 1; ``bench.py``'s end-to-end leg uses it."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._bufs, self._k, self._last = [None, None], 0, None
+        self._done = [None, None]
+
+    def put(self, frames):
+        k = self._k
+        if self._bufs[k] is None or self._bufs[k].shape != frames.shape or self._bufs[k].dtype != frames.dtype:
+            self._bufs[k] = torch.empty(frames.shape, dtype=frames.dtype).pin_memory()
+        if self._done[k] is not None:
+            self._done[k].synchronize()                                    # the buffer's previous copy (two puts ago)
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))    # frames are complete on the caller's stream
+        with torch.cuda.stream(self.stream):
+            self._bufs[k].copy_(frames, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        frames.record_stream(self.stream)
+        self._done[k], self._last = ev, k
+        self._k ^= 1
+        return self._bufs[k]
+
+    def wait(self):
+        if self._last is None:
+            return None
+        self._done[self._last].synchronize()
+        return self._bufs[self._last]
+
+
 class ShardedModel:
     """``Model`` whose ``forward`` splits the start-frame batch over the process group."""
 
