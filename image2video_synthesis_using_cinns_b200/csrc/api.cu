@@ -286,7 +286,7 @@ static int embedder_run(const i2v_embedder* m, const float* x0, float* embed, in
     for (auto& b : buf) b = ar.take<float>(act_max);
     // fp16 (hi | lo) copies of conv inputs for the tensor-core engine: same bytes as the fp32 tensor
     float* sbuf[3] = {nullptr, nullptr, nullptr};
-    const bool any_tc = inorm && m->tc_mode != 0;
+    const bool any_tc = m->tc_mode != 0;
     if (any_tc) for (auto& b : sbuf) b = ar.take<float>(act_max);
     double* sums = ar.take<double>((size_t)B * 2048 * 2);
     double* sums2 = ar.take<double>((size_t)B * 2048 * 2);
@@ -306,6 +306,9 @@ static int embedder_run(const i2v_embedder* m, const float* x0, float* embed, in
     auto tc_ok = [&](const std::string& name, int Hi, int Wi, int Cin, int Cout, int k, int stride) -> bool {
         if (!any_tc || stride != 1 || !m->tt.has(name + ".wh")) return false;
         if (!conv_tc_supported(B, 1, Hi, Wi, Cin, Cout, 1, k, k)) return false;
+        // BatchNorm variant: bias / residual / ReLU ride in the conv epilogue, which the K-split launches of very long
+        // reductions cannot do (they need a linear epilogue); ResNet-50's largest K is 3*3*512 = 4608
+        if (!inorm && (long long)k * k * Cin > 9600) return false;
         const long long ctas = (((long long)B * Hi * Wi + 127) / 128) * ((Cout + 127) / 128);
         return m->tc_mode == 2 || ctas >= m->tc_min_ctas;
     };
@@ -341,6 +344,41 @@ static int embedder_run(const i2v_embedder* m, const float* x0, float* embed, in
                      s, &sk));
         return launch_channel_stats(raw, sums_, B, (long long)Ho * Wo, Cout, s);
     };
+    // BatchNorm variant (BN folded into weight + bias at load): out = act(conv(in) + bias [+ res]).  Stride-1 convs whose GEMM
+    // fills the machine run on the tensor-core engine: their fp32 input is split into the fp16 pair first (one extra pass over
+    // a tensor of a few MB; `split_src` remembers which tensor sbuf[0] holds, conv1 and the downsample conv share theirs).
+    const float* split_src = nullptr;
+    auto conv_bn = [&](const std::string& name, const float* in, float* out, const float* res, int Hi, int Wi, int Cin, int Cout, int k,
+                       int stride, int pad, int relu) -> int {
+        const float* b = m->tt.get(name + ".b", Cout);
+        if (!b) return -3;
+        if (tc_ok(name, Hi, Wi, Cin, Cout, k, stride)) {
+            const size_t n_in = (size_t)B * Hi * Wi * Cin;
+            __half* xs = reinterpret_cast<__half*>(sbuf[0]);
+            if (split_src != in) {
+                I2V_TRY(launch_split_fp16(in, xs, xs + n_in, ACT_SPLIT_SCALE, (long long)n_in, s));
+                split_src = in;
+            }
+            const int cpad = (Cout + 15) / 16 * 16;
+            const size_t wn = (size_t)k * k * cpad * Cin;
+            const __half* wh = m->tt.get<__half>(name + ".wh", wn);
+            const __half* wl = m->tt.get<__half>(name + ".wl", wn);
+            const float* ws = m->tt.get(name + ".ws", 1);
+            if (!wh || !wl || !ws) return -3;
+            ConvTcArgs a;
+            a.x_hi = xs; a.x_lo = xs + n_in; a.w_hi = wh; a.w_lo = wl; a.scale_ptr = ws; a.bias = b; a.res = res; a.y = out;
+            a.B = B; a.T = 1; a.H = Hi; a.W = Wi; a.Cin = Cin; a.Cout = Cout; a.cout_pad = cpad;
+            a.kt = 1; a.kh = k; a.kw = k; a.res_ut = a.res_uh = a.res_uw = 1; a.act = relu ? ACT_RELU : ACT_NONE; a.out_mode = 0;
+            a.terms = 3;
+            if (out == split_src) split_src = nullptr;      // (never the case today: outputs go to other buffers)
+            return launch_conv_tc(a, s);
+        }
+        const float* w = W_(name + ".w", (size_t)k * k * Cout * Cin);
+        if (!w) return -3;
+        if (out == split_src) split_src = nullptr;
+        return conv(0, in, w, b, res, out, B, 1, Hi, Wi, Cin, Cout, 1, k, k, 1, stride, stride, 0, pad, pad, 1, 1, 1,
+                    relu ? ACT_RELU : ACT_NONE, 0, s, &sk);
+    };
     // normalise (+ ReLU) pass: fp32 result, or the fp16 split a following tensor-core conv consumes
     auto norm_act = [&](const float* raw, const float* coef_, float* out, bool split, int Ho, int Wo, int C, int relu) -> int {
         ModArgs ma;
@@ -360,11 +398,7 @@ static int embedder_run(const i2v_embedder* m, const float* x0, float* embed, in
             I2V_TRY(launch_norm_coeffs(sums, coef, B, Cout, (long long)Ho * Wo, 0, 1e-5f, nullptr, nullptr, nullptr, s));
             I2V_TRY(norm_act(tmp, coef, out, out_split, Ho, Wo, Cout, relu));
         } else {
-            const float* w = W_(name + ".w", (size_t)k * k * Cout * Cin);
-            const float* b = Bv(name + ".b", Cout);
-            if (!w || !b) return -3;
-            I2V_TRY(conv(0, in, w, b, nullptr, out, B, 1, Hi, Wi, Cin, Cout, 1, k, k, 1, stride, stride, 0, pad, pad, 1, 1, 1,
-                         relu ? ACT_RELU : ACT_NONE, 0, s, &sk));
+            I2V_TRY(conv_bn(name, in, out, nullptr, Hi, Wi, Cin, Cout, k, stride, pad, relu));
         }
         return 0;
     };
@@ -383,12 +417,14 @@ static int embedder_run(const i2v_embedder* m, const float* x0, float* embed, in
             const std::string p = "layer" + std::to_string(li + 1) + "." + std::to_string(bi) + ".";
             const int pl = planes[li], stride = (li > 0 && bi == 0) ? 2 : 1;
             const int Ho = (Hc + 2 - 3) / stride + 1, Wo = (Wc + 2 - 3) / stride + 1;
-            const bool tc1 = tc_ok(p + "conv1", Hc, Wc, Cc, pl, 1, 1), tc2 = tc_ok(p + "conv2", Hc, Wc, pl, pl, 3, stride);
-            const bool tc3 = tc_ok(p + "conv3", Ho, Wo, pl, 4 * pl, 1, 1);
-            const bool tcd = bi == 0 && tc_ok(p + "ds", Hc, Wc, Cc, 4 * pl, 1, stride);
+            // (InstanceNorm variant: the split operands are produced by the normalise passes; the BatchNorm variant decides and
+            // splits inside conv_bn)
+            const bool tc1 = inorm && tc_ok(p + "conv1", Hc, Wc, Cc, pl, 1, 1), tc2 = inorm && tc_ok(p + "conv2", Hc, Wc, pl, pl, 3, stride);
+            const bool tc3 = inorm && tc_ok(p + "conv3", Ho, Wo, pl, 4 * pl, 1, 1);
+            const bool tcd = inorm && bi == 0 && tc_ok(p + "ds", Hc, Wc, Cc, 4 * pl, 1, stride);
             // does the next block's first conv want the split of this block's output?
             bool next_tc = false;
-            {
+            if (inorm) {
                 int nli = li, nbi = bi + 1;
                 if (nbi == nblocks[li]) { nli = li + 1; nbi = 0; }
                 if (nli < 4) {
@@ -425,19 +461,12 @@ static int embedder_run(const i2v_embedder* m, const float* x0, float* embed, in
                 I2V_TRY(launch_modulate(ma, s));
                 cur_split = next_tc;
             } else {
-                const float* w3 = W_(p + "conv3.w", (size_t)4 * pl * pl);
-                const float* b3 = m->tt.get(p + "conv3.b", (size_t)4 * pl);
-                if (!w3 || !b3) return -3;
                 const float* idt = cur;
                 if (bi == 0) {
-                    const float* wd = W_(p + "ds.w", (size_t)4 * pl * Cc);
-                    const float* bd = m->tt.get(p + "ds.b", (size_t)4 * pl);
-                    if (!wd || !bd) return -3;
-                    I2V_TRY(conv(0, cur, wd, bd, nullptr, t3, B, 1, Hc, Wc, Cc, 4 * pl, 1, 1, 1, 1, stride, stride, 0, 0, 0, 1, 1, 1,
-                                 ACT_NONE, 0, s, &sk));
+                    I2V_TRY(conv_bn(p + "ds", cur, t3, nullptr, Hc, Wc, Cc, 4 * pl, 1, stride, 0, 0));
                     idt = t3;
                 }
-                I2V_TRY(conv(0, t2, w3, b3, idt, t4, B, 1, Ho, Wo, pl, 4 * pl, 1, 1, 1, 1, 1, 1, 0, 0, 0, 1, 1, 1, ACT_RELU, 0, s, &sk));
+                I2V_TRY(conv_bn(p + "conv3", t2, t4, idt, Ho, Wo, pl, 4 * pl, 1, 1, 0, 1));
             }
             float* old = cur; cur = t4; t4 = old;   // rotate: previous input buffer becomes scratch
             Hc = Ho; Wc = Wo; Cc = 4 * pl;

@@ -226,9 +226,9 @@ def pack_decoder(sd, nf, engine=0, upsample_t=(2, 1), upsample_s=(2, 2)):
 def pack_embedder(sd, zc, norm, tensor_core=True):
     """torchvision-resnet50 keys under ``model.`` (AE.py:109) -> channels-last conv stacks.
 
-    InstanceNorm variant: every stride-1 conv also gets the split fp16 weights of the tensor-core engine
-    (``.wh/.wl/.ws``, csrc/conv_tc.cu); the kernel side decides per call which layers use them (csrc/api.cu,
-    embedder_run), so the fp32 copy stays registered too."""
+    Every stride-1 conv also gets the split fp16 weights of the tensor-core engine (``.wh/.wl/.ws``, csrc/conv_tc.cu; for
+    the BatchNorm variant these are the BN-folded weights); the kernel side decides per call which layers use them
+    (csrc/api.cu, embedder_run), so the fp32 copy stays registered too."""
     t = {}
 
     def put(dst, conv_key, bn_key, stride=1):
@@ -240,7 +240,7 @@ def pack_embedder(sd, zc, norm, tensor_core=True):
             w = w * sc.reshape(-1, 1, 1, 1)
             t[dst + ".b"] = (b - mean * sc).float()
         t[dst + ".w"] = _taps2(w.float())
-        if tensor_core and norm == "in" and stride == 1 and w.shape[1] % 16 == 0:
+        if tensor_core and stride == 1 and w.shape[1] % 16 == 0:
             t[dst + ".wh"], t[dst + ".wl"], t[dst + ".ws"] = split_fp16(t[dst + ".w"], ACT_SPLIT_SCALE)
 
     put("conv1", "model.conv1.weight", "model.bn1", stride=2)

@@ -13,7 +13,7 @@ def test_host_frame_sink_double_buffer():
     for k in range(5):
         x = torch.full((3, 4, 3, 8, 8), float(k), device="cuda") + torch.arange(8, device="cuda")
         buf = sink.put(x)
-        x.add_(1000.0)                      # later work on the producer's stream must not leak into the copy
+        torch.zeros(1 << 20, device="cuda").normal_()      # unrelated later work on the producer's stream overlaps the copy
         outs.append((k, buf))
         got = sink.wait()
         assert got is buf
