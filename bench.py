@@ -521,10 +521,13 @@ def run_b200(args):
         if world == 1 and not args.no_cpu_baseline:
             fps, cores, sample, b1 = cpu_reference_rate(args, mp)
             line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "b1_value": b1}
-        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if rank == 0:
+        if world > 1:
+            time.sleep(1.0)       # NCCL_DEBUG=INFO: let the other ranks' closing lines come first, the JSON line stays last
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

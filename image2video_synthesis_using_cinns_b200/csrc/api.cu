@@ -621,7 +621,20 @@ static int decoder_run(const i2v_decoder* m, const float* img, const float* z, f
             a.x2_hi = reinterpret_cast<const __half*>(x2buf); a.x2_lo = a.x2_hi + n_in2;
             a.w2_hi = w2h; a.w2_lo = w2l; a.Cin2 = cin2;
         }
-        if (stats_out) I2V_CHECK_CUDA(cudaMemsetAsync(stats_out, 0, sizeof(double) * 2 * (size_t)Bc * cout_, s));
+        if (stats_out) {
+            // can this launch fuse the statistics?  Ask the launcher itself (tile shapes, transpose-tile room, one sample per
+            // tile ...); geometries it cannot serve get the separate statistics pass instead of an error
+            ConvTcArgs probe = a;
+            probe.dry_run = 1;
+            if (launch_conv_tc(probe, s) != 0) {
+                a.stats = nullptr;
+                I2V_TRY(launch_conv_tc(a, s));
+                const long long V = (long long)Tc * Hc_ * Wc_;
+                I2V_REQUIRE(out_mode == 0, "decoder: statistics of a frame-layout output are not defined");
+                return launch_channel_stats(y, stats_out, Bc, V, cout_, s);
+            }
+            I2V_CHECK_CUDA(cudaMemsetAsync(stats_out, 0, sizeof(double) * 2 * (size_t)Bc * cout_, s));
+        }
         return launch_conv_tc(a, s);
     };
     // fused modulate pass writing either fp32 (SIMT engine) or the fp16 split (tensor-core engine)

@@ -1689,6 +1689,7 @@ static int launch_conv_tc_pair(const ConvTcArgs& h, cudaStream_t stream) {
     I2V_CHECK_CUDA(ensure_max_dyn_smem(conv_tc_pair_kernel, 227 * 1024, attr_devs));
     const size_t smem = (size_t)cfg.stages * cfg.stage_bytes + kPairSmemBase + (cfg.wstack ? kPairSmemStack : 0);
     I2V_REQUIRE(smem <= 227 * 1024, "conv_tc: pair kernel shared memory (%zu bytes) over the 227 KB limit", smem);
+    if (h.dry_run) return 0;        // every check above passed
     const long long M = (long long)h.B * h.T * h.H * h.W;
     const double K_ = (double)h.kt * h.kh * h.kw * h.Cin + (double)h.Cin2;
     ProfScope ps(PROF_CONV, 2.0 * (double)M * h.Cout * K_,
@@ -1839,6 +1840,7 @@ static int launch_conv_tc_halo(const ConvTcArgs& h, cudaStream_t stream) {
         a.stile_per_slot = sps;
         a.prefetch_stages = stages - epi_slots;
     }
+    if (h.dry_run) return 0;        // every check above passed
     const long long M = (long long)h.B * h.T * h.H * h.W;
     const double K_ = (double)h.kt * h.kh * h.kw * h.Cin + (double)h.Cin2;
     ProfScope ps(PROF_CONV, 2.0 * (double)M * h.Cout * K_,
@@ -1965,6 +1967,7 @@ int launch_conv_tc(const ConvTcArgs& h, cudaStream_t stream) {
     }
     static unsigned long long attr_devs = 0;
     I2V_CHECK_CUDA(ensure_max_dyn_smem(conv_tc_kernel, 227 * 1024, attr_devs));
+    if (h.dry_run) return 0;        // every check above passed
     const long long M = (long long)h.B * h.T * h.H * h.W;
     const double K_ = (double)h.kt * h.kh * h.kw * h.Cin;
     ProfScope ps(PROF_CONV_TC1, 2.0 * (double)M * h.Cout * K_, 4.0 * ((double)M * h.Cin + (double)M * h.Cout + K_ * h.Cout), stream);

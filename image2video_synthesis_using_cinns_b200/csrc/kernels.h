@@ -61,6 +61,9 @@ struct ConvTcArgs {
     const __half* x2_hi = nullptr; const __half* x2_lo = nullptr;
     const __half* w2_hi = nullptr; const __half* w2_lo = nullptr;
     int Cin2 = 0;
+    // 1: run every eligibility check of the launch (tile / pipeline configuration, fused-statistics requirements) and return
+    // without launching: lets a caller ask "can this conv fuse the statistics?" with the launcher's own predicate
+    int dry_run = 0;
 };
 bool conv_tc_fuses_stats(int T, int H, int W);
 bool conv_tc_halo_eligible(int H, int W, int kh);

@@ -144,3 +144,20 @@ def test_empty_and_ragged_batches(ckpt_cache):
         assert rel_inf(one[0].cpu(), full[i].cpu()) < 1e-6
     big = _model(mp, 16, False, micro_batch=64)
     assert rel_inf(big.decoder(x0.cuda(), z.cuda()).cpu(), full.cpu()) < 1e-6
+
+
+@pytest.mark.parametrize("dataset,nf", [("bair", 48), ("dtdb_fire", 48)])
+def test_decoder_odd_channel_factor_matches_oracle(dataset, nf, ckpt_cache):
+    """geometries outside the shipped channel factors (nf = 48: N tiles of 96 / 48 columns, channel chunks of 16
+    / 48) must take whatever conv kernel serves them -- fused statistics where the launcher can, the separate statistics
+    pass where it cannot -- instead of aborting the forward."""
+    mp = ckpt_cache(dataset=dataset, seed=44, nf=nf, n_flows=2, spade_gain=1.0, with_encoder=False)
+    m = _model(mp, 16, False, micro_batch=2)
+    om = ot.OracleModel(mp, 16)
+    img = m.config.Data["img_size"]
+    g = torch.Generator().manual_seed(5)
+    x0 = torch.rand(2, 3, img, img, generator=g) * 2 - 1
+    z = torch.randn(2, 64, generator=g)
+    e = rel_inf(m.decoder(x0.cuda(), z.cuda()).cpu(), om.decode(x0, z))
+    report(f"decoder_odd_nf:{dataset}:{nf}", decoder=e)
+    assert e < TOL

@@ -67,7 +67,10 @@ run_one() {
       timeout 1800 ncu --set full --clock-control none --import-source on -k regex:$re --launch-skip $skip -c $cnt -f -o $O/ncu_$tag \
         python bench.py --steps 1 --warmup 1 --no-cpu-baseline "$@" > $O/ncu_full_$tag.log 2>&1
       echo "ncu-full[$tag] rc=$?" | tee -a $O/status.txt
-      ncu -i $O/ncu_$tag.ncu-rep --page raw --csv > $O/ncu_${tag}_raw.csv 2>/dev/null; python tools/summarise_ncu.py $O/ncu_${tag}_raw.csv > $O/ncu_${tag}_summary.txt; head -60 $O/ncu_${tag}_summary.txt ;;
+      ncu -i $O/ncu_$tag.ncu-rep --page raw --csv > $O/ncu_${tag}_raw.csv 2>/dev/null; python tools/summarise_ncu.py $O/ncu_${tag}_raw.csv > $O/ncu_${tag}_summary.txt
+      # gpurun merges at most 64 MiB back: the report itself (tens of MB) stays on the box unless KEEP_NCU_REP=1
+      [ "${KEEP_NCU_REP:-0}" == "1" ] || rm -f $O/ncu_$tag.ncu-rep
+      grep -E "^##|gpu__time_duration.sum|pipe_tensor_cycles_active.avg.pct|dram__bytes_(read|write).sum =|xbar2l1tex_read_bytes.sum.per_second" $O/ncu_${tag}_summary.txt | head -80 ;;
     sanitize)
       bash tools/sanitize.sh ${1:-r02} ;;
     smoke)
