@@ -87,8 +87,10 @@ def parse():
     ap.add_argument("--streams", type=int, default=1, help="decoder micro-batches alternate over this many CUDA streams")
     ap.add_argument("--dump-launches", default=None, help="CSV of per-launch device times of the timed steps")
     ap.add_argument("--opt", action="append", default=[], help="name=value tuning switch (i2v_set_option), A/B runs")
-    ap.add_argument("--gather", default="overlap", choices=["overlap", "inline", "uint8"],
-                    help="N>1: all-gather on a side stream behind the step (default), on the compute stream, or of uint8 pixels")
+    ap.add_argument("--gather", default="overlap", choices=["overlap", "inline", "uint8", "p2p"],
+                    help="N>1: NCCL all-gather of the frames on a side stream behind the next step (default), on the compute stream "
+                         "(inline), of uint8 pixels, or EXPERIMENTAL peer-to-peer copies into symmetric memory (p2p: passes "
+                         "tools/check_gather.py, but a full bench run at N = 2 hung -- do not use for measurements)")
     ap.add_argument("--graph", type=int, default=0, help="1: replay each decoder micro-batch from a CUDA graph")
     a = ap.parse_args()
     c = CONFIGS[a.config]
@@ -373,7 +375,7 @@ def run_b200(args):
     q_d = q_h.to(dev) if transfer else None
     passes = -(-args.seq_length // 16)
     T = 16 * passes
-    gather = FrameGather(dev) if world > 1 else None
+    gather = FrameGather(dev, mode="p2p" if args.gather == "p2p" else "nccl") if world > 1 else None
     sink = HostFrameSink(dev)           # pinned double buffer + copy stream: read-back of step i under the compute of step i + 1
     out_numel = B * T * 3 * img * img
 
@@ -505,7 +507,9 @@ def run_b200(args):
                                    2: "fp16 operands, one tensor-core product per MAC, fp32 accumulate (flow/embedder fp32-grade)",
                                    0: "fp32 FFMA"}[args.conv_engine],
                     "conv_engine": args.conv_engine, "micro_batch": args.micro_batch, "streams": args.streams,
-                    "gather": args.gather if world > 1 else None, "graph": args.graph, "options": args.opt})
+                    "gather": (args.gather if args.gather != "p2p" else gather.mode) if world > 1 else None,
+                    "gather_fallback": getattr(gather, "fallback_reason", None) if world > 1 else None,
+                    "graph": args.graph, "options": args.opt})
         line = {
             "metric": args.metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

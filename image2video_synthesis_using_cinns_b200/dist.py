@@ -76,28 +76,63 @@ def global_residual(n, z_dim, group=None, device=None):
 
 
 class FrameGather:
-    """All-gather of finished frames on a side stream (NCCL): ``submit(frames)`` returns at once, the collective runs
-    behind the caller's next kernels, ``wait()`` makes the caller's stream own the gathered tensor.  Two output buffers
-    alternate, so one gather may be in flight while the previous result is still being read."""
+    """All-gather of finished frames on a side stream: ``submit(frames)`` returns at once, the transfer runs behind the
+    caller's next kernels, ``wait()`` makes the caller's stream own the gathered tensor.  Two output buffers alternate, so
+    one gather may be in flight while the previous result is still being read.
 
-    def __init__(self, device, group=None):
+    ``mode="nccl"`` (default): one ``all_gather_into_tensor`` on the side stream (its kernel finds its SMs between the
+    persistent conv kernels of the next step: measured +0.7 / +2 ms per step at N = 2 / 4).
+    ``mode="p2p"`` (EXPERIMENTAL): the output buffers live in symmetric memory (``torch.distributed._symmetric_memory``)
+    and every rank WRITES its shard straight into its peers' buffers with peer-to-peer copies -- NVLink through the copy
+    engines, no SM taken from the conv kernels -- bracketed by two device-side barriers on the side stream.  It passes
+    ``tools/check_gather.py`` at N = 2, but a full ``bench.py`` run hung with it (round 2, not yet understood): not used
+    by default."""
+
+    def __init__(self, device, group=None, mode="nccl"):
         self.device, self.group = torch.device(device), group
         self.stream = torch.cuda.Stream(device=self.device)
         self._bufs, self._k, self._pending = [None, None], 0, None
+        self.mode = mode
+        self._sym = [None, None]          # (handle, [peer views]) per buffer
+        self._n = 0
+
+    def _p2p_buffers(self, k, shape, dtype):
+        import torch.distributed._symmetric_memory as symm
+        world = dist.get_world_size(self.group)
+        buf = symm.empty(*shape, dtype=dtype, device=self.device)
+        hdl = symm.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+        peers = [hdl.get_buffer(r, shape, dtype) for r in range(world)]
+        self._bufs[k], self._sym[k] = buf, (hdl, peers)
 
     def submit(self, frames):
-        world = dist.get_world_size(self.group)
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
         frames = frames.contiguous()
         k = self._k
-        shape = (world * frames.shape[0],) + tuple(frames.shape[1:])
-        if self._bufs[k] is None or self._bufs[k].shape != shape or self._bufs[k].dtype != frames.dtype:
-            self._bufs[k] = torch.empty(shape, dtype=frames.dtype, device=self.device)
+        rows = frames.shape[0]
+        shape = (world * rows,) + tuple(frames.shape[1:])
+        if self._bufs[k] is None or tuple(self._bufs[k].shape) != shape or self._bufs[k].dtype != frames.dtype:
+            if self.mode == "p2p":
+                try:
+                    self._p2p_buffers(k, shape, frames.dtype)
+                except Exception as e:          # no symmetric memory on this system / group: NCCL path
+                    self.mode, self.fallback_reason = "nccl", repr(e)
+            if self.mode != "p2p":
+                self._bufs[k], self._sym[k] = torch.empty(shape, dtype=frames.dtype, device=self.device), None
         self.stream.wait_stream(torch.cuda.current_stream(self.device))     # frames are complete on the caller's stream
         with torch.cuda.stream(self.stream):
-            dist.all_gather_into_tensor(self._bufs[k], frames, group=self.group)
+            if self.mode == "p2p" and self._sym[k] is not None:
+                hdl, peers = self._sym[k]
+                hdl.barrier(channel=0)            # every rank is past the consumers of this buffer's previous content
+                for i in range(world):
+                    r = (rank + i) % world        # start with the local copy, then walk the peers in a rotated order
+                    peers[r][rank * rows:(rank + 1) * rows].copy_(frames, non_blocking=True)
+                hdl.barrier(channel=1)            # all shards have landed in this rank's buffer
+            else:
+                dist.all_gather_into_tensor(self._bufs[k], frames, group=self.group)
         frames.record_stream(self.stream)                                   # the allocator must not recycle it early
         self._pending = self._bufs[k]
         self._k ^= 1
+        self._n += 1
         return self._pending
 
     def wait(self):
