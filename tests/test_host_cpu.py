@@ -137,7 +137,12 @@ def test_pack_embedder_in_adds_tensor_core_split():
     s = 1.0 / (loader.ACT_SPLIT_SCALE * float(ws))
     assert ((hi.double() + lo.double()) / s - w.double()).abs().max() / w.abs().max() < 2 ** -21
     assert not any(k.endswith(".wh") for k in loader.pack_embedder(sd, 64, "in", tensor_core=False))
-    assert not any(k.endswith(".wh") for k in loader.pack_embedder(synthetic.embedder_state_dict(gen, 64, "bn"), 64, "bn"))
+    # BatchNorm variant (round 2): the BN-folded stride-1 weights carry the split too, next to weight + bias
+    tb = loader.pack_embedder(synthetic.embedder_state_dict(gen, 64, "bn"), 64, "bn")
+    assert "layer1.0.conv1.wh" in tb and "layer1.0.conv1.b" in tb and "layer2.0.conv2.wh" not in tb
+    wb, hb, lb, sb = tb["layer2.1.conv2.w"], tb["layer2.1.conv2.wh"], tb["layer2.1.conv2.wl"], tb["layer2.1.conv2.ws"]
+    sb = 1.0 / (loader.ACT_SPLIT_SCALE * float(sb))
+    assert ((hb.double() + lb.double()) / sb - wb.double()).abs().max() / wb.abs().max() < 2 ** -21
 
 
 def test_embed_pos_wraps_inside_its_block_like_the_reference():
@@ -157,3 +162,32 @@ def test_embed_pos_wraps_inside_its_block_like_the_reference():
         for k in range(3):
             assert got[b, k * 10 + (idx[b, k].item() % 10)] == 1        # python's % = the reference's negative indexing
     assert torch.equal(got, ot.embed_pos(pos))
+
+
+def test_pack_flow_chunks_is_the_per_cta_k_major_stream():
+    """`wpack` of the cluster-resident flow kernel (csrc/flow_cluster.cu): per coupling and CTA rank the x-part of the first
+    Linear, the hidden Linears and the last Linear, k-major, in consumption order."""
+    gen = torch.Generator().manual_seed(8)
+    n_flows, H, depth = 3, 256, 2
+    sd = synthetic.flow_state_dict(gen, 64, 64, H, depth, n_flows, False)
+    t, _, _ = loader.pack_flow(sd, n_flows, 64, 64, H, depth, False)
+    wp = t["wpack"]
+    Cc = H // 8
+    assert wp.shape == (n_flows * 2, 16, 1 + depth * (H // 32) + 1, 32 * Cc)
+    flat = wp.reshape(n_flows * 2, 16, -1)
+    for c, r in ((0, 0), (3, 5), (5, 12)):
+        fl, i, net, j = c // 2, c % 2, r // 8, r % 8
+        cols = slice(j * Cc, (j + 1) * Cc)
+        s = flat[c, r]
+        l1 = s[: 32 * Cc].reshape(32, Cc)                                   # [k][col]
+        assert torch.equal(l1, t["w1x"][fl, i, net * H:(net + 1) * H][cols].t())
+        off = 32 * Cc
+        for l in range(depth):
+            hid = s[off: off + H * Cc].reshape(H, Cc)                       # all k-rows of the layer, chunk after chunk
+            assert torch.equal(hid, t["wh"][fl, i, l, net][cols].t())
+            off += H * Cc
+        last = s[off: off + 4 * H].reshape(H, 4)
+        assert torch.equal(last, t["wo"][fl, i, net * 32 + 4 * j: net * 32 + 4 * j + 4].t())
+    # geometries the cluster kernel does not take keep the cooperative kernel's tensors only
+    t128, _, _ = loader.pack_flow(synthetic.flow_state_dict(gen, 64, 64, 128, 2, 2, False), 2, 64, 64, 128, 2, False)
+    assert "wpack" not in t128
