@@ -215,6 +215,7 @@ int i2v_set_option(const char* name, double value) {
     else if (k == "tc_pair_stages") t.tc_pair_stages = v < 0 ? 0 : v;
     else if (k == "linear_bfly") t.linear_bfly = v != 0;
     else if (k == "flow_cluster") t.flow_cluster = v != 0;
+    else if (k == "mod_spade") t.mod_spade = v != 0;
     else I2V_REQUIRE(false, "set_option: unknown option '%s'", name);
     return 0;
 }
@@ -813,6 +814,8 @@ void i2v_decoder_destroy(i2v_decoder* h) { delete h; }
 // =============================================================================== 3-D encoder
 struct i2v_encoder3d {
     int ch[5], ss[4], st[4], z_dim;
+    int tc_mode = 1;      // 0: fp32 SIMT convs only  1: tensor-core engine for stride-1 convs that fill >= tc_min_ctas tiles  2: wherever supported
+    int tc_min_ctas = 8;
     TensorTable tt;
 };
 
@@ -820,6 +823,12 @@ struct i2v_encoder3d {
 // (resnet3D.py:101-135; the downsample branch is a 3x3x3 conv + GN, :185-193) -> conv_mu on the
 // 4x4 map, emitted as (mu | logvar) [B, 2*z_dim]; the reparameterised sample (resnet3D.py:202-206)
 // is formed by the caller from CPU noise like the reference does.
+//
+// Engines (round 2): the stride-1 3x3x3 convs -- conv2 of every block, conv1 of every second block, and conv1 / downsample of a
+// stride-1 stage: 3/4 of the encoder's 52 GFLOP per clip -- run on the tensor-core engine (error-compensated fp16 split,
+// conv_tc.cu) whenever their GEMM has >= tc_min_ctas 128 x 128 tiles: the GroupNorm+ReLU pass feeding such a conv writes the
+// fp16 pair, the block's final pass writes the fp32 tensor (next residual) AND its split, and GroupNorm's sums come out of the
+// conv epilogue.  Strided convs, the Cin = 3 stem and the 1x4x4 tail stay on the fp32 SIMT engine (split-K).
 static int encoder3d_run(const i2v_encoder3d* m, const float* seq, float* mu, int B, int T, int H, int W, Arena& ar,
                          cudaStream_t s, bool dry) {
     auto od = [](int n, int k, int st, int p) { return (n + 2 * p - k) / st + 1; };
@@ -839,6 +848,10 @@ static int encoder3d_run(const i2v_encoder3d* m, const float* seq, float* mu, in
     float* xin = ar.take<float>((size_t)B * T * H * W * 3);
     float* buf[4];
     for (auto& b : buf) b = ar.take<float>(amax);
+    // fp16 (hi | lo) copies of tensor-core conv inputs: same bytes as the fp32 tensor
+    const bool any_tc = m->tc_mode != 0;
+    float* cur_s = any_tc ? ar.take<float>(amax) : nullptr;     // split of the block input / output
+    float* mid_s = any_tc ? ar.take<float>(amax) : nullptr;     // split of relu(GN(conv1))
     double* sums = ar.take<double>((size_t)B * cmax * 2);
     double* sums2 = ar.take<double>((size_t)B * cmax * 2);
     float* coef = ar.take<float>((size_t)B * cmax * 2);
@@ -850,6 +863,51 @@ static int encoder3d_run(const i2v_encoder3d* m, const float* seq, float* mu, in
     if (dry) return 0;
     I2V_CHECK_CUDA(cudaMemsetAsync(sk.counters, 0, sizeof(unsigned) * kSplitKTiles, s));
     auto G = [&](const std::string& n, size_t e) { return m->tt.get(n, e); };
+    // does this 3x3x3 conv run on the tensor-core engine?  (mode 2 forces it wherever the shape is supported: test aid)
+    auto tc_ok = [&](const std::string& name, int Ti, int Hi, int Wi, int Cin, int Cout, int st_, int ss_) -> bool {
+        if (!any_tc || st_ != 1 || ss_ != 1 || !m->tt.has(name + ".wh")) return false;
+        if (!conv_tc_supported(B, Ti, Hi, Wi, Cin, Cout, 3, 3, 3)) return false;
+        const long long ctas = (((long long)B * Ti * Hi * Wi + 127) / 128) * ((Cout + 127) / 128);
+        return m->tc_mode == 2 || ctas >= m->tc_min_ctas;
+    };
+    // raw = conv3x3x3(split input) on the tensor-core engine + per-(sample, channel) sums of raw (fused where the launcher can)
+    auto conv_tc_stats = [&](const std::string& name, const float* xs, float* raw, double* sums_, int Ti, int Hi, int Wi, int Cin,
+                             int Cout) -> int {
+        const int cpad = (Cout + 15) / 16 * 16;
+        const size_t wn = (size_t)27 * cpad * Cin, n_in = (size_t)B * Ti * Hi * Wi * Cin;
+        const __half* wh = m->tt.get<__half>(name + ".wh", wn);
+        const __half* wl = m->tt.get<__half>(name + ".wl", wn);
+        const float* ws = m->tt.get(name + ".ws", 1);
+        if (!wh || !wl || !ws) return -3;
+        ConvTcArgs a;
+        a.x_hi = reinterpret_cast<const __half*>(xs); a.x_lo = a.x_hi + n_in;
+        a.w_hi = wh; a.w_lo = wl; a.scale_ptr = ws; a.bias = nullptr; a.res = nullptr; a.y = raw;
+        a.B = B; a.T = Ti; a.H = Hi; a.W = Wi; a.Cin = Cin; a.Cout = Cout; a.cout_pad = cpad;
+        a.kt = a.kh = a.kw = 3; a.res_ut = a.res_uh = a.res_uw = 1; a.act = ACT_NONE; a.out_mode = 0;
+        a.terms = 3;
+        a.stats = sums_;
+        ConvTcArgs probe = a;
+        probe.dry_run = 1;
+        if (launch_conv_tc(probe, s) != 0) {        // this geometry cannot fuse the statistics: separate pass
+            a.stats = nullptr;
+            I2V_TRY(launch_conv_tc(a, s));
+            return launch_channel_stats(raw, sums_, B, (long long)Ti * Hi * Wi, Cout, s);
+        }
+        I2V_CHECK_CUDA(cudaMemsetAsync(sums_, 0, sizeof(double) * 2 * (size_t)B * Cout, s));
+        return launch_conv_tc(a, s);
+    };
+    // GroupNorm (+ residual branch) + ReLU pass: fp32 result, the fp16 split a tensor-core conv consumes, or both
+    auto norm_act = [&](const float* raw, const float* coef_, const float* res_, const float* coef2_, float* out_f32, float* out_split,
+                        int To_, int Ho_, int Wo_, int C_) -> int {
+        ModArgs ma;
+        ma.x = raw; ma.coef = coef_; ma.gb = nullptr; ma.r = res_; ma.coef2 = coef2_; ma.out = out_f32;
+        ma.B = B; ma.T = To_; ma.H = Ho_; ma.W = Wo_; ma.C = C_; ma.ut = ma.uh = ma.uw = 1; ma.act = ACT_RELU;
+        if (out_split != nullptr) {
+            ma.out_hi = reinterpret_cast<__half*>(out_split); ma.out_lo = ma.out_hi + (size_t)B * To_ * Ho_ * Wo_ * C_;
+            ma.split_scale = ACT_SPLIT_SCALE; ma.out_f32 = out_f32;
+        }
+        return launch_modulate(ma, s);
+    };
 
     // [B,T,3,H,W] -> [B,T,H,W,3]
     I2V_TRY(launch_resize_bilinear_nchw_to_nhwc(seq, xin, B * T, 3, H, W, H, W, s));
@@ -864,6 +922,7 @@ static int encoder3d_run(const i2v_encoder3d* m, const float* seq, float* mu, in
     float* cur = buf[0]; float* ta = buf[1]; float* tb = buf[2]; float* tc = buf[3];
     int Tc = T1, Hc = H1, Wc = W1, Cc = 64;   // resnet3D.py:140 hard-codes inplanes = 64
     I2V_REQUIRE(m->ch[0] == 64, "encoder3d: channels[0] must be 64 (resnet3D.py:140)");
+    bool cur_split = false;                 // cur_s holds the split of cur
     for (int l = 0; l < 4; ++l) {
         const int pl = m->ch[l + 1];
         for (int bi = 0; bi < 2; ++bi) {
@@ -871,31 +930,64 @@ static int encoder3d_run(const i2v_encoder3d* m, const float* seq, float* mu, in
             const int st = bi == 0 ? m->st[l] : 1, ss = bi == 0 ? m->ss[l] : 1;
             const int To = od(Tc, 3, st, 1), Ho = od(Hc, 3, ss, 1), Wo = od(Wc, 3, ss, 1);
             const long long Vo = (long long)To * Ho * Wo;
-            I2V_PTR(wc1, G(p + "conv1.w", (size_t)27 * pl * Cc));
+            const bool has_ds = m->tt.has(p + "ds.w");
             I2V_PTR(g1w, G(p + "bn1.w", pl)); I2V_PTR(g1b, G(p + "bn1.b", pl));
-            I2V_PTR(wc2, G(p + "conv2.w", (size_t)27 * pl * pl));
             I2V_PTR(g2w, G(p + "bn2.w", pl)); I2V_PTR(g2b, G(p + "bn2.b", pl));
+            const bool tc1 = tc_ok(p + "conv1", Tc, Hc, Wc, Cc, pl, st, ss), tc2 = tc_ok(p + "conv2", To, Ho, Wo, pl, pl, 1, 1);
+            const bool tcd = has_ds && tc_ok(p + "ds", Tc, Hc, Wc, Cc, pl, st, ss);
+            // does the next block's conv1 / downsample conv want the split of this block's output?
+            bool next_tc = false;
+            {
+                const int nl = bi == 0 ? l : l + 1, nbi = bi == 0 ? 1 : 0;
+                if (nl < 4) {
+                    const std::string np = "layer." + std::to_string(nl) + "." + std::to_string(nbi) + ".";
+                    const int nst = nbi == 0 ? m->st[nl] : 1, nss = nbi == 0 ? m->ss[nl] : 1;
+                    next_tc = tc_ok(np + "conv1", To, Ho, Wo, pl, m->ch[nl + 1], nst, nss) ||
+                              (m->tt.has(np + "ds.w") && tc_ok(np + "ds", To, Ho, Wo, pl, m->ch[nl + 1], nst, nss));
+                }
+            }
+            if ((tc1 || tcd) && !cur_split) {
+                const long long n = (long long)B * Tc * Hc * Wc * Cc;
+                I2V_TRY(launch_split_fp16(cur, reinterpret_cast<__half*>(cur_s), reinterpret_cast<__half*>(cur_s) + n, ACT_SPLIT_SCALE, n, s));
+                cur_split = true;
+            }
             // o = relu(GN(conv1(h)))
-            I2V_TRY(conv(0, cur, wc1, nullptr, nullptr, ta, B, Tc, Hc, Wc, Cc, pl, 3, 3, 3, st, ss, ss, 1, 1, 1, 1, 1, 1, ACT_NONE, 0, s, &sk));
-            I2V_TRY(launch_channel_stats(ta, sums, B, Vo, pl, s));
+            if (tc1) {
+                I2V_TRY(conv_tc_stats(p + "conv1", cur_s, ta, sums, Tc, Hc, Wc, Cc, pl));
+            } else {
+                I2V_PTR(wc1, G(p + "conv1.w", (size_t)27 * pl * Cc));
+                I2V_TRY(conv(0, cur, wc1, nullptr, nullptr, ta, B, Tc, Hc, Wc, Cc, pl, 3, 3, 3, st, ss, ss, 1, 1, 1, 1, 1, 1, ACT_NONE, 0, s, &sk));
+                I2V_TRY(launch_channel_stats(ta, sums, B, Vo, pl, s));
+            }
             I2V_TRY(launch_norm_coeffs(sums, coef, B, pl, Vo, 16, 1e-5f, g1w, g1b, nullptr, s));
-            I2V_TRY(modulate(ta, coef, nullptr, nullptr, nullptr, tb, B, To, Ho, Wo, pl, 1, 1, 1, ACT_RELU, s));
+            I2V_TRY(norm_act(ta, coef, nullptr, nullptr, tc2 ? nullptr : tb, tc2 ? mid_s : nullptr, To, Ho, Wo, pl));
             // o = GN(conv2(o))
-            I2V_TRY(conv(0, tb, wc2, nullptr, nullptr, ta, B, To, Ho, Wo, pl, pl, 3, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, ACT_NONE, 0, s, &sk));
-            I2V_TRY(launch_channel_stats(ta, sums, B, Vo, pl, s));
+            if (tc2) {
+                I2V_TRY(conv_tc_stats(p + "conv2", mid_s, ta, sums, To, Ho, Wo, pl, pl));
+            } else {
+                I2V_PTR(wc2, G(p + "conv2.w", (size_t)27 * pl * pl));
+                I2V_TRY(conv(0, tb, wc2, nullptr, nullptr, ta, B, To, Ho, Wo, pl, pl, 3, 3, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, ACT_NONE, 0, s, &sk));
+                I2V_TRY(launch_channel_stats(ta, sums, B, Vo, pl, s));
+            }
             I2V_TRY(launch_norm_coeffs(sums, coef, B, pl, Vo, 16, 1e-5f, g2w, g2b, nullptr, s));
             const float* res = cur; const float* c2 = nullptr;
-            if (m->tt.has(p + "ds.w")) {
-                I2V_PTR(wd, G(p + "ds.w", (size_t)27 * pl * Cc));
+            if (has_ds) {
                 I2V_PTR(gdw, G(p + "ds.gn.w", pl)); I2V_PTR(gdb, G(p + "ds.gn.b", pl));
-                I2V_TRY(conv(0, cur, wd, nullptr, nullptr, tb, B, Tc, Hc, Wc, Cc, pl, 3, 3, 3, st, ss, ss, 1, 1, 1, 1, 1, 1, ACT_NONE, 0, s, &sk));
-                I2V_TRY(launch_channel_stats(tb, sums2, B, Vo, pl, s));
+                if (tcd) {
+                    I2V_TRY(conv_tc_stats(p + "ds", cur_s, tb, sums2, Tc, Hc, Wc, Cc, pl));
+                } else {
+                    I2V_PTR(wd, G(p + "ds.w", (size_t)27 * pl * Cc));
+                    I2V_TRY(conv(0, cur, wd, nullptr, nullptr, tb, B, Tc, Hc, Wc, Cc, pl, 3, 3, 3, st, ss, ss, 1, 1, 1, 1, 1, 1, ACT_NONE, 0, s, &sk));
+                    I2V_TRY(launch_channel_stats(tb, sums2, B, Vo, pl, s));
+                }
                 I2V_TRY(launch_norm_coeffs(sums2, coef2, B, pl, Vo, 16, 1e-5f, gdw, gdb, nullptr, s));
                 res = tb; c2 = coef2;
             } else {
                 I2V_REQUIRE(st == 1 && ss == 1 && Cc == pl, "encoder3d: block %s needs a downsample branch but none was registered", p.c_str());
             }
-            I2V_TRY(modulate(ta, coef, nullptr, res, c2, tc, B, To, Ho, Wo, pl, 1, 1, 1, ACT_RELU, s));
+            // h = relu(GN(o) + identity): fp32 (the next residual / SIMT input) and, when a tensor-core conv follows, its split
+            I2V_TRY(norm_act(ta, coef, res, c2, tc, next_tc ? cur_s : nullptr, To, Ho, Wo, pl));
+            cur_split = next_tc;
             float* old = cur; cur = tc; tc = old;
             Tc = To; Hc = Ho; Wc = Wo; Cc = pl;
         }
@@ -917,6 +1009,14 @@ i2v_encoder3d* i2v_encoder3d_create(const int channels[5], const int stride_s[4]
     return h;
 }
 int i2v_encoder3d_set_tensor(i2v_encoder3d* h, const char* n, const void* p, size_t b) { return h ? h->tt.set(n, p, b) : -1; }
+int i2v_encoder3d_set_scalar(i2v_encoder3d* h, const char* n, double v) {
+    I2V_REQUIRE(h && n, "encoder3d_set_scalar: null argument");
+    const std::string k(n);
+    if (k == "tc_min_ctas" && v >= 1 && v <= 65536) { h->tc_min_ctas = (int)v; return 0; }
+    I2V_REQUIRE(k == "tc_mode" && (v == 0 || v == 1 || v == 2), "encoder3d_set_scalar: unknown option '%s' = %g", n, v);
+    h->tc_mode = (int)v;
+    return 0;
+}
 size_t i2v_encoder3d_workspace_bytes(const i2v_encoder3d* h, int batch, int frames, int height, int width) {
     Arena ar(nullptr, 0, true);
     if (encoder3d_run(h, nullptr, nullptr, batch, frames, height, width, ar, nullptr, true)) return 0;

@@ -9,6 +9,8 @@
 //                   normalization_layer.py:22-23 does).
 #include <cuda_fp16.h>
 
+#include <cmath>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "prof.h"
@@ -246,13 +248,115 @@ __global__ void __launch_bounds__(256) modulate8_split_kernel(const ModArgs a, i
     }
 }
 
+// SPADE passes of the decoder (coefficients + gamma|beta maps + LeakyReLU(0.2), the only form decoder_run issues for the
+// T-walking kernel): the same arithmetic as modulate8_split_kernel, restructured around the memory system.  ncu on the generic
+// kernel (profiles/r02_ncu_modulate_summary.txt): 128 registers, 16 warps per SM, and -- because the activation switch and the
+// runtime `ut` loop keep branches between a plane's loads and its stores -- only ONE plane (32 bytes) in flight per thread:
+// long-scoreboard-bound at 3.3 TB/s.  Here the activation and the temporal factor are compile-time, a thread owns one
+// (h, w, 8-channel) position (fine-grained grid: no 8.2-wave tail), and a rotating window keeps TCH source planes (128 bytes)
+// in flight per thread: plane ts + TCH is requested the moment plane ts has been written out.  Instruction diet (the generic
+// kernel spends ~210 instructions per plane and thread, enough to be issue-bound at 5 TB/s): power-of-two split scale folded
+// into gamma / beta, lrelu as max(v, 0.2 v), NaN-propagating two-instruction clamp, packed conversions, pointer increments.
+// NaN-propagating clamp to the fp16 range (same values as sat_f16: NaN stays NaN) in two FMNMX instead of compare + select + FMNMX
+__device__ __forceinline__ float sat_f16_fast(float f) {
+    float r;
+    asm("{\n\t.reg .f32 t;\n\tmax.NaN.f32 t, %1, 0fC77FE000;\n\tmin.NaN.f32 %0, t, 0f477FE000;\n\t}" : "=f"(r) : "f"(f));
+    return r;
+}
+// split of a PAIR of (already scaled) values: one packed conversion for the two high words
+__device__ __forceinline__ void split_f16x2(float f0, float f1, __half2& hi, __half2& lo) {
+    f0 = sat_f16_fast(f0); f1 = sat_f16_fast(f1);
+    hi = __floats2half2_rn(f0, f1);
+    lo = __floats2half2_rn(f0 - __low2float(hi), f1 - __high2float(hi));
+}
+
+template <bool SECOND, int UT>
+__global__ void __launch_bounds__(256, 2) modulate8_spade_kernel(const ModArgs a, int c8_shift, int w_shift) {
+    pdl_launch_dependents();
+    pdl_wait();
+    constexpr int TCH = 4;                   // host guarantees Ts % TCH == 0 and a power-of-two split scale
+    const int C8 = a.C >> 3;
+    const int b = blockIdx.y;
+    const int Ts = a.T / UT, Hs = a.H / a.uh, Ws = a.W / a.uw;
+    const int per_plane = a.H * a.W * C8;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= per_plane) return;
+    const int c8 = i & (C8 - 1);
+    const int hw = i >> c8_shift;
+    const int w = hw & (a.W - 1), h = hw >> w_shift;
+    const long long src_plane = (long long)Hs * Ws * (C8 * 2);      // float4 per source plane
+    const float4* xp = reinterpret_cast<const float4*>(a.x) + (long long)b * Ts * src_plane + ((h / a.uh) * Ws + (w / a.uw)) * (C8 * 2) + c8 * 2;
+    float4 xv[TCH][2];
+#pragma unroll
+    for (int u = 0; u < TCH; ++u) { xv[u][0] = __ldg(xp); xv[u][1] = __ldg(xp + 1); xp += src_plane; }
+    const float s = a.split_scale;
+    // v * s = fma(fma(ca, x, cb), ga * s, gbv * s): exact for a power-of-two s, so the scale costs nothing per plane
+    float ca[8], cb[8], ga[8], gbv[8];
+    {
+        const float4* c = reinterpret_cast<const float4*>(a.coef + (long long)b * a.C * 2) + c8 * 4;
+        const float4 c0 = __ldg(c), c1 = __ldg(c + 1), c2 = __ldg(c + 2), c3 = __ldg(c + 3);
+        ca[0] = c0.x; cb[0] = c0.y; ca[1] = c0.z; cb[1] = c0.w; ca[2] = c1.x; cb[2] = c1.y; ca[3] = c1.z; cb[3] = c1.w;
+        ca[4] = c2.x; cb[4] = c2.y; ca[5] = c2.z; cb[5] = c2.w; ca[6] = c3.x; cb[6] = c3.y; ca[7] = c3.z; cb[7] = c3.w;
+        const float4* g = reinterpret_cast<const float4*>(a.gb + (long long)b * a.H * a.W * 2 * a.C) + (long long)hw * (C8 * 4) + c8 * 2;
+        const float4 g0 = __ldg(g), g1 = __ldg(g + 1), b0 = __ldg(g + C8 * 2), b1 = __ldg(g + C8 * 2 + 1);
+        ga[0] = 1.f + g0.x; ga[1] = 1.f + g0.y; ga[2] = 1.f + g0.z; ga[3] = 1.f + g0.w;
+        ga[4] = 1.f + g1.x; ga[5] = 1.f + g1.y; ga[6] = 1.f + g1.z; ga[7] = 1.f + g1.w;
+        gbv[0] = b0.x; gbv[1] = b0.y; gbv[2] = b0.z; gbv[3] = b0.w; gbv[4] = b1.x; gbv[5] = b1.y; gbv[6] = b1.z; gbv[7] = b1.w;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { ga[j] *= s; gbv[j] *= s; }
+    }
+    float c2a[8], c2b[8];
+    if (SECOND) {
+        const float4* c = reinterpret_cast<const float4*>(a.coef_b + (long long)b * a.C * 2) + c8 * 4;
+        const float4 c0 = __ldg(c), c1 = __ldg(c + 1), c2 = __ldg(c + 2), c3 = __ldg(c + 3);
+        c2a[0] = c0.x; c2b[0] = c0.y; c2a[1] = c0.z; c2b[1] = c0.w; c2a[2] = c1.x; c2b[2] = c1.y; c2a[3] = c1.z; c2b[3] = c1.w;
+        c2a[4] = c2.x; c2b[4] = c2.y; c2a[5] = c2.z; c2b[5] = c2.w; c2a[6] = c3.x; c2b[6] = c3.y; c2a[7] = c3.z; c2b[7] = c3.w;
+    }
+    uint4* oh = reinterpret_cast<uint4*>(a.out_hi) + (long long)b * a.T * per_plane + i;
+    uint4* ol = reinterpret_cast<uint4*>(a.out_lo) + (long long)b * a.T * per_plane + i;
+    uint4* o2h = SECOND ? reinterpret_cast<uint4*>(a.outb_hi) + (long long)b * a.T * per_plane + i : nullptr;
+    uint4* o2l = SECOND ? reinterpret_cast<uint4*>(a.outb_lo) + (long long)b * a.T * per_plane + i : nullptr;
+    for (int ts0 = 0; ts0 < Ts; ts0 += TCH) {
+        const bool more = ts0 + TCH < Ts;
+#pragma unroll
+        for (int u = 0; u < TCH; ++u) {
+            const float v[8] = {xv[u][0].x, xv[u][0].y, xv[u][0].z, xv[u][0].w, xv[u][1].x, xv[u][1].y, xv[u][1].z, xv[u][1].w};
+            __half2 hh[4], ll[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                // the generic kernels' operation order -- fma(A, x, B), fma(v, 1 + gamma, beta), lrelu, scale, split -- with the
+                // (power-of-two) scale folded into gamma / beta: bit-identical results
+                float f0 = fmaf(ca[2 * j], v[2 * j], cb[2 * j]), f1 = fmaf(ca[2 * j + 1], v[2 * j + 1], cb[2 * j + 1]);
+                f0 = fmaf(f0, ga[2 * j], gbv[2 * j]); f1 = fmaf(f1, ga[2 * j + 1], gbv[2 * j + 1]);
+                f0 = fmaxf(f0, 0.2f * f0); f1 = fmaxf(f1, 0.2f * f1);
+                split_f16x2(f0, f1, hh[j], ll[j]);
+            }
+#pragma unroll
+            for (int r = 0; r < UT; ++r) {
+                *oh = *reinterpret_cast<const uint4*>(hh); oh += per_plane;
+                *ol = *reinterpret_cast<const uint4*>(ll); ol += per_plane;
+            }
+            if (SECOND) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    split_f16x2(fmaf(c2a[2 * j], v[2 * j], c2b[2 * j]) * s, fmaf(c2a[2 * j + 1], v[2 * j + 1], c2b[2 * j + 1]) * s, hh[j], ll[j]);
+                *o2h = *reinterpret_cast<const uint4*>(hh); o2h += per_plane;
+                *o2l = *reinterpret_cast<const uint4*>(ll); o2l += per_plane;
+            }
+            if (more) { xv[u][0] = __ldg(xp); xv[u][1] = __ldg(xp + 1); xp += src_plane; }   // plane ts + TCH into the freed registers
+        }
+    }
+}
+
 // Map-free variant (AdaIN / GroupNorm-affine / plain activation passes): one (b, t) plane per blockIdx.y -- a pure
 // stream, which DRAM serves better than 16 interleaved plane streams (measured: 5.3 vs 4.5 TB/s).  A thread's channel group
 // is fixed (the grid stride is a multiple of C/8), so its 8 coefficient pairs are loaded ONCE instead of once per element
 // (they cost 4 of the 6 load instructions of an iteration: 3.7 TB/s at C = 128 against 6.0 TB/s without coefficients), two
 // elements are in flight per thread.  (Streaming stores, st.global.cs, for the fp16 pair were measured slower: 1.25 -> 1.32 /
 // 1.51 -> 1.75 ms on the two big SPADE passes, profiles/r02_bench_ab.txt.)
-template <bool COEF>
+// ACT >= 0: compile-time activation (none / ReLU / LeakyReLU) and a power-of-two split scale, folded into the coefficients
+// (exact), with the SPADE kernel's instruction diet; ACT = -1: the generic form (run-time activation, any scale).  Same bits.
+template <bool COEF, int ACT>
 __global__ void __launch_bounds__(256, 4) modulate8_split_plane_kernel(const ModArgs a, int c8_shift, int w_shift) {
     pdl_launch_dependents();
     pdl_wait();
@@ -276,6 +380,10 @@ __global__ void __launch_bounds__(256, 4) modulate8_split_plane_kernel(const Mod
         const float4 c0 = __ldg(c), c1 = __ldg(c + 1), c2 = __ldg(c + 2), c3 = __ldg(c + 3);
         ca[0] = c0.x; cb[0] = c0.y; ca[1] = c0.z; cb[1] = c0.w; ca[2] = c1.x; cb[2] = c1.y; ca[3] = c1.z; cb[3] = c1.w;
         ca[4] = c2.x; cb[4] = c2.y; ca[5] = c2.z; cb[5] = c2.w; ca[6] = c3.x; cb[6] = c3.y; ca[7] = c3.z; cb[7] = c3.w;
+        if (ACT >= 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { ca[j] *= s; cb[j] *= s; }
+        }
     }
     auto src_of = [&](int i) {
         const int hw = i >> c8_shift;
@@ -284,18 +392,29 @@ __global__ void __launch_bounds__(256, 4) modulate8_split_plane_kernel(const Mod
     };
     auto finish = [&](int i, const float4& x0, const float4& x1) {
         float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-        if (has_coef) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = fmaf(ca[j], v[j], cb[j]);
-        }
         __half2 hh[4], ll[4];
+        if (ACT >= 0) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float f0 = apply_act(v[2 * j], a.act) * s, f1 = apply_act(v[2 * j + 1], a.act) * s;
-            __half h0, h1, l0, l1;
-            split_f16(f0, h0, l0); split_f16(f1, h1, l1);
-            hh[j] = __halves2half2(h0, h1);
-            ll[j] = __halves2half2(l0, l1);
+            for (int j = 0; j < 4; ++j) {
+                float f0 = has_coef ? fmaf(ca[2 * j], v[2 * j], cb[2 * j]) : v[2 * j] * s;
+                float f1 = has_coef ? fmaf(ca[2 * j + 1], v[2 * j + 1], cb[2 * j + 1]) : v[2 * j + 1] * s;
+                if (ACT == ACT_RELU) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
+                if (ACT == ACT_LRELU02) { f0 = fmaxf(f0, 0.2f * f0); f1 = fmaxf(f1, 0.2f * f1); }
+                split_f16x2(f0, f1, hh[j], ll[j]);
+            }
+        } else {
+            if (has_coef) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = fmaf(ca[j], v[j], cb[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float f0 = apply_act(v[2 * j], a.act) * s, f1 = apply_act(v[2 * j + 1], a.act) * s;
+                __half h0, h1, l0, l1;
+                split_f16(f0, h0, l0); split_f16(f1, h1, l1);
+                hh[j] = __halves2half2(h0, h1);
+                ll[j] = __halves2half2(l0, l1);
+            }
         }
         oh[i] = *reinterpret_cast<const uint4*>(hh);
         ol[i] = *reinterpret_cast<const uint4*>(ll);
@@ -370,7 +489,17 @@ int launch_modulate(const ModArgs& a, cudaStream_t stream) {
         if (bx > cap) bx = cap < 1 ? 1 : cap;
         const double tot = (double)a.B * a.T * per_plane * 8;
         ProfScope ps(PROF_MODULATE, 4.0 * tot, 4.0 * (tot + tot / ((double)a.ut * a.uh * a.uw)) + (a.gb ? 8.0 * tot / a.T : 0.0), stream);
-        if (a.gb != nullptr || a.outb_hi != nullptr) {
+        int sexp = 0;
+        const bool scale_pow2 = a.split_scale > 0.f && std::frexp(a.split_scale, &sexp) == 0.5f;
+        const bool spade_form = a.gb != nullptr && a.coef != nullptr && a.act == ACT_LRELU02 && (a.ut == 1 || a.ut == 2) &&
+                                (a.T / a.ut) % 4 == 0 && scale_pow2 && (a.outb_hi == nullptr || a.ut == 1) && tune().mod_spade != 0;
+        if (spade_form) {
+            const dim3 grid((per_plane + 255) / 256, a.B);
+            const int cs = ilog2(a.C / 8), wsft = ilog2(a.W);
+            if (a.outb_hi != nullptr) I2V_CHECK_CUDA(launch_k(modulate8_spade_kernel<true, 1>, grid, dim3(256), 0, stream, a, cs, wsft));
+            else if (a.ut == 1) I2V_CHECK_CUDA(launch_k(modulate8_spade_kernel<false, 1>, grid, dim3(256), 0, stream, a, cs, wsft));
+            else I2V_CHECK_CUDA(launch_k(modulate8_spade_kernel<false, 2>, grid, dim3(256), 0, stream, a, cs, wsft));
+        } else if (a.gb != nullptr || a.outb_hi != nullptr) {
             I2V_CHECK_CUDA(launch_k(modulate8_split_kernel, dim3(bx, a.B), dim3(256), 0, stream, a, ilog2(a.C / 8), ilog2(a.W)));
         } else {
             const int planes = a.B * a.T;
@@ -378,10 +507,22 @@ int launch_modulate(const ModArgs& a, cudaStream_t stream) {
             int bp = (per_plane + 255) / 256;
             const int capp = (kNumSMs * 16 + planes - 1) / planes;
             if (bp > capp) bp = capp < 1 ? 1 : capp;
-            if (a.coef != nullptr)
-                I2V_CHECK_CUDA(launch_k(modulate8_split_plane_kernel<true>, dim3(bp, planes), dim3(256), 0, stream, a, ilog2(a.C / 8), ilog2(a.W)));
-            else
-                I2V_CHECK_CUDA(launch_k(modulate8_split_plane_kernel<false>, dim3(bp, planes), dim3(256), 0, stream, a, ilog2(a.C / 8), ilog2(a.W)));
+            const dim3 grid(bp, planes);
+            const int cs = ilog2(a.C / 8), wsft = ilog2(a.W);
+            const bool ct = scale_pow2 && tune().mod_spade != 0;      // compile-time activation + folded scale
+#define I2V_PLANE(COEF_, ACT_) I2V_CHECK_CUDA(launch_k(modulate8_split_plane_kernel<COEF_, ACT_>, grid, dim3(256), 0, stream, a, cs, wsft))
+            if (a.coef != nullptr) {
+                if (ct && a.act == ACT_LRELU02) I2V_PLANE(true, ACT_LRELU02);
+                else if (ct && a.act == ACT_RELU) I2V_PLANE(true, ACT_RELU);
+                else if (ct && a.act == ACT_NONE) I2V_PLANE(true, ACT_NONE);
+                else I2V_PLANE(true, -1);
+            } else {
+                if (ct && a.act == ACT_LRELU02) I2V_PLANE(false, ACT_LRELU02);
+                else if (ct && a.act == ACT_RELU) I2V_PLANE(false, ACT_RELU);
+                else if (ct && a.act == ACT_NONE) I2V_PLANE(false, ACT_NONE);
+                else I2V_PLANE(false, -1);
+            }
+#undef I2V_PLANE
         }
         return 0;
     }

@@ -105,6 +105,7 @@ SIGNATURES = {
     "i2v_decoder_destroy": (None, [_P]),
     "i2v_encoder3d_create": (_P, [_P, _P, _P, _I]),
     "i2v_encoder3d_set_tensor": (_I, [_P, _c.c_char_p, _P, _SZ]),
+    "i2v_encoder3d_set_scalar": (_I, [_P, _c.c_char_p, _c.c_double]),
     "i2v_encoder3d_workspace_bytes": (_SZ, [_P, _I, _I, _I, _I]),
     "i2v_encoder3d_forward": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _SZ, _P]),
     "i2v_encoder3d_destroy": (None, [_P]),

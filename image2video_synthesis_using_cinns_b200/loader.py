@@ -261,18 +261,29 @@ def pack_embedder(sd, zc, norm, tensor_core=True):
 
 
 # ------------------------------------------------------------------------------------ 3-D encoder
-def pack_encoder3d(sd, n_stages=4, blocks=2):
+def pack_encoder3d(sd, n_stages=4, blocks=2, tensor_core=True):
+    """resnet3D.Encoder keys -> channels-last conv stacks [27, Cout, Cin].  Every 3x3x3 conv of the blocks also gets the split
+    fp16 weights of the tensor-core engine (``.wh/.wl/.ws``, csrc/conv_tc.cu); the kernel side uses them for the stride-1
+    convs whose GEMM fills the machine (csrc/api.cu, encoder3d_run) and the fp32 copy everywhere else."""
     t = {"conv1.w": _taps3(sd["conv1.weight"].float()), "norm1.w": sd["norm1.weight"].float(),
          "norm1.b": sd["norm1.bias"].float()}
+
+    def put_split(dst):
+        if tensor_core and t[dst + ".w"].shape[2] % 16 == 0:
+            t[dst + ".wh"], t[dst + ".wl"], t[dst + ".ws"] = split_fp16(t[dst + ".w"], ACT_SPLIT_SCALE)
+
     for l in range(n_stages):
         for b in range(blocks):
             p = f"layer.{l}.{b}."
             t[p + "conv1.w"] = _taps3(sd[p + "conv1.weight"].float())
             t[p + "conv2.w"] = _taps3(sd[p + "conv2.weight"].float())
+            put_split(p + "conv1")
+            put_split(p + "conv2")
             for nm in ("bn1", "bn2"):
                 t[p + nm + ".w"], t[p + nm + ".b"] = sd[p + nm + ".weight"].float(), sd[p + nm + ".bias"].float()
             if p + "downsample.0.weight" in sd:
                 t[p + "ds.w"] = _taps3(sd[p + "downsample.0.weight"].float())
+                put_split(p + "ds")
                 t[p + "ds.gn.w"] = sd[p + "downsample.1.weight"].float()
                 t[p + "ds.gn.b"] = sd[p + "downsample.1.bias"].float()
     # conv_mu / conv_var: (z, C, 4, 4) valid conv on the 4x4 map -> Linear over the (h, w, c) flattening

@@ -359,7 +359,7 @@ class Encoder(_Native):
 
     _destroy = "i2v_encoder3d_destroy"
 
-    def __init__(self, state_dict, dic, device="cuda"):
+    def __init__(self, state_dict, dic, device="cuda", tc_mode=1, tc_min_ctas=None):
         super().__init__(device)
         if dic["res_type_encoder"] != "resnet18" or dic["use_max_pool"]:
             raise ValueError("only the resnet18 / no-max-pool encoder of the reference configs is implemented")
@@ -370,7 +370,11 @@ class Encoder(_Native):
         self.h = self.L.i2v_encoder3d_create(ch, ss, st, self.z_dim)
         if not self.h:
             raise RuntimeError(self.L.i2v_last_error().decode())
-        self._register(self.L.i2v_encoder3d_set_tensor, loader.pack_encoder3d(state_dict))
+        self._register(self.L.i2v_encoder3d_set_tensor, loader.pack_encoder3d(state_dict, tensor_core=tc_mode != 0))
+        # tc_mode 0: fp32 SIMT convs only; 1: tensor-core engine for the stride-1 convs that fill the machine; 2: wherever supported
+        if tc_min_ctas is not None:
+            _lib.check(self.L.i2v_encoder3d_set_scalar(self.h, b"tc_min_ctas", float(tc_min_ctas)), "encoder3d_set_scalar(tc_min_ctas)")
+        _lib.check(self.L.i2v_encoder3d_set_scalar(self.h, b"tc_mode", float(tc_mode)), "encoder3d_set_scalar(tc_mode)")
 
     def mu_logvar(self, x):
         # the reference accepts (B,3,T,H,W) and transposes (B,T,3,H,W) itself (resnet3D.py:209-210)

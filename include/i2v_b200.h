@@ -109,6 +109,9 @@ void i2v_decoder_destroy(i2v_decoder* h);
 typedef struct i2v_encoder3d i2v_encoder3d;
 i2v_encoder3d* i2v_encoder3d_create(const int channels[5], const int stride_s[4], const int stride_t[4], int z_dim);
 int i2v_encoder3d_set_tensor(i2v_encoder3d* h, const char* name, const void* dev_ptr, size_t nbytes);
+/* "tc_mode": 0 fp32 SIMT convs only, 1 (default) tensor-core engine for the stride-1 3x3x3 convs (resnet3D.py:101-135) whose GEMM
+ * has >= "tc_min_ctas" (default 8) 128x128 tiles, 2 wherever the shape is supported; needs the "<conv>.wh/.wl/.ws" tensors */
+int i2v_encoder3d_set_scalar(i2v_encoder3d* h, const char* name, double value);
 size_t i2v_encoder3d_workspace_bytes(const i2v_encoder3d* h, int batch, int frames, int height, int width);
 /* seq: [B,T,3,H,W] fp32 (the query clip without its first frame, get_model.py:87)
  * -> mu_logvar [B, 2*z_dim] = (conv_mu | conv_var) outputs, resnet3D.py:202-203 */

@@ -163,23 +163,25 @@ def test_config5_iper128_transfer_sample_matches_oracle(ckpts):
     assert_parity("oracle:iper128_transfer:frames", gs.cpu(), ws_, ts)
 
 
-@pytest.mark.parametrize("dataset", ["bair", "landscape", "dtdb_fire", "iper128"])
-def test_encoder3d_full_size_matches_oracle(dataset):
+@pytest.mark.parametrize("dataset,tc_mode", [("bair", 1), ("landscape", 1), ("dtdb_fire", 1), ("iper128", 1),
+                                             ("bair", 0), ("iper128", 0), ("bair", 2), ("iper128", 2)])
+def test_encoder3d_full_size_matches_oracle(dataset, tc_mode):
     """the 3-D encoder at its FULL-size channels (resnet3D.py:138-219) against the oracle's mu,
-    for the 64x64 geometry and the three 128x128 ones (flat 1e-4)."""
+    for the 64x64 geometry and the three 128x128 ones (flat 1e-4).  tc_mode 1 = the default engine mix (stride-1 convs that fill
+    the machine on the tensor-core engine), 0 = fp32 SIMT engine only, 2 = tensor-core engine wherever the shape is supported."""
     from image2video_synthesis_using_cinns_b200 import modules, synthetic
     from image2video_synthesis_using_cinns_b200.config import DATASETS
     cfg = DATASETS[dataset]
     e = cfg["enc"]
     sd = synthetic.encoder3d_state_dict(G(50), e["channels"], e["stride_s"])
     dic = dict(res_type_encoder="resnet18", deterministic=False, use_max_pool=False, z_dim=64, **e)
-    enc = modules.Encoder(sd, dic)
+    enc = modules.Encoder(sd, dic, tc_mode=tc_mode)
     img = cfg["img_size"]
     clip = torch.rand(2, 15, 3, img, img, generator=G(51)) * 2 - 1          # the query minus its first frame (get_model.py:87)
     mu, logvar = enc.mu_logvar(clip.cuda().transpose(1, 2))
     want = ot.encoder3d_mu(sd, clip.transpose(1, 2), e["stride_s"], e["stride_t"])
     truth = ot.encoder3d_mu({k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}, clip.double().transpose(1, 2),
                             e["stride_s"], e["stride_t"])
-    e_ref, _, _ = assert_parity(f"oracle:encoder3d_full:{dataset}", mu.cpu(), want, truth)
+    e_ref, _, _ = assert_parity(f"oracle:encoder3d_full:{dataset}:tc{tc_mode}", mu.cpu(), want, truth)
     assert e_ref < 1e-4
     assert torch.isfinite(logvar).all()
