@@ -216,6 +216,7 @@ int i2v_set_option(const char* name, double value) {
     else if (k == "linear_bfly") t.linear_bfly = v != 0;
     else if (k == "flow_cluster") t.flow_cluster = v != 0;
     else if (k == "mod_spade") t.mod_spade = v != 0;
+    else if (k == "tc_t2_split") t.tc_t2_split = v != 0;
     else I2V_REQUIRE(false, "set_option: unknown option '%s'", name);
     return 0;
 }
@@ -705,7 +706,8 @@ static int decoder_run(const i2v_decoder* m, const float* img, const float* z, f
         while (cin % groups) --groups;
         I2V_TRY(launch_norm_coeffs(sums, coef, B, cin, vlow, groups, 1e-5f, nullptr, nullptr, nullptr, s));
         // conv_0 behind a x2 temporal upsample: keep a0 at T/2 and let the conv use its 2-tap phase form
-        const bool phase = tc && k.ut == 2 && m->tt.has(nm + ".conv_0.wph") && conv_tc_halo_eligible(Hc, Wc, 3);
+        // (planes >= 16x16: halo / CTA-pair kernel; smaller planes, i.e. g_0 at 8x8: per-tap kernel, one launch per phase)
+        const bool phase = tc && k.ut == 2 && T % 2 == 0 && m->tt.has(nm + ".conv_0.wph");
         const int Ta = phase ? T / 2 : T;                       // stored planes of a0
         const size_t n_a0 = (size_t)B * Ta * Hc * Wc * cin;
         // a block that keeps the resolution runs its learned shortcut inside conv_1 (side input through the centre tap)

@@ -61,6 +61,9 @@ struct ConvTcKArgs {
     int nmain;                             // ... of which the first nmain take hi*hi, the rest the small cross terms
     int res_ut, res_uh, res_uw, act, out_mode;
     int cc_lo, cc_hi;             // channel-chunk range [cc_lo, cc_hi) of this launch (K split across launches)
+    // 1: temporal phase form (see halo_tile): T is the OUTPUT frame count, the input holds T/2 planes, tiles walk the INPUT
+    // planes, blockIdx.z is the output phase p (frame 2j + p) and the weights are the 2 x 2 phase-combined temporal taps
+    int t_phase;
 };
 
 struct EpiArgs {
@@ -488,7 +491,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
         hi = extent - 1 - origin + k / 2; if (hi > k - 1) hi = k - 1;   // last d with origin + d - k/2 < extent
     };
     int dt_lo, dt_hi, dh_lo, dh_hi, dw_lo, dw_hi;
-    tap_range(a.kt, t0, a.bt, a.T, dt_lo, dt_hi);
+    // Phase form (g_0.conv_0: 8x8 planes behind a x2 temporal upsample): output frame 2j + p reads the source planes
+    // j - 1 + p + q, q = 0, 1, with the pre-summed weight slabs 2p + q; t0 counts SOURCE planes.  With one source plane
+    // (T = 2) a single temporal tap per phase survives the range check: a third of the plain form's MMAs.
+    const int ph_out = a.t_phase ? (int)blockIdx.z : 0;
+    const int t_shift = a.t_phase ? 1 - ph_out : a.kt / 2;        // source plane of temporal tap d: t0 + d - t_shift
+    if (a.t_phase) {
+        dt_lo = t_shift - t0 - a.bt + 1; if (dt_lo < 0) dt_lo = 0;
+        dt_hi = a.T / 2 - 1 - t0 + t_shift; if (dt_hi > 1) dt_hi = 1;
+    } else {
+        tap_range(a.kt, t0, a.bt, a.T, dt_lo, dt_hi);
+    }
     tap_range(a.kh, h0, a.bh, a.H, dh_lo, dh_hi);
     tap_range(a.kw, w0, a.bw, a.W, dw_lo, dw_hi);
     const int n_total = (dt_hi - dt_lo + 1) * (dh_hi - dh_lo + 1) * (dw_hi - dw_lo + 1) * cchunks;   // >= 1: the centre tap
@@ -507,8 +520,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
             for (int dh = dh_lo; dh <= dh_hi; ++dh)
             for (int dw = dw_lo; dw <= dw_hi; ++dw)
             for (int cc = a.cc_lo; cc < a.cc_hi; ++cc) {
-                const int tap = (dt * a.kh + dh) * a.kw + dw, c0 = cc * a.kc;
-                const int cw = w0 + dw - a.kw / 2, ch = h0 + dh - a.kh / 2, ct = t0 + dt - a.kt / 2;
+                const int tap = ((2 * ph_out + dt) * a.kh + dh) * a.kw + dw, c0 = cc * a.kc;     // ph_out = 0 outside the phase form
+                const int cw = w0 + dw - a.kw / 2, ch = h0 + dh - a.kh / 2, ct = t0 + dt - t_shift;
                 ptx::mbar_wait(empty + s, ph ^ 1u);
                 uint8_t* st = smem + (size_t)s * stage_bytes;
                 if (ptx::elect_one()) {
@@ -586,8 +599,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
         const int hi = r % a.bh; r /= a.bh;
         const int ti = r % a.bt;
         const int bi = r / a.bt;
-        // box dims grow only once the lower ones span the tensor (launch_conv_tc), so the 128 rows are consecutive voxels
-        EpiArgs e{a.bias, a.res, a.y, a.T, a.H, a.W, a.Cout, a.res_ut, a.res_uh, a.res_uw, a.act, a.out_mode, 1};
+        // box dims grow only once the lower ones span the tensor (launch_conv_tc), so the 128 rows are consecutive voxels;
+        // tiles of single planes (phase form, T = 2 tiling) keep every 32-row warp slice inside one plane when bw * bh % 32 == 0
+        const int t_out = a.t_phase ? 2 * (t0 + ti) + ph_out : t0 + ti;
+        const int contig = (!a.t_phase && (a.bt == a.T || a.bb == 1)) || (a.bw * a.bh) % 32 == 0 ? 1 : 0;
+        EpiArgs e{a.bias, a.res, a.y, a.T, a.H, a.W, a.Cout, a.res_ut, a.res_uh, a.res_uw, a.act, a.out_mode, contig};
         const int nacc_used = a.nacc;       // host guarantees every accumulator is written by every CTA
         // column split between the two warps of a quarter (multiples of 16)
         const int nh0 = ((a.n_tile / 16 + 1) / 2) * 16;
@@ -597,9 +613,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
         if (a.out_mode == 0 && b0 + a.bb <= a.B && 8 * stile_bytes <= (size_t)a.stages * stage_bytes) {
             float* stile = reinterpret_cast<float*>(smem + (size_t)(warp - 2) * stile_bytes);
             const int Tr = a.T / a.res_ut, Hr = a.H / a.res_uh, Wr = a.W / a.res_uw;
-            const long long vox_lane = (((long long)(b0 + bi) * a.T + t0 + ti) * a.H + h0 + hi) * a.W + w0 + wi;
+            const long long vox_lane = (((long long)(b0 + bi) * a.T + t_out) * a.H + h0 + hi) * a.W + w0 + wi;
             const long long roff_lane =
-                ((((long long)(b0 + bi) * Tr + (t0 + ti) / a.res_ut) * Hr + (h0 + hi) / a.res_uh) * Wr + (w0 + wi) / a.res_uw) * a.Cout;
+                ((((long long)(b0 + bi) * Tr + t_out / a.res_ut) * Hr + (h0 + hi) / a.res_uh) * Wr + (w0 + wi) / a.res_uw) * a.Cout;
             if (ncols > 0) {
                 float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};
                 const bool want_stats = a.stats != nullptr;     // host guarantees bb == 1 (one sample per tile) and ncols <= 128
@@ -609,7 +625,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mAh, const __grid_constant__ 
             }
         } else if (half == 0) {
             epilogue_row(e, tmem_base + ((uint32_t)(q * 32) << 16), a.n_tile, nacc_used, a.n_tile, n0, __ldg(a.scale_ptr), b0 + bi,
-                         t0 + ti, h0 + hi, w0 + wi, b0 + bi < a.B);
+                         t_out, h0 + hi, w0 + wi, b0 + bi < a.B);
         }
     }
     ptx::tc_fence_before();
@@ -1885,20 +1901,27 @@ int launch_conv_tc(const ConvTcArgs& h, cudaStream_t stream) {
         if (rc <= 0) return rc;     // launched (0) or failed (<0); 1 = shape not eligible -> v1 below
         I2V_REQUIRE(h.variant != 2, "conv_tc: shape not eligible for the halo kernel");
     }
-    I2V_REQUIRE(!h.t_phase, "conv_tc: t_phase is only implemented by the halo kernel (ask conv_tc_halo_eligible first)");
+    I2V_REQUIRE(!h.t_phase || (h.kt == 3 && h.T % 2 == 0), "conv_tc: the phase form needs kt = 3 and an even output frame count");
     I2V_REQUIRE(h.Cin2 == 0, "conv_tc: a side input is only implemented by the halo kernel (ask conv_tc_halo_eligible first)");
     ConvTcKArgs a;
     a.bias = h.bias; a.res = h.res; a.scale_ptr = h.scale_ptr; a.y = h.y; a.stats = h.stats;
     a.B = h.B; a.T = h.T; a.H = h.H; a.W = h.W; a.Cin = h.Cin; a.Cout = h.Cout;
     a.kt = h.kt; a.kh = h.kh; a.kw = h.kw;
     a.kc = h.Cin % 64 == 0 ? 64 : (h.Cin % 32 == 0 ? 32 : 16);
+    a.t_phase = h.t_phase ? 1 : 0;
+    const int Tin = h.t_phase ? h.T / 2 : h.T;       // stored input planes (tiles walk these)
     // box: 128 rows = bw x bh x bt x bb voxels
     int rem = TILE_M;
     a.bw = h.W < rem ? h.W : rem; rem /= a.bw;
     a.bh = h.H < rem ? h.H : rem; rem /= a.bh;
-    a.bt = h.T < rem ? h.T : rem; rem /= a.bt;
+    a.bt = Tin < rem ? Tin : rem;
+    // a two-frame clip under a temporal 3-tap kernel (g_0.conv_1: 2 x 8 x 8): a tile that holds BOTH frames needs all three
+    // temporal taps, two of them half padding; tiles of one frame (and two samples) skip the tap that falls outside -- 2/3 of
+    // the MMAs and operand loads.  The fused statistics (one sample per tile) give way to the separate pass: 8x8 planes.
+    if (!h.t_phase && h.kt == 3 && h.T == 2 && a.bt == 2 && (a.bw * a.bh) % 32 == 0 && tune().tc_t2_split) a.bt = 1;
+    rem /= a.bt;
     a.bb = rem;
-    a.tiles_w = h.W / a.bw; a.tiles_h = h.H / a.bh; a.tiles_t = h.T / a.bt;
+    a.tiles_w = h.W / a.bw; a.tiles_h = h.H / a.bh; a.tiles_t = Tin / a.bt;
     const int tiles_b = (h.B + a.bb - 1) / a.bb;
     I2V_REQUIRE(h.stats == nullptr || (a.bb == 1 && h.out_mode == 0),
                 "conv_tc: fused statistics need one sample per tile (ask conv_tc_fuses_stats first)");
@@ -1917,7 +1940,10 @@ int launch_conv_tc(const ConvTcArgs& h, cudaStream_t stream) {
         if (nmain < 1) nmain = 1;
         // K split across launches, same reasoning as the halo kernel (main chains of <= kMaxChain truncating MMAs)
         if (h.terms > 1) {
-            const long long chain = (long long)h.kt * h.kh * h.kw * cch1 * (a.kc / 16) / nmain;
+            // temporal taps that can be live in one tile: 2 in the phase form (1 when there is a single source plane), 2 for
+            // the one-frame tiles of a two-frame clip, kt otherwise
+            const int kt_live = h.t_phase ? (Tin == 1 ? 1 : 2) : (h.kt == 3 && h.T == 2 && a.bt == 1 ? 2 : h.kt);
+            const long long chain = (long long)kt_live * h.kh * h.kw * cch1 * (a.kc / 16) / nmain;
             parts1 = (int)((chain + kMaxChain - 1) / kMaxChain);
             if (parts1 > cch1) parts1 = cch1;
             if (parts1 < 1) parts1 = 1;
@@ -1950,15 +1976,15 @@ int launch_conv_tc(const ConvTcArgs& h, cudaStream_t stream) {
 
     CUtensorMap mAh, mAl, mBh, mBl;
     {
-        const cuuint64_t dims[5] = {(cuuint64_t)h.Cin, (cuuint64_t)h.W, (cuuint64_t)h.H, (cuuint64_t)h.T, (cuuint64_t)h.B};
+        const cuuint64_t dims[5] = {(cuuint64_t)h.Cin, (cuuint64_t)h.W, (cuuint64_t)h.H, (cuuint64_t)Tin, (cuuint64_t)h.B};
         const cuuint64_t st[4] = {(cuuint64_t)h.Cin * 2, (cuuint64_t)h.W * h.Cin * 2, (cuuint64_t)h.H * h.W * h.Cin * 2,
-                                  (cuuint64_t)h.T * h.H * h.W * h.Cin * 2};
+                                  (cuuint64_t)Tin * h.H * h.W * h.Cin * 2};
         const cuuint32_t box[5] = {(cuuint32_t)a.kc, (cuuint32_t)a.bw, (cuuint32_t)a.bh, (cuuint32_t)a.bt, (cuuint32_t)a.bb};
         if (int rc = encode_map(&mAh, h.x_hi, 5, dims, st, box, rb)) return rc;
         if (int rc = encode_map(&mAl, h.terms > 1 ? h.x_lo : h.x_hi, 5, dims, st, box, rb)) return rc;
     }
     {
-        const int taps = h.kt * h.kh * h.kw;
+        const int taps = (h.t_phase ? 4 : h.kt) * h.kh * h.kw;
         const cuuint64_t dims[3] = {(cuuint64_t)h.Cin, (cuuint64_t)h.cout_pad, (cuuint64_t)taps};
         const cuuint64_t st[2] = {(cuuint64_t)h.Cin * 2, (cuuint64_t)h.cout_pad * h.Cin * 2};
         const cuuint32_t box[3] = {(cuuint32_t)a.kc, (cuuint32_t)a.n_tile, 1};
@@ -1971,7 +1997,8 @@ int launch_conv_tc(const ConvTcArgs& h, cudaStream_t stream) {
     const long long M = (long long)h.B * h.T * h.H * h.W;
     const double K_ = (double)h.kt * h.kh * h.kw * h.Cin;
     ProfScope ps(PROF_CONV_TC1, 2.0 * (double)M * h.Cout * K_, 4.0 * ((double)M * h.Cin + (double)M * h.Cout + K_ * h.Cout), stream);
-    dim3 grid((unsigned)(a.tiles_w * a.tiles_h * a.tiles_t * tiles_b), (unsigned)((h.cout_pad + a.n_tile - 1) / a.n_tile));
+    dim3 grid((unsigned)(a.tiles_w * a.tiles_h * a.tiles_t * tiles_b), (unsigned)((h.cout_pad + a.n_tile - 1) / a.n_tile),
+              h.t_phase ? 2u : 1u);
     const int cper1 = (cch1 + parts1 - 1) / parts1;
     for (int p = 0; p < parts1; ++p) {
         a.cc_lo = p * cper1;

@@ -18,6 +18,7 @@ struct TuneOptions {
     int tc_pair_stages = 0;  // CTA-pair kernel: cap on the ring depth (0 = as many as fit, up to 8)
     int linear_bfly = 1;     // linear kernel: 9-shuffle transpose-reduce (0: 8 x warp_sum)
     int flow_cluster = 1;    // flow: cluster-resident kernel where eligible (0: cooperative grid-barrier kernel)
+    int tc_t2_split = 1;     // per-tap conv kernel: two-frame clips under a temporal 3-tap kernel run as one-frame tiles (skip the padded tap)
     int mod_spade = 1;       // SPADE modulate passes: pipelined fine-grained kernel (0: generic T-walking kernel)
 };
 TuneOptions& tune();

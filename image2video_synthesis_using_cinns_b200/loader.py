@@ -194,11 +194,11 @@ def pack_decoder(sd, nf, engine=0, upsample_t=(2, 1), upsample_s=(2, 2)):
         for name in DEC_BLOCKS:
             convs = ["conv_0", "conv_1"] + (["conv_s"] if f"{name}.conv_s.w" in t else [])
             # conv_0 of the blocks that run on 16x16+ planes behind a x2 temporal upsample: phase-combined weights
-            ut = {"g_1": 2, "g_2": 2, "g_3": upsample_t[0], "g_4": upsample_t[1]}.get(name, 0)
+            ut = {"g_0": 2, "g_1": 2, "g_2": 2, "g_3": upsample_t[0], "g_4": upsample_t[1]}.get(name, 0)
             if ut == 2:
                 ph, pl, ps = split_fp16(phase_weights(t[f"{name}.conv_0.w"]), ACT_SPLIT_SCALE)   # float64 sums -> split
                 tc[f"{name}.conv_0.wph"], tc[f"{name}.conv_0.wpl"], tc[f"{name}.conv_0.wps"] = ph, pl, ps
-            us = {"g_1": 2, "g_2": 2, "g_3": upsample_s[0], "g_4": upsample_s[1]}.get(name, 0)
+            us = {"g_0": 2, "g_1": 2, "g_2": 2, "g_3": upsample_s[0], "g_4": upsample_s[1]}.get(name, 0)
             if "conv_s" in convs and ut == 1 and us == 1:
                 w1, wsc = t[f"{name}.conv_1.w"], t[f"{name}.conv_s.w"]                # [27,Cout,Cmid], [1,Cout,Cin]
                 wmax = max(float(w1.abs().max()), float(wsc.abs().max()))

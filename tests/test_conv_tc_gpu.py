@@ -16,7 +16,8 @@ CASES = [
     ("w16_n256", (1, 64, 4, 16, 16), 256, (3, 3, 3)),         # box 16x8, N=256
     ("n512_two_ntiles", (1, 64, 1, 8, 8), 512, (3, 3, 3)),    # 2 N tiles, box 8x8x1x2 (bb=2 > B)
     ("head_4x4_batchbox", (3, 64, 1, 4, 4), 64, (3, 3, 3)),   # box 4x4x1x8 over the batch dim
-    ("g0_t2", (2, 64, 2, 8, 8), 64, (3, 3, 3)),               # box 8x8x2
+    ("g0_t2", (2, 64, 2, 8, 8), 64, (3, 3, 3)),               # two-frame clip: one-frame tiles of two samples (box 8x8x1x2)
+    ("g0_t2_b3", (3, 64, 2, 8, 8), 128, (3, 3, 3)),           # ... with a half-empty last tile
     ("kc32", (1, 32, 2, 16, 16), 32, (3, 3, 3)),              # SWIZZLE_64B rows
     ("kc16", (1, 16, 2, 16, 16), 16, (3, 3, 3)),              # SWIZZLE_32B rows
     ("conv_s_1x1x1", (2, 128, 2, 8, 8), 64, (1, 1, 1)),
@@ -200,6 +201,12 @@ PHASE_CASES = [
     ("pair_g3_conv0", (1, 128, 4, 16, 32), 64, 4),      # CTA-pair kernel
     ("pair_n128", (2, 64, 2, 16, 16), 128, 4),
     ("pair_t_half_1", (2, 64, 1, 8, 64), 64, 4),
+    # per-tap kernel (planes below 16x16, i.e. g_0.conv_0 at 2 x 8 x 8: one launch dimension per output phase)
+    ("pertap_g0_like", (2, 64, 1, 8, 8), 128, 0),       # one source plane: a single temporal tap per phase survives
+    ("pertap_g0_b3", (3, 64, 1, 8, 8), 64, 0),          # tiles of two samples, the last one half empty
+    ("pertap_tsrc2", (2, 32, 2, 8, 8), 32, 1),          # two source planes in one tile: both taps live, output frames interleave
+    ("pertap_4x4", (2, 32, 4, 4, 4), 32, 1),            # 16-voxel planes: warp slices straddle output frames (generic write-out)
+    ("pertap_forced_16x16", (1, 64, 2, 16, 16), 64, 1), # per-tap kernel forced on a halo-eligible shape
 ]
 
 
@@ -218,6 +225,25 @@ def test_conv_tc_temporal_phase_form(name, xs, cout, variant):
     report("conv_tc_phase:" + name, split3=e, fp16_single=e1)
     assert got.shape == want.shape
     assert e < 1e-5 and e1 < 1e-3
+
+
+def test_conv_tc_two_frame_tiling_switch():
+    """tc_t2_split: a two-frame clip runs as one-frame tiles that skip the padded temporal tap; both tilings give the conv."""
+    from image2video_synthesis_using_cinns_b200 import lib
+    g = G(77)
+    x = torch.randn(4, 64, 2, 8, 8, generator=g)
+    w = torch.randn(64, 64, 3, 3, 3, generator=g) / (27 * 64) ** 0.5
+    b = torch.randn(64, generator=g)
+    want = F.conv3d(x.double(), w.double(), b.double(), 1, 1)
+    errs = {}
+    try:
+        for sw in (0, 1):
+            lib.set_option("tc_t2_split", sw)
+            errs[sw] = rel_inf(ou.from_cl(ou.conv_tc(ou.to_cl(x), ou.taps(w), b.cuda(), None, (3, 3, 3))), want)
+    finally:
+        lib.set_option("tc_t2_split", 1)
+    report("conv_tc:t2_split", whole_clip_tiles=errs[0], one_frame_tiles=errs[1])
+    assert errs[0] < 1e-5 and errs[1] < 1e-5
 
 
 def test_split_saturates_instead_of_overflowing():
