@@ -216,6 +216,7 @@ int i2v_set_option(const char* name, double value) {
     else if (k == "linear_bfly") t.linear_bfly = v != 0;
     else if (k == "flow_cluster") t.flow_cluster = v != 0;
     else if (k == "mod_spade") t.mod_spade = v != 0;
+    else if (k == "linear_k64") t.linear_k64 = v != 0;
     else if (k == "tc_t2_split") t.tc_t2_split = v != 0;
     else I2V_REQUIRE(false, "set_option: unknown option '%s'", name);
     return 0;
@@ -695,9 +696,7 @@ static int decoder_run(const i2v_decoder* m, const float* img, const float* z, f
             ca.y_hi = reinterpret_cast<__half*>(sh); ca.y_lo = ca.y_hi + nsh; ca.split_scale = (float)it->second;
             // dedicated K = 27 kernel (same bits as the SIMT engine); scalar "opt.spade_simt" keeps the implicit-GEMM path (A/B switch)
             const bool spade_simt = m->scalars.count("opt.spade_simt") && m->scalars.at("opt.spade_simt") != 0;
-            const int hw = Hc * Wc, tv = hw < 64 ? hw : 64;
-            const bool tiles = hw % tv == 0 && (Wc >= tv ? Wc % tv == 0 : tv % Wc == 0);
-            if (!spade_simt && tiles) I2V_TRY(launch_spade_conv3(imgr, scw, scb, ca.y_hi, ca.y_lo, ca.split_scale, B, Hc, Wc, ACT_LRELU02, s));
+            if (!spade_simt && spade_conv3_tiles(Hc, Wc)) I2V_TRY(launch_spade_conv3(imgr, scw, scb, ca.y_hi, ca.y_lo, ca.split_scale, B, Hc, Wc, ACT_LRELU02, s));
             else I2V_TRY(launch_conv_simt(ca, s));
             I2V_TRY(conv_tc(nm + ".spade.gb", sh, nsh, sgb, nullptr, gb, B, 1, Hc, Wc, 128, 2 * cin, 1, 3, 3, 1, 1, 1, ACT_NONE, 0));
         }

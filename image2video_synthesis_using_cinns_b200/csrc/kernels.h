@@ -17,6 +17,7 @@ struct TuneOptions {
     int tc_pair_stack = 1;   // kw-stacked narrow layers on the CTA-pair kernel: 0 never, 1 frame-layout output only (conv_img), 2 all
     int tc_pair_stages = 0;  // CTA-pair kernel: cap on the ring depth (0 = as many as fit, up to 8)
     int linear_bfly = 1;     // linear kernel: 9-shuffle transpose-reduce (0: 8 x warp_sum)
+    int linear_k64 = 1;      // Linear: thread-per-feature kernel for K = 64, N >= 8192 (0: warp-per-feature kernel everywhere)
     int flow_cluster = 1;    // flow: cluster-resident kernel where eligible (0: cooperative grid-barrier kernel)
     int tc_t2_split = 1;     // per-tap conv kernel: two-frame clips under a temporal 3-tap kernel run as one-frame tiles (skip the padded tap)
     int mod_spade = 1;       // SPADE modulate passes: pipelined fine-grained kernel (0: generic T-walking kernel)
@@ -121,6 +122,7 @@ int launch_resize_bilinear_nchw_to_nhwc(const float* img, float* out, int B, int
                                         cudaStream_t stream);
 // SPADE's Conv2d(3 -> 128, k3, p1) + activation on img [B,H,W,3], result as the fp16 split of split_scale * v
 // (y_hi / y_lo [B,H,W,128]); same bits as launch_conv_simt with y_hi set.  H*W must tile into 64-voxel patches.
+bool spade_conv3_tiles(int H, int W);     // does the plane tile into the kernel's patches?
 int launch_spade_conv3(const float* img, const float* w, const float* bias, __half* y_hi, __half* y_lo, float split_scale, int B,
                        int H, int W, int act, cudaStream_t stream);
 // CLI pre/post-processing on the device (generate_samples.py:36-41,57-62; utils/auxiliaries.py:15-22,53-55)

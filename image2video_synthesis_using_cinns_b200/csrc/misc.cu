@@ -70,22 +70,66 @@ __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x
     }
 }
 
+// Shallow, wide Linears (K = 64, N >= 8192): the flow's hoisted conditioning GEMM (N = n_flows * 2 * 2 * hidden = 40 960 for
+// BAIR) and the decoder's fc (N = 16 * 16 nf).  The warp-per-feature kernel above leaves half its lanes idle at K = 64 and lives
+// for one dependent load -> FMA -> shuffle round per warp: 0.17 ms for 21 MB of traffic.  Here a thread owns a feature, keeps its
+// 64 weights in registers and walks the batch rows, which sit in shared memory and are read as broadcasts: FMA-bound.
+constexpr int LSK_K = 64, LSK_ROWS = 64, LSK_THREADS = 128;
+__global__ void __launch_bounds__(LSK_THREADS) linear_k64_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                 const float* __restrict__ bias, float* __restrict__ y, int B, int N,
+                                                                 int act) {
+    __shared__ float4 xs[LSK_ROWS * (LSK_K / 4)];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int b0 = blockIdx.y * LSK_ROWS;
+    const int nb = B - b0 < LSK_ROWS ? B - b0 : LSK_ROWS;
+    const int nb4 = (nb + 3) & ~3;
+    for (int i = threadIdx.x; i < nb4 * (LSK_K / 4); i += LSK_THREADS)
+        xs[i] = i < nb * (LSK_K / 4) ? __ldg(reinterpret_cast<const float4*>(x + (long long)b0 * LSK_K) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int n = blockIdx.x * LSK_THREADS + threadIdx.x;
+    const int nc = n < N ? n : N - 1;          // spare threads of the last CTA repeat its last feature (no divergent barrier)
+    float4 wr[LSK_K / 4];
+#pragma unroll
+    for (int k = 0; k < LSK_K / 4; ++k) wr[k] = __ldg(reinterpret_cast<const float4*>(w + (long long)nc * LSK_K) + k);
+    const float bn = bias != nullptr ? __ldg(bias + nc) : 0.f;
+    __syncthreads();
+    for (int b = 0; b < nb4; b += 4) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < LSK_K / 4; ++k) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float4 xv = xs[(b + r) * (LSK_K / 4) + k];
+                acc[r] = fmaf(wr[k].x, xv.x, acc[r]); acc[r] = fmaf(wr[k].y, xv.y, acc[r]);
+                acc[r] = fmaf(wr[k].z, xv.z, acc[r]); acc[r] = fmaf(wr[k].w, xv.w, acc[r]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            if (n < N && b + r < nb) y[(long long)(b0 + b + r) * N + n] = apply_act(acc[r] + bn, act);
+    }
+}
+
 // SPADE's first conv (normalization_layer.py:13,21): Conv2d(3 -> 128, k3, p1) + LeakyReLU(0.2) on the resized start frame,
 // written as the fp16 (hi, lo) split the gamma|beta conv consumes.  K = 27: as an implicit GEMM it is all overhead (the
 // SIMT engine ran it at 6 TFLOP/s, 220 us per 64x64 block at B = 64).  Here a lane keeps the 27 x 4 weights of its 4
 // output channels in registers, a warp owns a voxel (128 channels = one 256-byte row of each output word), the CTA's
 // input patch sits in shared memory and is read as broadcasts: 108 FMAs per 27 shared loads, FMA-bound.
 // Summation order = the SIMT engine's (taps outer, input channels inner, one fp32 FMA chain), so both produce the same bits.
-constexpr int SP_TILE = 64;      // voxels per CTA
+// A CTA takes 256 voxels on planes that have them (64 below): the 108 weight loads per lane and the patch staging are paid once
+// per 32 voxels of a warp instead of once per 8 (the kernel holds one CTA per SM and was latency-bound at 64 voxels: 0.20-0.25 ms
+// per 64x64 block at B = 64 for 134 MB of output).
+constexpr int SP_TILE = 256;      // most voxels per CTA
+constexpr int SP_PATCH = 2400;    // floats: the largest (rows + 2) x (cols + 2) x 3 patch of a 256-voxel tile (1 x 256 voxels: 3 x 258 x 3)
+static int spade_tile_voxels(int HW) { return HW >= SP_TILE ? SP_TILE : (HW < 64 ? HW : 64); }
 __global__ void __launch_bounds__(256) spade_conv3_kernel(const float* __restrict__ img, const float* __restrict__ w,
                                                           const float* __restrict__ bias, __half* __restrict__ y_hi,
-                                                          __half* __restrict__ y_lo, float scale, int H, int W, int act) {
-    __shared__ float in_s[3 * (SP_TILE + 2) * 3 + 8];
+                                                          __half* __restrict__ y_lo, float scale, int H, int W, int act, int tile_v) {
+    __shared__ float in_s[SP_PATCH];
     pdl_launch_dependents();
     pdl_wait();
     const int b = blockIdx.y;
     const int HW = H * W;
-    const int tile_v = HW < SP_TILE ? HW : SP_TILE;
     const int v0 = blockIdx.x * tile_v;
     // patch: a segment of one row (W >= tile_v) or tile_v / W whole rows
     const int cols = W >= tile_v ? tile_v : W, rows = tile_v / cols;
@@ -287,20 +331,33 @@ int launch_linear(const float* x, const float* w, const float* bias, float* y, i
                   cudaStream_t stream) {
     I2V_REQUIRE(K % 4 == 0, "linear: K=%d must be a multiple of 4", K);
     ProfScope ps(PROF_OTHER, 2.0 * (double)B * K * N, 4.0 * ((double)K * N + (double)B * (K + N)), stream);
+    if (K == LSK_K && N >= 8192 && tune().linear_k64) {
+        I2V_CHECK_CUDA(launch_k(linear_k64_kernel, dim3(ceil_div(N, LSK_THREADS), ceil_div(B, LSK_ROWS)), dim3(LSK_THREADS), 0, stream, x, w,
+                                bias, y, B, N, act));
+        return 0;
+    }
     const long long warps = (long long)N * ((B + 7) / 8);
     const int bfly = tune().linear_bfly;   // A/B switch (0: 8 x warp_sum)
     I2V_CHECK_CUDA(launch_k(linear_kernel, dim3(ceil_div(warps * 32, 256)), dim3(256), 0, stream, x, w, bias, y, B, K, N, act, bfly));
     return 0;
 }
 
+// planes the dedicated kernel takes: whole tiles that are a segment of one row or a stack of whole rows, patch within SP_PATCH
+bool spade_conv3_tiles(int H, int W) {
+    const int HW = H * W, tv = spade_tile_voxels(HW);
+    if (tv <= 0 || HW % tv != 0 || !(W >= tv ? W % tv == 0 : tv % W == 0)) return false;
+    const int cols = W >= tv ? tv : W, rows = tv / cols;
+    return (rows + 2) * (cols + 2) * 3 <= SP_PATCH;
+}
+
 int launch_spade_conv3(const float* img, const float* w, const float* bias, __half* y_hi, __half* y_lo, float split_scale, int B,
                        int H, int W, int act, cudaStream_t stream) {
-    const int HW = H * W, tile_v = HW < SP_TILE ? HW : SP_TILE;
-    I2V_REQUIRE(HW % tile_v == 0 && (W >= tile_v ? W % tile_v == 0 : tile_v % W == 0) && B < 65536,
-                "spade_conv3: plane %dx%d does not tile into %d-voxel patches", H, W, tile_v);
+    const int HW = H * W, tile_v = spade_tile_voxels(HW);
+    I2V_REQUIRE(spade_conv3_tiles(H, W) && B < 65536, "spade_conv3: plane %dx%d does not tile into %d-voxel patches", H, W, tile_v);
     const double M = (double)B * HW;
     ProfScope ps(PROF_CONV_SIMT, 2.0 * M * 128 * 27, 4.0 * (M * 3 + M * 128 + 27.0 * 128), stream);
-    I2V_CHECK_CUDA(launch_k(spade_conv3_kernel, dim3(HW / tile_v, B), dim3(256), 0, stream, img, w, bias, y_hi, y_lo, split_scale, H, W, act));
+    I2V_CHECK_CUDA(launch_k(spade_conv3_kernel, dim3(HW / tile_v, B), dim3(256), 0, stream, img, w, bias, y_hi, y_lo, split_scale, H, W, act,
+                            tile_v));
     return 0;
 }
 

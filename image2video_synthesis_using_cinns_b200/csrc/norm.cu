@@ -20,11 +20,11 @@ namespace i2v {
 namespace {
 
 constexpr int STATS_THREADS = 256;
-constexpr int STATS_ELEMS_PER_THREAD = 256;   // voxels summed by one thread per channel group
+constexpr int STATS_ELEMS_PER_THREAD = 256;   // most voxels summed by one thread per channel group (fewer on small tensors)
 
 __global__ void __launch_bounds__(STATS_THREADS) channel_stats_kernel(const float* __restrict__ x,
                                                                       double* __restrict__ sums, long long V,
-                                                                      int C, int lanes_c, int rows) {
+                                                                      int C, int lanes_c, int rows, int ept) {
     extern __shared__ double sh[];   // [C][2]
     pdl_launch_dependents();
     pdl_wait();
@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(STATS_THREADS) channel_stats_kernel(const floa
     for (int i = threadIdx.x; i < 2 * C; i += STATS_THREADS) sh[i] = 0.0;
     __syncthreads();
     const int cl = threadIdx.x % lanes_c, rl = threadIdx.x / lanes_c;
-    const long long chunk = (long long)rows * STATS_ELEMS_PER_THREAD;
+    const long long chunk = (long long)rows * ept;
     const long long v0 = (long long)blockIdx.x * chunk;
     const long long v1 = min(V, v0 + chunk);
     const float4* xb = reinterpret_cast<const float4*>(x + (long long)b * V * C);
@@ -270,11 +270,11 @@ __device__ __forceinline__ void split_f16x2(float f0, float f1, __half2& hi, __h
     lo = __floats2half2_rn(f0 - __low2float(hi), f1 - __high2float(hi));
 }
 
-template <bool SECOND, int UT>
+template <bool SECOND, int UT, int TCH>
 __global__ void __launch_bounds__(256, 2) modulate8_spade_kernel(const ModArgs a, int c8_shift, int w_shift) {
     pdl_launch_dependents();
     pdl_wait();
-    constexpr int TCH = 4;                   // host guarantees Ts % TCH == 0 and a power-of-two split scale
+    // TCH source planes in flight (4; 2 for the two-plane tensors of g_0 / g_1); host guarantees Ts % TCH == 0 and a power-of-two scale
     const int C8 = a.C >> 3;
     const int b = blockIdx.y;
     const int Ts = a.T / UT, Hs = a.H / a.uh, Ws = a.W / a.uw;
@@ -456,10 +456,14 @@ int launch_channel_stats(const float* x, double* sums, int B, long long V, int C
     const int C4 = C / 4;
     const int lanes_c = C4 < STATS_THREADS ? C4 : STATS_THREADS;
     const int rows = STATS_THREADS / lanes_c;
-    const long long chunk = (long long)rows * STATS_ELEMS_PER_THREAD;
+    // voxels per thread: 256 on large tensors; small ones (8x8 / 4x4 planes of the decoder, the embedder's deep layers) are cut
+    // finer so that the grid still covers the machine about twice -- a (1, B) grid of 128-voxel serial loops ran at 0.4 TB/s
+    int ept = STATS_ELEMS_PER_THREAD;
+    while (ept > 8 && (long long)B * ((V + (long long)rows * ept - 1) / ((long long)rows * ept)) < 2 * kNumSMs) ept >>= 1;
+    const long long chunk = (long long)rows * ept;
     ProfScope ps(PROF_STATS, 3.0 * (double)B * V * C, 4.0 * (double)B * V * C, stream);
     dim3 grid(ceil_div(V, chunk), B);
-    I2V_CHECK_CUDA(launch_k(channel_stats_kernel, grid, dim3(STATS_THREADS), sizeof(double) * 2 * C, stream, x, sums, V, C, lanes_c, rows));
+    I2V_CHECK_CUDA(launch_k(channel_stats_kernel, grid, dim3(STATS_THREADS), sizeof(double) * 2 * C, stream, x, sums, V, C, lanes_c, rows, ept));
     return 0;
 }
 
@@ -492,13 +496,16 @@ int launch_modulate(const ModArgs& a, cudaStream_t stream) {
         int sexp = 0;
         const bool scale_pow2 = a.split_scale > 0.f && std::frexp(a.split_scale, &sexp) == 0.5f;
         const bool spade_form = a.gb != nullptr && a.coef != nullptr && a.act == ACT_LRELU02 && (a.ut == 1 || a.ut == 2) &&
-                                (a.T / a.ut) % 4 == 0 && scale_pow2 && (a.outb_hi == nullptr || a.ut == 1) && tune().mod_spade != 0;
+                                (a.T / a.ut) % 2 == 0 && scale_pow2 && (a.outb_hi == nullptr || a.ut == 1) && tune().mod_spade != 0;
         if (spade_form) {
             const dim3 grid((per_plane + 255) / 256, a.B);
             const int cs = ilog2(a.C / 8), wsft = ilog2(a.W);
-            if (a.outb_hi != nullptr) I2V_CHECK_CUDA(launch_k(modulate8_spade_kernel<true, 1>, grid, dim3(256), 0, stream, a, cs, wsft));
-            else if (a.ut == 1) I2V_CHECK_CUDA(launch_k(modulate8_spade_kernel<false, 1>, grid, dim3(256), 0, stream, a, cs, wsft));
-            else I2V_CHECK_CUDA(launch_k(modulate8_spade_kernel<false, 2>, grid, dim3(256), 0, stream, a, cs, wsft));
+            const bool four = (a.T / a.ut) % 4 == 0;
+#define I2V_SPADE(SECOND_, UT_, TCH_) I2V_CHECK_CUDA(launch_k(modulate8_spade_kernel<SECOND_, UT_, TCH_>, grid, dim3(256), 0, stream, a, cs, wsft))
+            if (a.outb_hi != nullptr) { if (four) I2V_SPADE(true, 1, 4); else I2V_SPADE(true, 1, 2); }
+            else if (a.ut == 1) { if (four) I2V_SPADE(false, 1, 4); else I2V_SPADE(false, 1, 2); }
+            else { if (four) I2V_SPADE(false, 2, 4); else I2V_SPADE(false, 2, 2); }
+#undef I2V_SPADE
         } else if (a.gb != nullptr || a.outb_hi != nullptr) {
             I2V_CHECK_CUDA(launch_k(modulate8_split_kernel, dim3(bx, a.B), dim3(256), 0, stream, a, ilog2(a.C / 8), ilog2(a.W)));
         } else {

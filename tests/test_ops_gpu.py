@@ -133,7 +133,9 @@ def test_linear_resize_maxpool():
     assert rel_inf(ou.linear(x.cuda(), w.cuda(), None).cpu(), F.linear(x, w)) < 1e-5
     # the shapes launch_linear meets on the path: the flow's conditioning GEMM, AdaIN / fc widths, the control=True embedding
     # width (160), ragged batch and feature counts, the embedder fc and conv_mu|var (deep K, few features)
-    for B_, K_, N_ in ((64, 64, 40960), (7, 128, 1000), (3, 160, 513), (200, 64, 256), (64, 2048, 64), (1, 8192, 128)):
+    # (K = 64 with N >= 8192 takes the thread-per-feature kernel: full / ragged / several 64-row chunks, ragged feature count)
+    for B_, K_, N_ in ((64, 64, 40960), (7, 128, 1000), (3, 160, 513), (200, 64, 256), (64, 2048, 64), (1, 8192, 128),
+                       (6, 64, 40960), (1, 64, 16384), (131, 64, 8200), (70, 64, 8193)):
         x, w, b = torch.randn(B_, K_, generator=g), torch.randn(N_, K_, generator=g) * 0.05, torch.randn(N_, generator=g)
         assert rel_inf(ou.linear(x.cuda(), w.cuda(), b.cuda()).cpu(), F.linear(x.double(), w.double(), b.double())) < 1e-5
     img = torch.rand(3, 3, 64, 64, generator=g) * 2 - 1
@@ -151,6 +153,11 @@ def test_linear_resize_maxpool():
     (32, (8, 16, 16), (1, 1, 1), False, True),     # AdaIN pass
     (16, (2, 8, 8), (1, 1, 1), False, False),      # plain lrelu split ahead of conv_img
     (24, (2, 8, 8), (2, 1, 1), True, True),        # C/8 not a power of two -> generic kernel
+    (64, (8, 16, 16), (2, 1, 1), True, True),      # SPADE kernel: 4 source planes in flight, each written to 2 output planes
+    (32, (2, 8, 8), (1, 1, 1), True, True),        # SPADE kernel: two-plane window
+    (64, (16, 8, 8), (1, 2, 2), True, True),       # SPADE kernel: window refilled three times
+    (32, (3, 8, 8), (1, 1, 1), True, True),        # odd plane count -> generic T-walking kernel
+    (64, (4, 8, 8), (1, 1, 1), False, True),       # map-free pass with coefficients (compile-time lrelu)
 ])
 def test_modulate_split_matches_fp32_pass(C, dims, up, with_gb, with_coef):
     """The fp16 (hi, lo) pair is the exact split of 16 x the fp32 pass: hi = fp16(16 v), lo = fp16(16 v - hi)."""
@@ -166,10 +173,12 @@ def test_modulate_split_matches_fp32_pass(C, dims, up, with_gb, with_coef):
     assert torch.equal(lo, (w16 - w16.half().float()).half())
 
 
-def test_modulate_split_second_result_shares_the_read():
-    """a0 = lrelu(SPADE(x)) and the shortcut's GroupNorm-affine input from one pass over x (BAIR g_4 geometry, scaled down)."""
+@pytest.mark.parametrize("T", [4, 2, 3])
+def test_modulate_split_second_result_shares_the_read(T):
+    """a0 = lrelu(SPADE(x)) and the shortcut's GroupNorm-affine input from one pass over x (BAIR g_4 geometry, scaled down;
+    T = 4 / 2: SPADE kernel with a 4- / 2-plane window, T = 3: generic T-walking kernel)."""
     g = torch.Generator().manual_seed(9)
-    B, T, H, W, C = 2, 4, 16, 16, 64
+    B, H, W, C = 2, 16, 16, 64
     x = torch.randn(B, T, H, W, C, generator=g).cuda()
     coef, coef_b = torch.randn(B, C, 2, generator=g).cuda(), torch.randn(B, C, 2, generator=g).cuda()
     gb = (0.3 * torch.randn(B, H, W, 2 * C, generator=g)).cuda()
