@@ -39,15 +39,17 @@ run_one() {
       echo "bench[$tag] rc=$?" | tee -a $O/status.txt; summ $O/bench_$tag.json $tag ;;
     configs)
       tag=${1:-cfg}
+      # CPU baseline leg (10-30 s of host time) only on the headline config; REFGPU=1 adds the reference-gpu legs (minutes)
       for c in bair_b64 bair_b6 bair_b1 landscape_b32_fast landscape_b32 dtdb_fire_seq24_b32 iper128_transfer_b64; do
-        timeout 900 python bench.py --config $c --steps 5 --warmup 3 > $O/bench_${tag}_$c.json 2> $O/bench_${tag}_$c.err
+        extra="--no-cpu-baseline"; [ $c == bair_b64 ] && extra=""
+        timeout 900 python bench.py --config $c --steps 5 --warmup 3 $extra > $O/bench_${tag}_$c.json 2> $O/bench_${tag}_$c.err
         echo "bench[$c] rc=$?" | tee -a $O/status.txt; summ $O/bench_${tag}_$c.json $c
       done
       for c in bair_b6 bair_b1; do
         timeout 600 python bench.py --config $c --graph 1 --steps 20 --warmup 5 --no-cpu-baseline > $O/bench_${tag}_${c}_graph.json 2> $O/bench_${tag}_${c}_graph.err
         echo "bench[$c graph] rc=$?" | tee -a $O/status.txt; summ $O/bench_${tag}_${c}_graph.json ${c}_graph
       done
-      for c in bair_b64 landscape_b32 iper128_transfer_b64; do
+      [ "${REFGPU:-0}" == "1" ] && for c in bair_b64 landscape_b32 iper128_transfer_b64; do
         timeout 900 python bench.py --impl reference-gpu --config $c --steps 3 --warmup 2 > $O/bench_${tag}_refgpu_$c.json 2> $O/bench_${tag}_refgpu_$c.err
         echo "reference-gpu[$c] rc=$?" | tee -a $O/status.txt; cut -c1-400 $O/bench_${tag}_refgpu_$c.json
       done ;;
