@@ -92,6 +92,8 @@ def parse():
                          "(inline), of uint8 pixels, or EXPERIMENTAL peer-to-peer copies into symmetric memory (p2p: 52.8 ms "
                          "per step at N = 2, but one unexplained hang -- see dist.FrameGather)")
     ap.add_argument("--graph", type=int, default=0, help="1: replay each decoder micro-batch from a CUDA graph")
+    ap.add_argument("--legs", type=int, default=3, help="alternating (device, e2e) timing legs of K steps each; value / e2e = the median "
+                                                        "leg (1 under ncu, where every launch costs ~0.2 s of tool overhead)")
     ap.add_argument("--e2e-probe", action="store_true",
                     help="diagnostic: time device-resident / H2D-only / D2H-only / full end-to-end steps alternately and exit")
     a = ap.parse_args()
@@ -480,16 +482,16 @@ def run_b200(args):
     if sampler:
         sampler.mark()
     # the timed region: K steps back to back, nothing between the launches (the value) ...
-    ms_a, launches, _ = timed(step_device, args.steps)
     # ... the same K steps through host buffers (e2e), then both twice more: A B A B A B.  The board sits at its power cap and the
     # clock wanders by a few % between legs, so `value` and `e2e` are the MEDIAN leg of three (every leg is listed under "ab")
-    ms_e2e_a, _, _ = timed(step_e2e, args.steps)
-    ms_b, _, _ = timed(step_device, args.steps)
-    ms_e2e_b, _, _ = timed(step_e2e, args.steps)
-    ms_c, _, _ = timed(step_device, args.steps)
-    ms_e2e_c, _, _ = timed(step_e2e, args.steps)
-    ms = sorted((ms_a, ms_b, ms_c))[1]
-    ms_e2e = sorted((ms_e2e_a, ms_e2e_b, ms_e2e_c))[1]
+    legs_dev, legs_e2e, launches = [], [], 0
+    for _ in range(max(1, args.legs)):
+        m, n, _ = timed(step_device, args.steps)
+        launches = launches or n
+        legs_dev.append(m)
+        legs_e2e.append(timed(step_e2e, args.steps)[0])
+    ms = sorted(legs_dev)[(len(legs_dev) - 1) // 2]
+    ms_e2e = sorted(legs_e2e)[(len(legs_e2e) - 1) // 2]
     # and K steps with CUDA events around every launch: per-kernel-family device times (the roofline);
     # the events serialise the programmatic-dependent-launch overlap, so this pass is a little slower than the value
     ms_prof, _, prof = timed(step_device, args.steps, profile=True)
@@ -554,8 +556,8 @@ def run_b200(args):
                     "d2h_bytes_per_step": world * out_numel * 4,
                     "note": "H2D of the step's inputs on the compute stream; D2H of its frames on a copy stream behind the next step's "
                             "kernels (dist.HostFrameSink), all copies complete inside the timed region"},
-            "ab": {"device_ms_per_step": [ms_a / args.steps, ms_b / args.steps, ms_c / args.steps],
-                   "e2e_ms_per_step": [ms_e2e_a / args.steps, ms_e2e_b / args.steps, ms_e2e_c / args.steps],
+            "ab": {"device_ms_per_step": [m / args.steps for m in legs_dev],
+                   "e2e_ms_per_step": [m / args.steps for m in legs_e2e],
                    "note": "legs of K steps each, alternating; value / e2e = the median leg"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
         }

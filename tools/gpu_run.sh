@@ -62,12 +62,12 @@ run_one() {
     ncu-list)
       tag=${1:-n1}; [ $# -gt 0 ] && shift
       timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $O/launches_$tag.csv \
-        python bench.py --steps 1 --warmup 1 --no-cpu-baseline "$@" > $O/ncu_list_$tag.log 2>&1
+        python bench.py --steps 1 --warmup 1 --legs 1 --no-cpu-baseline "$@" > $O/ncu_list_$tag.log 2>&1
       echo "ncu-list[$tag] rc=$?" | tee -a $O/status.txt; python tools/summarise_launches.py $O/launches_$tag.csv > $O/launches_${tag}_summary.csv; head -30 $O/launches_${tag}_summary.csv ;;
     ncu-full)
       tag=$1; re=$2; skip=$3; cnt=$4; shift 4
       timeout 1800 ncu --set full --clock-control none --import-source on -k regex:$re --launch-skip $skip -c $cnt -f -o $O/ncu_$tag \
-        python bench.py --steps 1 --warmup 1 --no-cpu-baseline "$@" > $O/ncu_full_$tag.log 2>&1
+        python bench.py --steps 1 --warmup 1 --legs 1 --no-cpu-baseline "$@" > $O/ncu_full_$tag.log 2>&1
       echo "ncu-full[$tag] rc=$?" | tee -a $O/status.txt
       ncu -i $O/ncu_$tag.ncu-rep --page raw --csv > $O/ncu_${tag}_raw.csv 2>/dev/null; python tools/summarise_ncu.py $O/ncu_${tag}_raw.csv > $O/ncu_${tag}_summary.txt
       # gpurun merges at most 64 MiB back: the report itself (tens of MB) stays on the box unless KEEP_NCU_REP=1
