@@ -191,3 +191,64 @@ def test_pack_flow_chunks_is_the_per_cta_k_major_stream():
     # geometries the cluster kernel does not take keep the cooperative kernel's tensors only
     t128, _, _ = loader.pack_flow(synthetic.flow_state_dict(gen, 64, 64, 128, 2, 2, False), 2, 64, 64, 128, 2, False)
     assert "wpack" not in t128
+
+
+def test_pack_encoder3d_adds_tensor_core_split():
+    """Every 3x3x3 conv of the 3-D encoder's blocks carries the split fp16 copy (csrc/api.cu, encoder3d_run picks the engine per
+    conv); the Cin = 3 stem does not; hi + lo reproduces the fp32 weights to fp32 grade."""
+    from image2video_synthesis_using_cinns_b200.config import DATASETS
+    gen = torch.Generator().manual_seed(8)
+    e = DATASETS["bair"]["enc"]
+    sd = synthetic.encoder3d_state_dict(gen, [64, 32, 32, 64, 64], e["stride_s"])
+    t = loader.pack_encoder3d(sd)
+    assert "conv1.wh" not in t
+    for l in range(4):
+        for b in range(2):
+            for c in ("conv1", "conv2"):
+                k = f"layer.{l}.{b}.{c}"
+                w, hi, lo, ws = t[k + ".w"], t[k + ".wh"], t[k + ".wl"], t[k + ".ws"]
+                assert hi.shape == w.shape and hi.dtype == torch.float16 and w.shape[0] == 27
+                s = 1.0 / (loader.ACT_SPLIT_SCALE * float(ws))
+                assert ((hi.double() + lo.double()) / s - w.double()).abs().max() / w.abs().max() < 2 ** -21
+            assert (f"layer.{l}.{b}.ds.w" in t) == (f"layer.{l}.{b}.ds.wh" in t)
+    assert any(k.endswith("ds.wh") for k in t)
+    assert not any(k.endswith(".wh") for k in loader.pack_encoder3d(sd, tensor_core=False))
+
+
+def test_pack_decoder_phase_weights_cover_every_temporally_upsampled_block():
+    """conv_0 of g_0, g_1, g_2 (always x2 in time, decoder.py:102-108) and of g_3 / g_4 when the config upsamples them carries the
+    phase-combined weights [2 phases x 2 taps x 9, Cout, Cin]: out[2j] = W0 a[j-1] + (W1+W2) a[j], out[2j+1] = (W0+W1) a[j] + W2 a[j+1]."""
+    gen = torch.Generator().manual_seed(9)
+    sd = synthetic.decoder_state_dict(gen, 16)
+    t, _ = loader.pack_decoder(sd, 16, engine=1, upsample_t=(2, 1), upsample_s=(2, 1))
+    assert {k.split(".")[0] for k in t if k.endswith("conv_0.wph")} == {"g_0", "g_1", "g_2", "g_3"}
+    t0, _ = loader.pack_decoder(sd, 16)                       # fp32 taps of the same checkpoint
+    w = t0["g_0.conv_0.w"].double().reshape(3, 9, *t0["g_0.conv_0.w"].shape[1:])
+    want = torch.stack((w[0], w[1] + w[2], w[0] + w[1], w[2])).reshape(36, *w.shape[2:])
+    hi, lo, ws = t["g_0.conv_0.wph"], t["g_0.conv_0.wpl"], t["g_0.conv_0.wps"]
+    s = 1.0 / (loader.ACT_SPLIT_SCALE * float(ws))
+    assert hi.shape == want.shape
+    assert ((hi.double() + lo.double()) / s - want).abs().max() / want.abs().max() < 2 ** -21
+    # a clip of identical frame pairs through the 3-tap conv == the 2-tap phase form on the half-rate clip
+    a = torch.randn(1, w.shape[3], 3, 4, 4, generator=gen, dtype=torch.float64)
+    w5 = t0["g_0.conv_0.w"].double().reshape(3, 3, 3, *w.shape[2:]).permute(3, 4, 0, 1, 2)
+    full = torch.nn.functional.conv3d(a.repeat_interleave(2, dim=2), w5, padding=1)
+    wp = want.reshape(2, 2, 3, 3, *w.shape[2:]).permute(0, 4, 5, 1, 2, 3)           # [phase][Cout][Cin][tap][kh][kw]
+    ap = torch.nn.functional.pad(a, (1, 1, 1, 1, 1, 1))
+    for p in range(2):
+        got = torch.nn.functional.conv3d(ap[:, :, p:p + a.shape[2] + 1], wp[p])     # source planes j - 1 + p + q, q = 0, 1
+        assert torch.allclose(got, full[:, :, p::2], atol=1e-10)
+
+
+def test_bench_arguments_default_to_the_headline_config(monkeypatch):
+    import importlib
+    import sys
+    sys.path.insert(0, ROOT)
+    bench = importlib.import_module("bench")
+    monkeypatch.setattr(sys, "argv", ["bench.py"])
+    a = bench.parse()
+    assert (a.gpus, a.config, a.dataset, a.batch, a.seq_length, a.impl, a.legs) == (1, "bair_b64", "bair", 64, 16, "b200", 3)
+    assert a.steps >= 1 and a.warmup >= 3 and not a.e2e_probe
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--config", "iper128_transfer_b64", "--legs", "1"])
+    a = bench.parse()
+    assert a.mode == "transfer" and a.dataset == "iper128" and a.legs == 1
