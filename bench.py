@@ -528,8 +528,11 @@ def run_b200(args):
         arith = {1: "fp32-parity mode issues 3 fp16 MMAs per algorithmic MAC (hi*hi+hi*lo+lo*hi) and the phase form "
                     "skips 1/3 of conv_0's taps: tensor-pipe FLOP/s = achieved x 3 x (issued/nominal taps)",
                  2: "single fp16 product per MAC (reduced-precision decoder)", 0: "fp32 FFMA engine (no tensor cores)"}[args.conv_engine]
+        kernel_names = {"conv_tc_halo": "conv_tc_pair_kernel + conv_tc_halo_kernel (the 256-voxel-tile family: CTA pairs with "
+                                        "tcgen05.mma.cta_group::2 where eligible, single-CTA halo tiles otherwise)",
+                        "conv_tc_pertap": "conv_tc_kernel (per-tap tiles)", "conv_simt": "conv_simt_kernel (fp32 FFMA engine)"}
         roofline = {"bound": "tensor",
-                    "kernel": f"{dom}_kernel: all its launches in the timed steps (decoder Conv3d/Conv2d stack), algorithmic FLOPs = "
+                    "kernel": f"{kernel_names[dom]}: all its launches in the timed steps (decoder Conv3d/Conv2d stack), algorithmic FLOPs = "
                               "2*taps*Cin*Cout per output voxel (reference's nominal count, SURVEY 8d) / summed CUDA-event time",
                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                     "peak_source": peak_src, "note": arith,
