@@ -248,15 +248,6 @@ __global__ void __launch_bounds__(256) modulate8_split_kernel(const ModArgs a, i
     }
 }
 
-// SPADE passes of the decoder (coefficients + gamma|beta maps + LeakyReLU(0.2), the only form decoder_run issues for the
-// T-walking kernel): the same arithmetic as modulate8_split_kernel, restructured around the memory system.  ncu on the generic
-// kernel (profiles/r02_ncu_modulate_summary.txt): 128 registers, 16 warps per SM, and -- because the activation switch and the
-// runtime `ut` loop keep branches between a plane's loads and its stores -- only ONE plane (32 bytes) in flight per thread:
-// long-scoreboard-bound at 3.3 TB/s.  Here the activation and the temporal factor are compile-time, a thread owns one
-// (h, w, 8-channel) position (fine-grained grid: no 8.2-wave tail), and a rotating window keeps TCH source planes (128 bytes)
-// in flight per thread: plane ts + TCH is requested the moment plane ts has been written out.  Instruction diet (the generic
-// kernel spends ~210 instructions per plane and thread, enough to be issue-bound at 5 TB/s): power-of-two split scale folded
-// into gamma / beta, lrelu as max(v, 0.2 v), NaN-propagating two-instruction clamp, packed conversions, pointer increments.
 // NaN-propagating clamp to the fp16 range (same values as sat_f16: NaN stays NaN) in two FMNMX instead of compare + select + FMNMX
 __device__ __forceinline__ float sat_f16_fast(float f) {
     float r;
@@ -270,6 +261,15 @@ __device__ __forceinline__ void split_f16x2(float f0, float f1, __half2& hi, __h
     lo = __floats2half2_rn(f0 - __low2float(hi), f1 - __high2float(hi));
 }
 
+// SPADE passes of the decoder (coefficients + gamma|beta maps + LeakyReLU(0.2), the only form decoder_run issues for the
+// T-walking kernel): the same arithmetic as modulate8_split_kernel, restructured around the memory system.  ncu on the generic
+// kernel (profiles/r02_ncu_modulate_summary.txt): 128 registers, 16 warps per SM, and -- because the activation switch and the
+// runtime `ut` loop keep branches between a plane's loads and its stores -- only ONE plane (32 bytes) in flight per thread:
+// long-scoreboard-bound at 3.3 TB/s.  Here the activation and the temporal factor are compile-time, a thread owns one
+// (h, w, 8-channel) position (fine-grained grid: no 8.2-wave tail), and a rotating window keeps TCH source planes (128 bytes)
+// in flight per thread: plane ts + TCH is requested the moment plane ts has been written out.  Instruction diet (the generic
+// kernel spends ~210 instructions per plane and thread, enough to be issue-bound at 5 TB/s): power-of-two split scale folded
+// into gamma / beta, lrelu as max(v, 0.2 v), NaN-propagating two-instruction clamp, packed conversions, pointer increments.
 template <bool SECOND, int UT, int TCH>
 __global__ void __launch_bounds__(256, 2) modulate8_spade_kernel(const ModArgs a, int c8_shift, int w_shift) {
     pdl_launch_dependents();
